@@ -1,0 +1,252 @@
+/*
+ * b200kkt.h -- C ABI of the B200-native KKT hot path (assembly -> LDL^T + inertia -> solve).
+ *
+ * This is the drop-in boundary a MadNLP.jl maintainer binds with `ccall` (see INTEGRATION.md
+ * and madnlp.jl_b200/julia/B200KKT.jl).  Plain pointers and sizes only; no exceptions cross
+ * the boundary: every entry point returns a status code (B2_OK == 0) and b2_last_error()
+ * gives the message.  All matrix values are fp64; all sparse indices are 0-based int32
+ * (the reference uses 1-based Int32: src/KKT/Sparse/augmented.jl:20, condensed.jl:11,17);
+ * COO->CSC maps are int64 like the reference's Vector{Int} (src/matrixtools.jl:91).
+ *
+ * Pointer suffix convention:  *_h = host memory,  *_d = device memory (cuda:current).
+ * `stream` arguments are a cudaStream_t passed as void* (NULL = legacy default stream).
+ *
+ * Reference interface each group replaces (paths relative to MadNLP.jl @ v0.10.1):
+ *   b2_*  sparse solver  : AbstractLinearSolver surface, src/LinearSolvers/linearsolvers.jl:13-95,
+ *                          as implemented by CUDSSSolver lib/MadNLPGPU/ext/MadNLPGPUCUDAExt/cudss.jl:88-214
+ *                          and Ma97Solver lib/MadNLPHSL/src/ma97.jl:29-115.
+ *   b2d_* dense solver   : LapackCUDASolver/LapackCPUSolver, src/LinearSolvers/lapack.jl:164-172,
+ *                          lib/MadNLPGPU/ext/MadNLPGPUCUDAExt/cusolver.jl:150-187.
+ *   b2_coo_to_csc, b2_transfer*          : src/matrixtools.jl:55-95, lib/MadNLPGPU/src/KKT/gpu_sparse.jl:260-302,
+ *                                          kernels_sparse.jl:161-167.
+ *   b2_condensed_*                       : src/KKT/Sparse/condensed.jl:201-366, gpu_sparse.jl:308-340.
+ *   b2d_condensed_assemble               : src/KKT/Dense/condensed.jl:120-186, kernels_dense.jl:81-119.
+ *   b2_set_aug_diagonal .. b2_kkt_mul_*  : src/IPM/kernels.jl:4-27,161-204, src/IPM/factorization.jl:41-46,
+ *                                          143-167,190-237,303-324, src/KKT/KKTsystem.jl:222-226.
+ */
+#ifndef B200KKT_H
+#define B200KKT_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2_OK                 0
+#define B2_ERR_INVALID        1   /* bad argument */
+#define B2_ERR_CUDA           2   /* CUDA runtime error (message in b2_last_error) */
+#define B2_ERR_SYMBOLIC       3   /* analysis failed         (SymbolicException,      linearsolvers.jl:133) */
+#define B2_ERR_FACTORIZATION  4   /* numeric failure         (FactorizationException, linearsolvers.jl:134) */
+#define B2_ERR_SOLVE          5   /* solve before factorize  (SolveException,         linearsolvers.jl:135) */
+#define B2_ERR_NO_DEVICE      6   /* no CUDA device: the product path has no CPU fallback */
+
+#define B2_ORDER_METIS_ND 0   /* nested dissection (METIS_NodeND, statically linked)        */
+#define B2_ORDER_MINDEG   1   /* built-in minimum-degree                                    */
+#define B2_ORDER_NATURAL  2   /* identity                                                   */
+#define B2_ORDER_USER     3   /* caller-supplied permutation (cf. cudss_perm, cudss.jl:7)   */
+
+const char* b2_last_error(void);
+int b2_version(void);
+/* number of visible CUDA devices; B2_ERR_NO_DEVICE if none */
+int b2_device_count(int* count);
+
+/* ------------------------------------------------------------------ options */
+typedef struct b2_options {
+    int32_t ordering;        /* B2_ORDER_*                                              */
+    int32_t nemin;           /* supernode amalgamation: always merge while width <= nemin */
+    double  relax_zeros;     /* additionally merge when explicit-zero fraction below this */
+    double  pivot_eps;       /* |d| < pivot_eps -> static perturbation, counted as "zero"  */
+    int32_t use_cuda_graph;  /* 1: capture factor/solve launch sequences into CUDA graphs  */
+    int32_t small_front_max; /* fronts with order <= this run in the fused shared-memory kernel */
+    int32_t n_parts;         /* multi-GPU: number of ranks sharing the elimination tree (1 = off) */
+    int32_t part_rank;       /* multi-GPU: this rank                                        */
+    int32_t reserved[8];
+} b2_options;
+
+int b2_options_default(b2_options* opt);
+
+/* ------------------------------------------------------------------ sparse LDL^T */
+typedef struct b2_solver b2_solver;
+
+typedef struct b2_stats {
+    int64_t n, nnz_a, nnz_l, flops;        /* nnz(L) incl. diagonal and explicit zeros; flops of one factorisation */
+    int64_t n_supernodes, n_levels;
+    int64_t max_front, n_small_fronts, n_big_fronts;
+    int64_t factor_bytes, workspace_bytes; /* device memory held */
+    int64_t sep_rows;                      /* multi-GPU: order of the shared (replicated) top tree */
+    int64_t n_factor_launches, n_solve_launches;
+    int64_t n_perturbed;                   /* pivots perturbed in the last factorisation */
+} b2_stats;
+
+/* Analysis (ordering + symbolic factorisation); `nzval_d` is KEPT BY REFERENCE and re-read by
+ * every b2_factorize -- the reference's aliasing contract (cudss.jl:154-158, ma97.jl:72-88).
+ * colptr_h[n+1], rowval_h[nnz]: lower-triangular CSC pattern on the host, 0-based.
+ * user_perm_h: n entries (perm[new]=old) when ordering == B2_ORDER_USER, else NULL. */
+int b2_create(int32_t n, int64_t nnz, const int32_t* colptr_h, const int32_t* rowval_h,
+              const double* nzval_d, const b2_options* opt, const int32_t* user_perm_h,
+              b2_solver** out);
+/* analysis only (no device state): for tooling/tests on machines without a GPU; every numeric entry point
+ * returns B2_ERR_INVALID on such a handle -- it is NOT a compute fallback. */
+int b2_create_symbolic_only(int32_t n, int64_t nnz, const int32_t* colptr_h, const int32_t* rowval_h,
+                            const b2_options* opt, const int32_t* user_perm_h, b2_solver** out);
+int b2_destroy(b2_solver* s);
+/* re-point the aliased value buffer (same pattern) */
+int b2_set_values_ptr(b2_solver* s, const double* nzval_d);
+/* numeric factorisation of the CURRENT values; asynchronous on `stream` */
+int b2_factorize(b2_solver* s, void* stream);
+/* (num_pos, num_zero, num_neg) in the reference's code order (src/IPM/solver.jl:626);
+ * synchronises `stream`.  Perturbed pivots are reported as zeros (cf. mumps.jl:248-250). */
+int b2_inertia(b2_solver* s, int64_t* num_pos, int64_t* num_zero, int64_t* num_neg, void* stream);
+/* in-place x <- K^{-1} x, nrhs columns of length n (ld = n); asynchronous on `stream` */
+int b2_solve(b2_solver* s, double* x_d, int32_t nrhs, void* stream);
+/* raise robustness after a failed refinement (improve!, linearsolvers.jl / ma97.jl:103-111);
+ * *changed = 1 if something changed and a re-factorisation is worthwhile */
+int b2_improve(b2_solver* s, int32_t* changed);
+int b2_get_stats(b2_solver* s, b2_stats* st);
+/* copy out the fill-reducing permutation (perm[new]=old), n entries, host */
+int b2_get_perm(b2_solver* s, int32_t* perm_h);
+
+/* Multi-GPU (subtree-to-rank) support.  With opt.n_parts = P > 1 every rank analyses the same
+ * pattern; rank r factors the subtrees it owns plus (replicated) the shared top tree.  The only
+ * exchange is the sum of the subtree roots' update (Schur-complement) blocks, which the host
+ * reduces with NCCL:   b2_factorize_local -> allreduce(b2_exchange_buffer) -> b2_factorize_top.
+ * b2_solve_* mirror this for the triangular solves (the exchange buffer then holds vectors). */
+int b2_exchange_buffer(b2_solver* s, double** buf_d, int64_t* n_factor_doubles, int64_t* n_solve_doubles);
+int b2_exchange_vector(b2_solver* s, double** buf_d, int64_t* n_doubles);   /* forward-solve contributions */
+/* inertia split for the multi-GPU reduction: counts of the owned subtrees and of the replicated top tree */
+int b2_inertia_parts(b2_solver* s, int64_t* local_neg, int64_t* local_zero, int64_t* top_neg, int64_t* top_zero, void* stream);
+int b2_factorize_local(b2_solver* s, void* stream);
+int b2_factorize_top(b2_solver* s, void* stream);
+int b2_solve_fwd_local(b2_solver* s, double* x_d, void* stream);
+int b2_solve_top(b2_solver* s, double* x_d, void* stream);      /* after allreduce of the exchange buffer */
+int b2_solve_bwd_local(b2_solver* s, double* x_d, void* stream); /* leaves x complete only on owned + top rows */
+int b2_owned_mask(b2_solver* s, uint8_t* owned_h);               /* n entries: 1 if this rank finalises x[i] */
+
+/* Debug/test export of the symbolic structure (host arrays, caller-allocated; pass NULL to query sizes):
+ * used by tests/ to replay the multifrontal arithmetic in numpy on machines without a GPU. */
+typedef struct b2_symbolic_sizes {
+    int64_t n, n_supernodes, n_rows, n_children, n_rel, n_amap, n_levels, lval_size, cb_size;
+} b2_symbolic_sizes;
+int b2_symbolic_query(b2_solver* s, b2_symbolic_sizes* sz);
+int b2_symbolic_export(b2_solver* s, int32_t* perm, int32_t* sn_first, int32_t* sn_parent, int32_t* sn_level,
+                       int64_t* rows_ptr, int32_t* rows, int64_t* lp_off, int64_t* cb_off,
+                       int64_t* rel_ptr, int32_t* rel, int64_t* amap_ptr, int64_t* amap_src, int64_t* amap_dst);
+int b2_symbolic_owner(b2_solver* s, int32_t* owner);   /* n_supernodes entries: rank, or -1 for the shared top tree */
+
+/* ------------------------------------------------------------------ dense LDL^T */
+typedef struct b2d_solver b2d_solver;
+/* A_d: N x N column-major (ld = lda) on the device, lower triangle read, KEPT BY REFERENCE
+ * (lapack.jl:40); the factor is written to an internal buffer (lapack_common.jl:28). */
+int b2d_create(int32_t N, int32_t lda, const double* A_d, const b2_options* opt, b2d_solver** out);
+int b2d_destroy(b2d_solver* s);
+int b2d_factorize(b2d_solver* s, void* stream);
+int b2d_inertia(b2d_solver* s, int64_t* num_pos, int64_t* num_zero, int64_t* num_neg, void* stream);
+int b2d_solve(b2d_solver* s, double* x_d, int32_t nrhs, void* stream);
+
+/* ------------------------------------------------------------------ assembly: COO -> CSC */
+/* Host, one-time: CSC pattern of a COO matrix with duplicate merging and the COO->CSC map
+ * (src/matrixtools.jl:55-95).  colptr_h[n+1]; rowval_h capacity nnz_coo; map_h[nnz_coo]. */
+int b2_coo_to_csc(int32_t m, int32_t n, int64_t nnz_coo, const int32_t* I_h, const int32_t* J_h,
+                  int32_t* colptr_h, int32_t* rowval_h, int64_t* map_h, int64_t* nnz_csc);
+
+/* Device plan for  dst .= 0; dst[map[k]] += V[k]  (src/matrixtools.jl:79-88) as a race-free,
+ * deterministic segmented gather: one thread per destination slot summing its sources in COO
+ * order -- bit-identical to the reference's sequential CPU loop. */
+typedef struct b2_transfer_plan b2_transfer_plan;
+int b2_transfer_plan_create(int64_t nnz_coo, int64_t nnz_csc, const int64_t* map_h, b2_transfer_plan** out);
+int b2_transfer_plan_destroy(b2_transfer_plan* p);
+int b2_transfer(b2_transfer_plan* p, double* dst_nz_d, const double* V_d, void* stream);
+
+/* ------------------------------------------------------------------ assembly: sparse condensed */
+typedef struct b2_condensed_plan b2_condensed_plan;
+/* Symbolic (host, one-time): pattern of tril(H) U diag U tril(Jt*Jt') and the dptr/hptr/jptr maps
+ * (src/KKT/Sparse/condensed.jl:201-301).  H: n x n lower CSC; Jt: n x m CSC. */
+int b2_condensed_symbolic(int32_t n, int32_t m,
+                          const int32_t* H_colptr_h, const int32_t* H_rowval_h,
+                          const int32_t* Jt_colptr_h, const int32_t* Jt_rowval_h,
+                          b2_condensed_plan** out, int64_t* nnz_aug);
+int b2_condensed_pattern(b2_condensed_plan* p, int32_t* colptr_h, int32_t* rowval_h);
+int b2_condensed_plan_sizes(b2_condensed_plan* p, int64_t* n_dptr, int64_t* n_hptr, int64_t* n_jptr);
+int b2_condensed_plan_destroy(b2_condensed_plan* p);
+/* Numeric (device, every iteration), two launches instead of the reference's fill! + 3 kernels
+ * (src/KKT/Sparse/condensed.jl:328-366, gpu_sparse.jl:308-340):
+ *   diag_buffer = Ss ./ (1 - Sd .* Ss)   with Ss = pr_diag[n:n+m], Sd = du_diag
+ *   nz[i] = sum H.nz[..] + pr_diag[..] + sum diag_buffer[c]*Jt.nz[k]*Jt.nz[l]
+ * summed per slot in the reference's order (hess, diag, triples) without FMA contraction. */
+int b2_condensed_assemble(b2_condensed_plan* p, double* aug_nz_d, const double* pr_diag_d,
+                          const double* du_diag_d, const double* H_nz_d, const double* Jt_nz_d,
+                          double* diag_buffer_d, void* stream);
+
+/* ------------------------------------------------------------------ assembly: dense condensed */
+/* src/KKT/Dense/condensed.jl:157-186.  hess n x n (ld n), jac m x n (ld m), aug N x N (ld N), N = n + n_eq.
+ * Only the LOWER triangle of aug is written (what dsytrf('L') and b2d_* read), plus the equality rows. */
+int b2d_condensed_assemble(int32_t n, int32_t m, int32_t ns, int32_t n_eq,
+                           const int64_t* ind_ineq_d, const int64_t* ind_eq_d,
+                           const double* hess_d, const double* jac_d,
+                           const double* pr_diag_d, const double* du_diag_d,
+                           double* diag_buffer_d, double* aug_d, void* stream);
+
+/* ------------------------------------------------------------------ IPM vector kernels */
+/* Index sets ind_lb / ind_ub over the primal vector (x,s) (src/Callbacks/nlpmodels.jl:369-406), uploaded once
+ * together with their inverse maps so that every kernel below is a single race-free pass over n_tot. */
+typedef struct b2_bounds b2_bounds;
+int b2_bounds_create(int64_t n_tot, int64_t nlb, int64_t nub, const int64_t* ind_lb_h, const int64_t* ind_ub_h,
+                     b2_bounds** out);
+int b2_bounds_destroy(b2_bounds* b);
+
+/* pr_diag = reg; pr_diag[ind_lb] -= l_lower./l_diag; pr_diag[ind_ub] -= u_lower./u_diag  (IPM/kernels.jl:22-27) */
+int b2_set_aug_diagonal(b2_bounds* b, const double* reg_d, const double* l_lower_d, const double* l_diag_d,
+                        const double* u_lower_d, const double* u_diag_d, double* pr_diag_d, void* stream);
+/* reg += dw; pr_diag += dw; du_diag -= dc   (KKTsystem.jl:222-226) */
+int b2_regularize_diagonal(int64_t n_tot, int64_t m, double dw, double dc, double* reg_d, double* pr_diag_d,
+                           double* du_diag_d, void* stream);
+/* reduce_rhs! / finish_aug_solve!  (IPM/kernels.jl:182-204) on an UnreducedKKTVector buffer
+ * w = [xp(n_tot) | y(m) | zl(nlb) | zu(nub)]  (KKT/rhs.jl:101-117) */
+int b2_reduce_rhs(b2_bounds* b, int64_t m, const double* l_diag_d, const double* u_diag_d, double* w_d, void* stream);
+int b2_finish_aug_solve(b2_bounds* b, int64_t m, const double* l_lower_d, const double* u_lower_d,
+                        const double* l_diag_d, const double* u_diag_d, double* w_d, void* stream);
+
+/* CSC sparse mat-vec helpers:  y = alpha*A*x + beta*y  /  y = alpha*A'*x + beta*y  and the symmetric-lower
+ * product y = alpha*(L + L' - diag(L))*x + beta*y; gather (row-parallel) forms built once per pattern --
+ * replaces the cuSPARSE SpMV calls of lib/MadNLPGPU/src/KKT/gpu_sparse.jl:14-65. */
+typedef struct b2_spmv_plan b2_spmv_plan;
+int b2_spmv_plan_create(int32_t nrow, int32_t ncol, const int32_t* colptr_h, const int32_t* rowval_h, b2_spmv_plan** out);
+int b2_spmv_plan_destroy(b2_spmv_plan* p);
+int b2_spmv_n(b2_spmv_plan* p, const double* nz_d, const double* x_d, double* y_d, double alpha, double beta, void* stream);
+int b2_spmv_t(b2_spmv_plan* p, const double* nz_d, const double* x_d, double* y_d, double alpha, double beta, void* stream);
+int b2_spmv_symlower(b2_spmv_plan* p, const double* nz_d, const double* x_d, double* y_d, double alpha, double beta, void* stream);
+
+/* _kktmul!  (IPM/kernels.jl:161-180) on UnreducedKKTVector buffers w, x */
+int b2_kktmul(b2_bounds* b, int64_t m, const double* reg_d, const double* du_diag_d,
+              const double* l_lower_d, const double* u_lower_d, const double* l_diag_d, const double* u_diag_d,
+              double alpha, double beta, const double* x_d, double* w_d, void* stream);
+
+/* solve_kkt!(::SparseCondensedKKTSystem) pre/post stages around b2_solve (IPM/factorization.jl:143-167), n = nvar, m = ncon:
+ *   pre : reduce_rhs!; buffer = D.*(wz + ws./Ss); wx += Jt*buffer
+ *   post: buffer2 = Jt'*wx; wz = -buffer + D.*buffer2; ws = (ws+wz)./Ss; finish_aug_solve! */
+int b2_condensed_solve_pre(b2_bounds* b, b2_spmv_plan* jt, int64_t n, int64_t m,
+                           const double* jt_nz_d, const double* pr_diag_d, const double* diag_buffer_d,
+                           const double* l_diag_d, const double* u_diag_d, double* buffer_d, double* w_d, void* stream);
+int b2_condensed_solve_post(b2_bounds* b, b2_spmv_plan* jt, int64_t n, int64_t m,
+                            const double* jt_nz_d, const double* pr_diag_d, const double* diag_buffer_d,
+                            const double* l_lower_d, const double* u_lower_d, const double* l_diag_d, const double* u_diag_d,
+                            const double* buffer_d, double* w_d, void* stream);
+/* mul!(w, ::SparseCondensedKKTSystem, x, alpha, beta)  (IPM/factorization.jl:303-324) incl. _kktmul! */
+int b2_condensed_kkt_mul(b2_bounds* b, b2_spmv_plan* hess, b2_spmv_plan* jt, int64_t n, int64_t m,
+                         const double* hess_nz_d, const double* jt_nz_d,
+                         const double* reg_d, const double* du_diag_d, const double* l_lower_d, const double* u_lower_d,
+                         const double* l_diag_d, const double* u_diag_d, double alpha, double beta,
+                         const double* x_d, double* w_d, void* stream);
+
+/* infinity norm of a device vector into a device scalar (no host sync) */
+int b2_norm_inf(int64_t n, const double* x_d, double* out_d, void* stream);
+/* y += a*x ; y = x ; x = v */
+int b2_axpy(int64_t n, double a, const double* x_d, double* y_d, void* stream);
+int b2_copy(int64_t n, const double* x_d, double* y_d, void* stream);
+int b2_fill(int64_t n, double v, double* x_d, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200KKT_H */

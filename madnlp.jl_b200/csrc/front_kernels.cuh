@@ -1,0 +1,363 @@
+// Device kernels of the supernodal multifrontal LDL^T (numeric phase).
+//
+// Data model (see analysis.hpp): one dense front per supernode, order f = w + r.
+//   factor panel   L + lp_off : f x w column-major (ld = f).  On exit the strict lower part holds the unit-lower
+//                               factor (L11 over L21), the diagonal holds D, the strict upper part of the w x w block
+//                               holds U = D*L' (scratch).
+//   update block   ws + cb_off: r x r column-major (ld = r), lower triangle = Schur complement passed to the parent.
+// Fronts are processed level by level (children strictly below parents); inside a level every front is
+// independent.  Extend-add is a PULL by the parent over its children in ascending child id, so the summation
+// order -- and therefore every bit of the factor -- is deterministic.
+//
+// Three execution classes per level:
+//   S/M  whole front resident in shared memory, one CTA per front (k_front_smem)   -- f <= small_front_max
+//   B    front in HBM, blocked right-looking LDL^T across many CTAs (k_big_*)      -- tensor-pipe (DMMA) update
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace b2 {
+
+struct FrontDesc {
+    int32_t col0, w, f, nchild;
+    int32_t child_off, amap_cnt;
+    int64_t rows_off, lp_off, cb_off, rel_off, amap_off;
+};
+static_assert(sizeof(FrontDesc) == 64, "FrontDesc must be 64 bytes");
+
+struct FactorArgs {
+    const FrontDesc* desc;
+    const int32_t* child_idx;
+    const int32_t* rel;
+    const int32_t* amap_src;
+    const int32_t* amap_dst;
+    const double* A;      // caller's CSC values (aliased)
+    double* L;            // factor panels
+    double* ws;           // update blocks
+    double* dvec;         // D, permuted order
+    int32_t* counters;    // [0] = #negative pivots, [1] = #perturbed pivots
+    double eps;
+};
+
+// ----------------------------------------------------------------------------------------------------------
+// S/M class: fused assemble + factor + store with the whole front in shared memory.
+// ----------------------------------------------------------------------------------------------------------
+template <int NT>
+__global__ void __launch_bounds__(NT) k_front_smem(FactorArgs a, const int32_t* __restrict__ list) {
+    extern __shared__ double F[];
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = NT / 32;
+    const int s = list[blockIdx.x];
+    const FrontDesc d = a.desc[s];
+    const int f = d.f, w = d.w, r = f - w;
+    const int ff = f * f;
+
+    for (int i = tid; i < ff; i += NT) F[i] = 0.0;
+    __syncthreads();
+    // original matrix entries (each lands in a distinct slot of the panel part)
+    {
+        const int32_t* src = a.amap_src + d.amap_off;
+        const int32_t* dst = a.amap_dst + d.amap_off;
+        for (int t = tid; t < d.amap_cnt; t += NT) F[dst[t]] = __ldg(a.A + src[t]);
+    }
+    __syncthreads();
+    // extend-add of the children's update blocks, in ascending child order
+    for (int c = 0; c < d.nchild; ++c) {
+        const int cs = a.child_idx[d.child_off + c];
+        const FrontDesc dc = a.desc[cs];
+        const int rc = dc.f - dc.w;
+        const double* CB = a.ws + dc.cb_off;
+        const int32_t* rl = a.rel + dc.rel_off;
+        for (int j = warp; j < rc; j += NW) {
+            const int pj = rl[j] * f;
+            const double* col = CB + (size_t)j * rc;
+            for (int i = j + lane; i < rc; i += 32) F[rl[i] + pj] += col[i];
+        }
+        __syncthreads();
+    }
+
+    // ---- factor the w pivot columns (right-looking inside the panel)
+    int nneg = 0, npert = 0;
+    for (int k = 0; k < w; ++k) {
+        __syncthreads();                        // updates of the previous pivot are complete
+        double dk = F[k + k * f];
+        bool pert = false;
+        if (!(fabs(dk) >= a.eps)) {            // also catches NaN
+            dk = (dk < 0.0) ? -a.eps : a.eps;
+            pert = true;
+            if (tid == 0) ++npert;
+        } else if (dk < 0.0 && tid == 0) ++nneg;
+        const double dinv = 1.0 / dk;
+        for (int i = k + 1 + tid; i < f; i += NT) {
+            const double u = F[i + k * f];
+            F[k + i * f] = u;                   // U(k,i) = D*L' kept in the (free) upper triangle
+            F[i + k * f] = u * dinv;
+        }
+        __syncthreads();                        // column k scaled, row k of U written
+        if (pert && tid == 0) F[k + k * f] = dk;
+        // update the remaining panel columns j in (k, w); the update block is done once below
+        for (int j = k + 1 + warp; j < w; j += NW) {
+            const double ukj = F[k + j * f];
+            for (int i = j + lane; i < f; i += 32) F[i + j * f] -= F[i + k * f] * ukj;
+        }
+    }
+    __syncthreads();
+    // ---- Schur complement: C(i,j) -= sum_k L(i,k) * U(k,j),  i >= j >= w, 4x4 register tiles
+    if (r > 0 && w > 0) {
+        const int nt = (r + 3) >> 2;
+        const int ntiles = nt * (nt + 1) / 2;
+        for (int t = tid; t < ntiles; t += NT) {
+            // lower-triangular tile index t -> (ti, tj), ti >= tj
+            int ti = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+            while (ti * (ti + 1) / 2 > t) --ti;
+            while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
+            const int tj = t - ti * (ti + 1) / 2;
+            const int i0 = w + 4 * ti, j0 = w + 4 * tj;
+            double acc[4][4];
+#pragma unroll
+            for (int x = 0; x < 4; ++x)
+#pragma unroll
+                for (int y = 0; y < 4; ++y) acc[x][y] = 0.0;
+            for (int k = 0; k < w; ++k) {
+                double av[4], bv[4];
+#pragma unroll
+                for (int x = 0; x < 4; ++x) av[x] = (i0 + x < f) ? F[i0 + x + k * f] : 0.0;
+#pragma unroll
+                for (int y = 0; y < 4; ++y) bv[y] = (j0 + y < f) ? F[k + (j0 + y) * f] : 0.0;
+#pragma unroll
+                for (int x = 0; x < 4; ++x)
+#pragma unroll
+                    for (int y = 0; y < 4; ++y) acc[x][y] = fma(av[x], bv[y], acc[x][y]);
+            }
+#pragma unroll
+            for (int y = 0; y < 4; ++y)
+#pragma unroll
+                for (int x = 0; x < 4; ++x) {
+                    const int i = i0 + x, j = j0 + y;
+                    if (i < f && j < f && i >= j) F[i + j * f] -= acc[x][y];
+                }
+        }
+    }
+    __syncthreads();
+    // ---- store: panel (first w columns, contiguous), D, update block
+    {
+        double* Lp = a.L + d.lp_off;
+        const int pw = f * w;
+        for (int i = tid; i < pw; i += NT) Lp[i] = F[i];
+        for (int k = tid; k < w; k += NT) a.dvec[d.col0 + k] = F[k + k * f];
+        double* CB = a.ws + d.cb_off;
+        for (int j = warp; j < r; j += NW) {
+            const double* src = F + (w + j) * f + w;
+            double* dst = CB + (size_t)j * r;
+            for (int i = j + lane; i < r; i += 32) dst[i] = src[i];
+        }
+    }
+    if (tid == 0) {
+        if (nneg) atomicAdd(a.counters + 0, nneg);
+        if (npert) atomicAdd(a.counters + 1, npert);
+    }
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// B class: fronts that do not fit in shared memory live in HBM:  panel at L+lp_off (ld f), update block at
+// ws+cb_off (ld r).  Element (i,j), i>=j, of the front is addressed by front_ptr().
+// ----------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double* front_ptr(const FactorArgs& a, const FrontDesc& d, int i, int j) {
+    const int w = d.w;
+    return (j < w) ? a.L + d.lp_off + (size_t)j * d.f + i
+                   : a.ws + d.cb_off + (size_t)(j - w) * (d.f - w) + (i - w);
+}
+
+// zero panel + update block of every big front in `list` (grid.y = front)
+__global__ void k_big_zero(FactorArgs a, const int32_t* __restrict__ list) {
+    const FrontDesc d = a.desc[list[blockIdx.y]];
+    const size_t np = (size_t)d.f * d.w, r = d.f - d.w, nc = r * r;
+    double* Lp = a.L + d.lp_off;
+    double* CB = a.ws + d.cb_off;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < np + nc; i += (size_t)gridDim.x * blockDim.x) {
+        if (i < np) Lp[i] = 0.0; else CB[i - np] = 0.0;
+    }
+}
+
+__global__ void k_big_scatter_A(FactorArgs a, const int32_t* __restrict__ list) {
+    const FrontDesc d = a.desc[list[blockIdx.y]];
+    const int32_t* src = a.amap_src + d.amap_off;
+    const int32_t* dst = a.amap_dst + d.amap_off;
+    double* Lp = a.L + d.lp_off;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < d.amap_cnt; t += gridDim.x * blockDim.x)
+        Lp[dst[t]] = __ldg(a.A + src[t]);
+}
+
+// extend-add of the `rank`-th child of every big front in `list` (plain +=: one contribution per element per launch)
+__global__ void k_big_extend_add(FactorArgs a, const int32_t* __restrict__ list, int rank) {
+    const FrontDesc d = a.desc[list[blockIdx.y]];
+    if (rank >= d.nchild) return;
+    const FrontDesc dc = a.desc[a.child_idx[d.child_off + rank]];
+    const int rc = dc.f - dc.w;
+    const double* CB = a.ws + dc.cb_off;
+    const int32_t* rl = a.rel + dc.rel_off;
+    const int lane = threadIdx.x & 31;
+    const int wglob = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int j = wglob; j < rc; j += nwarps) {
+        const int pj = rl[j];
+        const double* col = CB + (size_t)j * rc;
+        for (int i = j + lane; i < rc; i += 32) *front_ptr(a, d, rl[i], pj) += col[i];
+    }
+}
+
+constexpr int BIG_NB = 32;       // pivot block width of the blocked right-looking factorisation
+constexpr int BIG_ROWS = 128;    // rows of the panel solved by one CTA
+
+// Step kb of every big front, part 1: unblocked LDL^T of the NB x NB diagonal block in shared memory
+// (one CTA per front); writes L11 (unit lower, scaled) and D back in place, D into dvec, inertia counts.
+__global__ void __launch_bounds__(32) k_big_diag(FactorArgs a, const int32_t* __restrict__ list, int step) {
+    const FrontDesc d = a.desc[list[blockIdx.x]];
+    const int kb = step * BIG_NB;
+    if (kb >= d.w) return;
+    const int f = d.f;
+    const int nb = min(BIG_NB, d.w - kb);
+    __shared__ double D11[BIG_NB][BIG_NB + 1];   // row-major [i][k]
+    __shared__ double dd[BIG_NB];
+    const int tid = threadIdx.x;                 // one warp; lane i owns row i
+    double* Lp = a.L + d.lp_off;
+    for (int t = tid; t < nb * nb; t += 32) {
+        const int i = t % nb, k = t / nb;
+        D11[i][k] = (i >= k) ? Lp[(size_t)(kb + k) * f + kb + i] : 0.0;
+    }
+    __syncwarp();
+    int nneg = 0, npert = 0;
+    for (int k = 0; k < nb; ++k) {
+        double dk = D11[k][k];
+        if (!(fabs(dk) >= a.eps)) { dk = (dk < 0.0) ? -a.eps : a.eps; ++npert; }
+        else if (dk < 0.0) ++nneg;
+        if (tid == 0) dd[k] = dk;
+        if (tid > k && tid < nb) {
+            const double l = D11[tid][k] / dk;
+            for (int j = k + 1; j <= tid; ++j) D11[tid][j] -= l * D11[j][k];   // column k still unscaled (U)
+        }
+        __syncwarp();
+    }
+    for (int t = tid; t < nb * nb; t += 32) {
+        const int i = t % nb, k = t / nb;
+        if (i > k) Lp[(size_t)(kb + k) * f + kb + i] = D11[i][k] / dd[k];
+        else if (i == k) Lp[(size_t)(kb + k) * f + kb + i] = dd[k];
+    }
+    if (tid < nb) a.dvec[d.col0 + kb + tid] = dd[tid];
+    if (tid == 0) {
+        if (nneg) atomicAdd(a.counters + 0, nneg);
+        if (npert) atomicAdd(a.counters + 1, npert);
+    }
+}
+
+// Step kb, part 2: rows below the diagonal block:  L21 = A21 * L11^{-T} * D^{-1}; one thread per row,
+// BIG_ROWS rows per CTA, L11/D staged in shared memory.
+__global__ void __launch_bounds__(BIG_ROWS) k_big_panel(FactorArgs a, const int32_t* __restrict__ list, int step) {
+    const FrontDesc d = a.desc[list[blockIdx.y]];
+    const int kb = step * BIG_NB;
+    if (kb >= d.w) return;
+    const int f = d.f;
+    const int nb = min(BIG_NB, d.w - kb);
+    const int row0 = kb + nb + blockIdx.x * BIG_ROWS;
+    if (row0 >= f) return;
+    __shared__ double L11[BIG_NB][BIG_NB + 1];   // [k][j] = d_j * L11(k,j), j < k
+    __shared__ double dinv[BIG_NB];
+    const int tid = threadIdx.x;
+    double* Lp = a.L + d.lp_off;
+    for (int t = tid; t < BIG_NB * BIG_NB; t += BIG_ROWS) {
+        const int k = t % BIG_NB, j = t / BIG_NB;
+        double v = 0.0;
+        if (k < nb && j < k) v = Lp[(size_t)(kb + j) * f + kb + k] * Lp[(size_t)(kb + j) * f + kb + j];
+        L11[k][j] = v;
+    }
+    if (tid < BIG_NB) dinv[tid] = (tid < nb) ? 1.0 / Lp[(size_t)(kb + tid) * f + kb + tid] : 0.0;
+    __syncthreads();
+    const int i = row0 + tid;
+    if (i < f) {
+        double x[BIG_NB];
+#pragma unroll
+        for (int k = 0; k < BIG_NB; ++k) x[k] = (k < nb) ? Lp[(size_t)(kb + k) * f + i] : 0.0;
+        // a_k = sum_{j<=k} x_j d_j L11(k,j)  =>  x_k = (a_k - sum_{j<k} x_j * (d_j L11(k,j))) / d_k
+#pragma unroll
+        for (int k = 0; k < BIG_NB; ++k) {
+            double sacc = x[k];
+#pragma unroll
+            for (int j = 0; j < BIG_NB; ++j)
+                if (j < k) sacc = fma(-x[j], L11[k][j], sacc);
+            x[k] = sacc * dinv[k];
+        }
+#pragma unroll
+        for (int k = 0; k < BIG_NB; ++k)
+            if (k < nb) Lp[(size_t)(kb + k) * f + i] = x[k];
+    }
+}
+
+// Trailing update of step kb:  C(i,j) -= sum_{k in block} L(i,k) d_k L(j,k)   for i >= j >= kb+nb.
+// 64x64 tiles, 256 threads (8 warps as 4x2, each warp 16x32 via m8n8k4 DMMA fragments), operands staged in
+// shared memory.  Tiles strictly above the diagonal are skipped.
+constexpr int UT = 64;
+__global__ void __launch_bounds__(256) k_big_update(FactorArgs a, const int32_t* __restrict__ list, int step) {
+    const FrontDesc d = a.desc[list[blockIdx.z]];
+    const int kb = step * BIG_NB;
+    if (kb >= d.w) return;
+    const int f = d.f;
+    const int nb = min(BIG_NB, d.w - kb);
+    const int t0 = kb + nb;                       // first trailing row/col
+    const int nt = (f - t0 + UT - 1) / UT;
+    const int ti = blockIdx.x, tj = blockIdx.y;
+    if (ti >= nt || tj > ti) return;
+    const int i0 = t0 + ti * UT, j0 = t0 + tj * UT;
+    __shared__ double As[BIG_NB][UT + 4];         // As[k][i] = L(i0+i, kb+k)
+    __shared__ double Bs[BIG_NB][UT + 4];         // Bs[k][j] = d_k * L(j0+j, kb+k)
+    const double* Lp = a.L + d.lp_off;
+    const int tid = threadIdx.x;
+    for (int t = tid; t < BIG_NB * UT; t += 256) {
+        const int i = t % UT, k = t / UT;
+        double va = 0.0, vb = 0.0;
+        if (k < nb) {
+            const double dk = Lp[(size_t)(kb + k) * f + kb + k];
+            if (i0 + i < f) va = Lp[(size_t)(kb + k) * f + i0 + i];
+            if (j0 + i < f) vb = dk * Lp[(size_t)(kb + k) * f + j0 + i];
+        }
+        As[k][i] = va;
+        Bs[k][i] = vb;
+    }
+    __syncthreads();
+    const int warp = tid >> 5, lane = tid & 31;
+    const int wi = (warp & 3) * 16, wj = (warp >> 2) * 32;     // warp tile origin inside the 64x64 tile
+    const int g = lane >> 2, q = lane & 3;                      // DMMA fragment coordinates
+    double c[2][4][2];
+#pragma unroll
+    for (int x = 0; x < 2; ++x)
+#pragma unroll
+        for (int y = 0; y < 4; ++y) c[x][y][0] = c[x][y][1] = 0.0;
+#pragma unroll
+    for (int k0 = 0; k0 < BIG_NB; k0 += 4) {
+        double af[2], bf[4];
+#pragma unroll
+        for (int x = 0; x < 2; ++x) af[x] = As[k0 + q][wi + 8 * x + g];      // A frag: row g, col q
+#pragma unroll
+        for (int y = 0; y < 4; ++y) bf[y] = Bs[k0 + q][wj + 8 * y + g];      // B frag: row q, col g
+#pragma unroll
+        for (int x = 0; x < 2; ++x)
+#pragma unroll
+            for (int y = 0; y < 4; ++y)
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                             : "+d"(c[x][y][0]), "+d"(c[x][y][1])
+                             : "d"(af[x]), "d"(bf[y]));
+    }
+    // C fragment: row g, cols 2q, 2q+1
+#pragma unroll
+    for (int x = 0; x < 2; ++x)
+#pragma unroll
+        for (int y = 0; y < 4; ++y)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int i = i0 + wi + 8 * x + g;
+                const int j = j0 + wj + 8 * y + 2 * q + e;
+                if (i < f && j < f && i >= j) *front_ptr(a, d, i, j) -= c[x][y][e];
+            }
+}
+
+}  // namespace b2

@@ -1,0 +1,436 @@
+// IPM vector kernels around the factorisation: diagonal updates, RHS reduction/expansion, KKT mat-vec and the
+// sparse mat-vecs they need (C-ABI in include/b200kkt.h; rows A1, A2, A12, A13 of SURVEY 8a).
+// The reference issues these as ~20 broadcast kernels + 3 cuSPARSE SpMV per refinement step
+// (src/IPM/kernels.jl:4-27,161-204; lib/MadNLPGPU/src/KKT/gpu_sparse.jl:14-65); here each reference function is
+// one or two single-pass kernels: every output entry is written by exactly one thread (inverse index maps instead
+// of scatter through ind_lb/ind_ub), so there are no atomics and results are deterministic.
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+
+using namespace b2;
+
+struct b2_bounds {
+    int64_t n_tot = 0, nlb = 0, nub = 0;
+    DevBuf<int64_t> ind_lb, ind_ub;
+    DevBuf<int32_t> lbpos, ubpos;   // [n_tot] position in ind_lb / ind_ub or -1
+};
+
+extern "C" int b2_bounds_create(int64_t n_tot, int64_t nlb, int64_t nub, const int64_t* ind_lb_h, const int64_t* ind_ub_h,
+                                b2_bounds** out) {
+    if (!out || n_tot < 0 || nlb < 0 || nub < 0 || (nlb && !ind_lb_h) || (nub && !ind_ub_h)) {
+        set_error("b2_bounds_create: invalid argument");
+        return B2_ERR_INVALID;
+    }
+    std::vector<int32_t> lp(n_tot, -1), up(n_tot, -1);
+    for (int64_t k = 0; k < nlb; ++k) {
+        if (ind_lb_h[k] < 0 || ind_lb_h[k] >= n_tot || lp[ind_lb_h[k]] != -1) { set_error("b2_bounds_create: bad ind_lb"); return B2_ERR_INVALID; }
+        lp[ind_lb_h[k]] = (int32_t)k;
+    }
+    for (int64_t k = 0; k < nub; ++k) {
+        if (ind_ub_h[k] < 0 || ind_ub_h[k] >= n_tot || up[ind_ub_h[k]] != -1) { set_error("b2_bounds_create: bad ind_ub"); return B2_ERR_INVALID; }
+        up[ind_ub_h[k]] = (int32_t)k;
+    }
+    auto* b = new b2_bounds();
+    b->n_tot = n_tot; b->nlb = nlb; b->nub = nub;
+    if (b->ind_lb.upload(ind_lb_h, nlb) != cudaSuccess || b->ind_ub.upload(ind_ub_h, nub) != cudaSuccess ||
+        b->lbpos.upload(lp.data(), lp.size()) != cudaSuccess || b->ubpos.upload(up.data(), up.size()) != cudaSuccess) {
+        delete b;
+        return cuda_fail(cudaGetLastError(), "bounds upload", __FILE__, __LINE__);
+    }
+    *out = b;
+    return B2_OK;
+}
+extern "C" int b2_bounds_destroy(b2_bounds* b) { delete b; return B2_OK; }
+
+static inline int grid_for(int64_t n) { return (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, 8 * sm_count())); }
+#define GRID_STRIDE(i, n) for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < (n); i += (int64_t)gridDim.x * blockDim.x)
+
+// ---------------------------------------------------------------------------------------------------------
+__global__ void k_set_aug_diagonal(int64_t n_tot, const int32_t* __restrict__ lbpos, const int32_t* __restrict__ ubpos,
+                                   const double* __restrict__ reg, const double* __restrict__ ll, const double* __restrict__ ld,
+                                   const double* __restrict__ ul, const double* __restrict__ ud, double* __restrict__ pr) {
+    GRID_STRIDE(i, n_tot) {
+        double v = reg[i];
+        const int p = lbpos[i], q = ubpos[i];
+        if (p >= 0) v = __dsub_rn(v, __ddiv_rn(ll[p], ld[p]));
+        if (q >= 0) v = __dsub_rn(v, __ddiv_rn(ul[q], ud[q]));
+        pr[i] = v;
+    }
+}
+extern "C" int b2_set_aug_diagonal(b2_bounds* b, const double* reg_d, const double* l_lower_d, const double* l_diag_d,
+                                   const double* u_lower_d, const double* u_diag_d, double* pr_diag_d, void* stream) {
+    if (!b || !reg_d || !pr_diag_d) { set_error("b2_set_aug_diagonal: invalid argument"); return B2_ERR_INVALID; }
+    if (b->n_tot == 0) return B2_OK;
+    k_set_aug_diagonal<<<grid_for(b->n_tot), 256, 0, as_stream(stream)>>>(b->n_tot, b->lbpos.p, b->ubpos.p, reg_d, l_lower_d, l_diag_d,
+                                                                         u_lower_d, u_diag_d, pr_diag_d);
+    B2_CUDA(cudaGetLastError());
+    return B2_OK;
+}
+
+__global__ void k_regularize(int64_t n_tot, int64_t m, double dw, double dc, double* __restrict__ reg, double* __restrict__ pr,
+                             double* __restrict__ du) {
+    GRID_STRIDE(i, n_tot + m) {
+        if (i < n_tot) { reg[i] += dw; pr[i] += dw; }
+        else du[i - n_tot] -= dc;
+    }
+}
+extern "C" int b2_regularize_diagonal(int64_t n_tot, int64_t m, double dw, double dc, double* reg_d, double* pr_diag_d,
+                                      double* du_diag_d, void* stream) {
+    if (n_tot < 0 || m < 0 || !reg_d || !pr_diag_d || (m && !du_diag_d)) { set_error("b2_regularize_diagonal: invalid argument"); return B2_ERR_INVALID; }
+    if (n_tot + m == 0) return B2_OK;
+    k_regularize<<<grid_for(n_tot + m), 256, 0, as_stream(stream)>>>(n_tot, m, dw, dc, reg_d, pr_diag_d, du_diag_d);
+    B2_CUDA(cudaGetLastError());
+    return B2_OK;
+}
+
+__global__ void k_reduce_rhs(int64_t n_tot, int64_t m, int64_t nlb, const int32_t* __restrict__ lbpos, const int32_t* __restrict__ ubpos,
+                             const double* __restrict__ ld, const double* __restrict__ ud, double* __restrict__ w) {
+    const double* wzl = w + n_tot + m;
+    const double* wzu = wzl + nlb;
+    GRID_STRIDE(i, n_tot) {
+        const int p = lbpos[i], q = ubpos[i];
+        if (p < 0 && q < 0) continue;
+        double v = w[i];
+        if (p >= 0) v = __dsub_rn(v, __ddiv_rn(wzl[p], ld[p]));
+        if (q >= 0) v = __dsub_rn(v, __ddiv_rn(wzu[q], ud[q]));
+        w[i] = v;
+    }
+}
+extern "C" int b2_reduce_rhs(b2_bounds* b, int64_t m, const double* l_diag_d, const double* u_diag_d, double* w_d, void* stream) {
+    if (!b || !w_d) { set_error("b2_reduce_rhs: invalid argument"); return B2_ERR_INVALID; }
+    if (b->n_tot == 0) return B2_OK;
+    k_reduce_rhs<<<grid_for(b->n_tot), 256, 0, as_stream(stream)>>>(b->n_tot, m, b->nlb, b->lbpos.p, b->ubpos.p, l_diag_d, u_diag_d, w_d);
+    B2_CUDA(cudaGetLastError());
+    return B2_OK;
+}
+
+__global__ void k_finish_aug_solve(int64_t n_tot, int64_t m, int64_t nlb, int64_t nub, const int64_t* __restrict__ ind_lb,
+                                   const int64_t* __restrict__ ind_ub, const double* __restrict__ ll, const double* __restrict__ ul,
+                                   const double* __restrict__ ld, const double* __restrict__ ud, double* __restrict__ w) {
+    double* dlb = w + n_tot + m;
+    double* dub = dlb + nlb;
+    GRID_STRIDE(t, nlb + nub) {
+        if (t < nlb) dlb[t] = __ddiv_rn(__dadd_rn(-dlb[t], __dmul_rn(ll[t], w[ind_lb[t]])), ld[t]);
+        else {
+            const int64_t k = t - nlb;
+            dub[k] = __ddiv_rn(__dsub_rn(dub[k], __dmul_rn(ul[k], w[ind_ub[k]])), ud[k]);
+        }
+    }
+}
+extern "C" int b2_finish_aug_solve(b2_bounds* b, int64_t m, const double* l_lower_d, const double* u_lower_d,
+                                   const double* l_diag_d, const double* u_diag_d, double* w_d, void* stream) {
+    if (!b || !w_d) { set_error("b2_finish_aug_solve: invalid argument"); return B2_ERR_INVALID; }
+    if (b->nlb + b->nub == 0) return B2_OK;
+    k_finish_aug_solve<<<grid_for(b->nlb + b->nub), 256, 0, as_stream(stream)>>>(b->n_tot, m, b->nlb, b->nub, b->ind_lb.p, b->ind_ub.p,
+                                                                               l_lower_d, u_lower_d, l_diag_d, u_diag_d, w_d);
+    B2_CUDA(cudaGetLastError());
+    return B2_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// SpMV plans: CSC (column gather = A'x) and its CSR view (row gather = Ax) sharing one value array
+// ---------------------------------------------------------------------------------------------------------
+struct b2_spmv_plan {
+    int32_t nrow = 0, ncol = 0;
+    int64_t nnz = 0;
+    DevBuf<int32_t> colptr, rowval, rowptr, colidx, valmap;
+};
+
+extern "C" int b2_spmv_plan_create(int32_t nrow, int32_t ncol, const int32_t* colptr_h, const int32_t* rowval_h, b2_spmv_plan** out) {
+    if (!out || nrow < 0 || ncol < 0 || !colptr_h) { set_error("b2_spmv_plan_create: invalid argument"); return B2_ERR_INVALID; }
+    const int64_t nnz = colptr_h[ncol];
+    std::vector<int32_t> rowptr(nrow + 1, 0), colidx(nnz), valmap(nnz);
+    for (int64_t p = 0; p < nnz; ++p) {
+        if (rowval_h[p] < 0 || rowval_h[p] >= nrow) { set_error("b2_spmv_plan_create: row index out of range"); return B2_ERR_INVALID; }
+        rowptr[rowval_h[p] + 1]++;
+    }
+    for (int32_t i = 0; i < nrow; ++i) rowptr[i + 1] += rowptr[i];
+    std::vector<int32_t> pos(rowptr.begin(), rowptr.end() - 1);
+    for (int32_t j = 0; j < ncol; ++j)
+        for (int32_t p = colptr_h[j]; p < colptr_h[j + 1]; ++p) {
+            const int32_t q = pos[rowval_h[p]]++;
+            colidx[q] = j;
+            valmap[q] = p;
+        }
+    auto* pl = new b2_spmv_plan();
+    pl->nrow = nrow; pl->ncol = ncol; pl->nnz = nnz;
+    if (pl->colptr.upload(colptr_h, ncol + 1) != cudaSuccess || pl->rowval.upload(rowval_h, nnz) != cudaSuccess ||
+        pl->rowptr.upload(rowptr.data(), rowptr.size()) != cudaSuccess || pl->colidx.upload(colidx.data(), nnz) != cudaSuccess ||
+        pl->valmap.upload(valmap.data(), nnz) != cudaSuccess) {
+        delete pl;
+        return cuda_fail(cudaGetLastError(), "spmv plan upload", __FILE__, __LINE__);
+    }
+    *out = pl;
+    return B2_OK;
+}
+extern "C" int b2_spmv_plan_destroy(b2_spmv_plan* p) { delete p; return B2_OK; }
+
+__device__ __forceinline__ double col_dot(const int32_t* __restrict__ colptr, const int32_t* __restrict__ rowval,
+                                          const double* __restrict__ nz, const double* __restrict__ x, int64_t j) {
+    double s = 0.0;
+    for (int p = colptr[j]; p < colptr[j + 1]; ++p) s = fma(nz[p], x[rowval[p]], s);
+    return s;
+}
+__device__ __forceinline__ double row_dot(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+                                          const int32_t* __restrict__ valmap, const double* __restrict__ nz,
+                                          const double* __restrict__ x, int64_t i) {
+    double s = 0.0;
+    for (int q = rowptr[i]; q < rowptr[i + 1]; ++q) s = fma(nz[valmap[q]], x[colidx[q]], s);
+    return s;
+}
+__device__ __forceinline__ double row_dot_strict(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+                                                 const int32_t* __restrict__ valmap, const double* __restrict__ nz,
+                                                 const double* __restrict__ x, int64_t i) {
+    double s = 0.0;
+    for (int q = rowptr[i]; q < rowptr[i + 1]; ++q) {
+        const int c = colidx[q];
+        if (c != i) s = fma(nz[valmap[q]], x[c], s);
+    }
+    return s;
+}
+
+__global__ void k_spmv_t(int64_t ncol, const int32_t* colptr, const int32_t* rowval, const double* nz, const double* x, double* y,
+                         double alpha, double beta) {
+    GRID_STRIDE(j, ncol) {
+        const double s = col_dot(colptr, rowval, nz, x, j);
+        y[j] = (beta == 0.0) ? alpha * s : alpha * s + beta * y[j];
+    }
+}
+__global__ void k_spmv_n(int64_t nrow, const int32_t* rowptr, const int32_t* colidx, const int32_t* valmap, const double* nz,
+                         const double* x, double* y, double alpha, double beta) {
+    GRID_STRIDE(i, nrow) {
+        const double s = row_dot(rowptr, colidx, valmap, nz, x, i);
+        y[i] = (beta == 0.0) ? alpha * s : alpha * s + beta * y[i];
+    }
+}
+__global__ void k_spmv_sym(int64_t n, const int32_t* colptr, const int32_t* rowval, const int32_t* rowptr, const int32_t* colidx,
+                           const int32_t* valmap, const double* nz, const double* x, double* y, double alpha, double beta) {
+    GRID_STRIDE(i, n) {
+        const double s = col_dot(colptr, rowval, nz, x, i) + row_dot_strict(rowptr, colidx, valmap, nz, x, i);
+        y[i] = (beta == 0.0) ? alpha * s : alpha * s + beta * y[i];
+    }
+}
+
+extern "C" int b2_spmv_n(b2_spmv_plan* p, const double* nz_d, const double* x_d, double* y_d, double alpha, double beta, void* stream) {
+    if (!p || !x_d || !y_d) { set_error("b2_spmv_n: invalid argument"); return B2_ERR_INVALID; }
+    if (p->nrow == 0) return B2_OK;
+    k_spmv_n<<<grid_for(p->nrow), 256, 0, as_stream(stream)>>>(p->nrow, p->rowptr.p, p->colidx.p, p->valmap.p, nz_d, x_d, y_d, alpha, beta);
+    B2_CUDA(cudaGetLastError());
+    return B2_OK;
+}
+extern "C" int b2_spmv_t(b2_spmv_plan* p, const double* nz_d, const double* x_d, double* y_d, double alpha, double beta, void* stream) {
+    if (!p || !x_d || !y_d) { set_error("b2_spmv_t: invalid argument"); return B2_ERR_INVALID; }
+    if (p->ncol == 0) return B2_OK;
+    k_spmv_t<<<grid_for(p->ncol), 256, 0, as_stream(stream)>>>(p->ncol, p->colptr.p, p->rowval.p, nz_d, x_d, y_d, alpha, beta);
+    B2_CUDA(cudaGetLastError());
+    return B2_OK;
+}
+extern "C" int b2_spmv_symlower(b2_spmv_plan* p, const double* nz_d, const double* x_d, double* y_d, double alpha, double beta, void* stream) {
+    if (!p || !x_d || !y_d || p->nrow != p->ncol) { set_error("b2_spmv_symlower: invalid argument"); return B2_ERR_INVALID; }
+    if (p->nrow == 0) return B2_OK;
+    k_spmv_sym<<<grid_for(p->nrow), 256, 0, as_stream(stream)>>>(p->nrow, p->colptr.p, p->rowval.p, p->rowptr.p, p->colidx.p, p->valmap.p,
+                                                                 nz_d, x_d, y_d, alpha, beta);
+    B2_CUDA(cudaGetLastError());
+    return B2_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// _kktmul!  (IPM/kernels.jl:161-180)
+// ---------------------------------------------------------------------------------------------------------
+struct KktMulArgs {
+    int64_t n_tot, m, nlb, nub;
+    const int32_t *lbpos, *ubpos;
+    const int64_t *ind_lb, *ind_ub;
+    const double *reg, *du, *ll, *ul, *ld, *ud;
+    double alpha, beta;
+};
+__device__ __forceinline__ double scl(double beta, double w) { return beta == 0.0 ? 0.0 : beta * w; }
+// contribution of _kktmul! to entry t of w (w already holds the mat-vec part for t < n_tot + m)
+__device__ __forceinline__ double kktmul_entry(const KktMulArgs& a, int64_t t, double wt, const double* __restrict__ x) {
+    const double* xzl = x + a.n_tot + a.m;
+    const double* xzu = xzl + a.nlb;
+    if (t < a.n_tot) {
+        double v = wt + a.alpha * a.reg[t] * x[t];
+        const int p = a.lbpos[t], q = a.ubpos[t];
+        if (p >= 0) v -= a.alpha * xzl[p];
+        if (q >= 0) v += a.alpha * xzu[q];
+        return v;
+    }
+    if (t < a.n_tot + a.m) return wt + a.alpha * a.du[t - a.n_tot] * x[t];
+    if (t < a.n_tot + a.m + a.nlb) {
+        const int64_t k = t - a.n_tot - a.m;
+        return scl(a.beta, wt) + a.alpha * (x[a.ind_lb[k]] * a.ll[k] - xzl[k] * a.ld[k]);
+    }
+    const int64_t k = t - a.n_tot - a.m - a.nlb;
+    return scl(a.beta, wt) + a.alpha * (x[a.ind_ub[k]] * a.ul[k] + xzu[k] * a.ud[k]);
+}
+__global__ void k_kktmul(KktMulArgs a, const double* __restrict__ x, double* __restrict__ w) {
+    GRID_STRIDE(t, a.n_tot + a.m + a.nlb + a.nub) w[t] = kktmul_entry(a, t, w[t], x);
+}
+static KktMulArgs make_kktmul(b2_bounds* b, int64_t m, const double* reg, const double* du, const double* ll, const double* ul,
+                              const double* ld, const double* ud, double alpha, double beta) {
+    KktMulArgs a;
+    a.n_tot = b->n_tot; a.m = m; a.nlb = b->nlb; a.nub = b->nub;
+    a.lbpos = b->lbpos.p; a.ubpos = b->ubpos.p; a.ind_lb = b->ind_lb.p; a.ind_ub = b->ind_ub.p;
+    a.reg = reg; a.du = du; a.ll = ll; a.ul = ul; a.ld = ld; a.ud = ud; a.alpha = alpha; a.beta = beta;
+    return a;
+}
+extern "C" int b2_kktmul(b2_bounds* b, int64_t m, const double* reg_d, const double* du_diag_d, const double* l_lower_d,
+                         const double* u_lower_d, const double* l_diag_d, const double* u_diag_d, double alpha, double beta,
+                         const double* x_d, double* w_d, void* stream) {
+    if (!b || !x_d || !w_d) { set_error("b2_kktmul: invalid argument"); return B2_ERR_INVALID; }
+    KktMulArgs a = make_kktmul(b, m, reg_d, du_diag_d, l_lower_d, u_lower_d, l_diag_d, u_diag_d, alpha, beta);
+    const int64_t tot = a.n_tot + a.m + a.nlb + a.nub;
+    if (tot == 0) return B2_OK;
+    k_kktmul<<<grid_for(tot), 256, 0, as_stream(stream)>>>(a, x_d, w_d);
+    B2_CUDA(cudaGetLastError());
+    return B2_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// solve_kkt!(::SparseCondensedKKTSystem) pre / post  (IPM/factorization.jl:143-167)
+// ---------------------------------------------------------------------------------------------------------
+__global__ void k_cond_pre1(int64_t n, int64_t m, int64_t nlb, const int32_t* __restrict__ lbpos, const int32_t* __restrict__ ubpos,
+                            const double* __restrict__ ld, const double* __restrict__ ud, const double* __restrict__ pr,
+                            const double* __restrict__ D, double* __restrict__ buffer, double* __restrict__ w) {
+    const int64_t n_tot = n + m;
+    const double* wzl = w + n_tot + m;
+    const double* wzu = wzl + nlb;
+    GRID_STRIDE(i, n_tot) {
+        double v = w[i];
+        const int p = lbpos[i], q = ubpos[i];
+        if (p >= 0) v = __dsub_rn(v, __ddiv_rn(wzl[p], ld[p]));
+        if (q >= 0) v = __dsub_rn(v, __ddiv_rn(wzu[q], ud[q]));
+        if (p >= 0 || q >= 0) w[i] = v;
+        if (i >= n) {
+            const int64_t j = i - n;
+            buffer[j] = D[j] * (w[n_tot + j] + v / pr[i]);
+        }
+    }
+}
+__global__ void k_cond_pre2(int64_t n, const int32_t* rowptr, const int32_t* colidx, const int32_t* valmap, const double* __restrict__ nz,
+                            const double* __restrict__ buffer, double* w) {
+    GRID_STRIDE(i, n) w[i] += row_dot(rowptr, colidx, valmap, nz, buffer, i);
+}
+__global__ void k_cond_post1(int64_t n, int64_t m, const int32_t* colptr, const int32_t* rowval, const double* __restrict__ nz,
+                             const double* __restrict__ pr, const double* __restrict__ D, const double* __restrict__ buffer,
+                             double* w) {
+    GRID_STRIDE(j, m) {
+        const double b2v = col_dot(colptr, rowval, nz, w, j);      // (Jt' * wx)_j ; wx = w[0:n]
+        const double wz = -buffer[j] + D[j] * b2v;
+        w[n + m + j] = wz;
+        w[n + j] = (w[n + j] + wz) / pr[n + j];
+    }
+}
+extern "C" int b2_condensed_solve_pre(b2_bounds* b, b2_spmv_plan* jt, int64_t n, int64_t m, const double* jt_nz_d,
+                                      const double* pr_diag_d, const double* diag_buffer_d, const double* l_diag_d,
+                                      const double* u_diag_d, double* buffer_d, double* w_d, void* stream) {
+    if (!b || !jt || !w_d || !buffer_d || b->n_tot != n + m || jt->nrow != n || jt->ncol != m) {
+        set_error("b2_condensed_solve_pre: invalid argument");
+        return B2_ERR_INVALID;
+    }
+    cudaStream_t st = as_stream(stream);
+    k_cond_pre1<<<grid_for(n + m), 256, 0, st>>>(n, m, b->nlb, b->lbpos.p, b->ubpos.p, l_diag_d, u_diag_d, pr_diag_d, diag_buffer_d, buffer_d, w_d);
+    k_cond_pre2<<<grid_for(n), 256, 0, st>>>(n, jt->rowptr.p, jt->colidx.p, jt->valmap.p, jt_nz_d, buffer_d, w_d);
+    B2_CUDA(cudaGetLastError());
+    return B2_OK;
+}
+extern "C" int b2_condensed_solve_post(b2_bounds* b, b2_spmv_plan* jt, int64_t n, int64_t m, const double* jt_nz_d,
+                                       const double* pr_diag_d, const double* diag_buffer_d, const double* l_lower_d,
+                                       const double* u_lower_d, const double* l_diag_d, const double* u_diag_d,
+                                       const double* buffer_d, double* w_d, void* stream) {
+    if (!b || !jt || !w_d || !buffer_d || b->n_tot != n + m) { set_error("b2_condensed_solve_post: invalid argument"); return B2_ERR_INVALID; }
+    cudaStream_t st = as_stream(stream);
+    if (m > 0) k_cond_post1<<<grid_for(m), 256, 0, st>>>(n, m, jt->colptr.p, jt->rowval.p, jt_nz_d, pr_diag_d, diag_buffer_d, buffer_d, w_d);
+    B2_CUDA(cudaGetLastError());
+    return b2_finish_aug_solve(b, m, l_lower_d, u_lower_d, l_diag_d, u_diag_d, w_d, stream);
+}
+
+// mul!(w, ::SparseCondensedKKTSystem, x, alpha, beta) in one pass (IPM/factorization.jl:303-324 + _kktmul!)
+struct CondMulArgs {
+    int64_t n, m;
+    const int32_t *h_colptr, *h_rowval, *h_rowptr, *h_colidx, *h_valmap;
+    const int32_t *j_colptr, *j_rowval, *j_rowptr, *j_colidx, *j_valmap;
+    const double *h_nz, *j_nz;
+};
+__global__ void k_cond_mul(CondMulArgs c, KktMulArgs a, const double* __restrict__ x, double* __restrict__ w) {
+    const int64_t n = c.n, m = c.m;
+    const double* xs = x + n;
+    const double* xz = x + n + m;
+    GRID_STRIDE(t, a.n_tot + a.m + a.nlb + a.nub) {
+        double wt = w[t];
+        if (t < n) {
+            const double hx = col_dot(c.h_colptr, c.h_rowval, c.h_nz, x, t) + row_dot_strict(c.h_rowptr, c.h_colidx, c.h_valmap, c.h_nz, x, t);
+            const double jz = row_dot(c.j_rowptr, c.j_colidx, c.j_valmap, c.j_nz, xz, t);
+            wt = a.alpha * hx + scl(a.beta, wt) + a.alpha * jz;
+        } else if (t < n + m) {
+            wt = scl(a.beta, wt) - a.alpha * xz[t - n];
+        } else if (t < n + 2 * m) {
+            const int64_t j = t - n - m;
+            wt = a.alpha * col_dot(c.j_colptr, c.j_rowval, c.j_nz, x, j) + scl(a.beta, wt) - a.alpha * xs[j];
+        }
+        w[t] = kktmul_entry(a, t, wt, x);
+    }
+}
+extern "C" int b2_condensed_kkt_mul(b2_bounds* b, b2_spmv_plan* hess, b2_spmv_plan* jt, int64_t n, int64_t m,
+                                    const double* hess_nz_d, const double* jt_nz_d, const double* reg_d, const double* du_diag_d,
+                                    const double* l_lower_d, const double* u_lower_d, const double* l_diag_d, const double* u_diag_d,
+                                    double alpha, double beta, const double* x_d, double* w_d, void* stream) {
+    if (!b || !hess || !jt || !x_d || !w_d || b->n_tot != n + m || hess->nrow != n || jt->nrow != n || jt->ncol != m) {
+        set_error("b2_condensed_kkt_mul: invalid argument");
+        return B2_ERR_INVALID;
+    }
+    CondMulArgs c;
+    c.n = n; c.m = m;
+    c.h_colptr = hess->colptr.p; c.h_rowval = hess->rowval.p; c.h_rowptr = hess->rowptr.p; c.h_colidx = hess->colidx.p; c.h_valmap = hess->valmap.p;
+    c.j_colptr = jt->colptr.p; c.j_rowval = jt->rowval.p; c.j_rowptr = jt->rowptr.p; c.j_colidx = jt->colidx.p; c.j_valmap = jt->valmap.p;
+    c.h_nz = hess_nz_d; c.j_nz = jt_nz_d;
+    KktMulArgs a = make_kktmul(b, m, reg_d, du_diag_d, l_lower_d, u_lower_d, l_diag_d, u_diag_d, alpha, beta);
+    const int64_t tot = a.n_tot + a.m + a.nlb + a.nub;
+    k_cond_mul<<<grid_for(tot), 256, 0, as_stream(stream)>>>(c, a, x_d, w_d);
+    B2_CUDA(cudaGetLastError());
+    return B2_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// small BLAS-1 helpers (device-resident results: no host sync inside the refinement loop)
+// ---------------------------------------------------------------------------------------------------------
+__global__ void k_norm_inf(int64_t n, const double* __restrict__ x, unsigned long long* out) {
+    double mx = 0.0;
+    GRID_STRIDE(i, n) { const double v = fabs(x[i]); if (v > mx || v != v) mx = v; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { const double t = __shfl_xor_sync(0xffffffffu, mx, o); if (t > mx || t != t) mx = t; }
+    if ((threadIdx.x & 31) == 0) atomicMax(out, (unsigned long long)__double_as_longlong(mx));   // non-negative doubles order as integers
+}
+extern "C" int b2_norm_inf(int64_t n, const double* x_d, double* out_d, void* stream) {
+    if (n < 0 || !out_d || (n && !x_d)) { set_error("b2_norm_inf: invalid argument"); return B2_ERR_INVALID; }
+    cudaStream_t st = as_stream(stream);
+    B2_CUDA(cudaMemsetAsync(out_d, 0, sizeof(double), st));
+    if (n) k_norm_inf<<<grid_for(n), 256, 0, st>>>(n, x_d, (unsigned long long*)out_d);
+    B2_CUDA(cudaGetLastError());
+    return B2_OK;
+}
+__global__ void k_axpy(int64_t n, double a, const double* __restrict__ x, double* __restrict__ y) { GRID_STRIDE(i, n) y[i] += a * x[i]; }
+__global__ void k_copy(int64_t n, const double* __restrict__ x, double* __restrict__ y) { GRID_STRIDE(i, n) y[i] = x[i]; }
+__global__ void k_fill(int64_t n, double v, double* __restrict__ x) { GRID_STRIDE(i, n) x[i] = v; }
+extern "C" int b2_axpy(int64_t n, double a, const double* x_d, double* y_d, void* stream) {
+    if (n < 0 || (n && (!x_d || !y_d))) return B2_ERR_INVALID;
+    if (n) k_axpy<<<grid_for(n), 256, 0, as_stream(stream)>>>(n, a, x_d, y_d);
+    B2_CUDA(cudaGetLastError());
+    return B2_OK;
+}
+extern "C" int b2_copy(int64_t n, const double* x_d, double* y_d, void* stream) {
+    if (n < 0 || (n && (!x_d || !y_d))) return B2_ERR_INVALID;
+    if (n) k_copy<<<grid_for(n), 256, 0, as_stream(stream)>>>(n, x_d, y_d);
+    B2_CUDA(cudaGetLastError());
+    return B2_OK;
+}
+extern "C" int b2_fill(int64_t n, double v, double* x_d, void* stream) {
+    if (n < 0 || (n && !x_d)) return B2_ERR_INVALID;
+    if (n) k_fill<<<grid_for(n), 256, 0, as_stream(stream)>>>(n, v, x_d);
+    B2_CUDA(cudaGetLastError());
+    return B2_OK;
+}

@@ -1,0 +1,751 @@
+// b2_* sparse LDL^T solver: host driver (analysis -> device schedule -> CUDA-graph replay).
+// C-ABI declared in include/b200kkt.h; replaces the AbstractLinearSolver back-end role of CUDSSSolver
+// (lib/MadNLPGPU/ext/MadNLPGPUCUDAExt/cudss.jl:88-214) / Ma97Solver (lib/MadNLPHSL/src/ma97.jl:29-115).
+#include <algorithm>
+#include <cstring>
+#include <stdexcept>
+#include <vector>
+
+#include "analysis.hpp"
+#include "common.cuh"
+#include "front_kernels.cuh"
+#include "solve_kernels.cuh"
+
+using namespace b2;
+
+namespace {
+
+struct FactorLevel {
+    int offS = 0, nS = 0, maxfS = 0;
+    int offM = 0, nM = 0, maxfM = 0;
+    int offB = 0, nB = 0, maxfB = 0, maxwB = 0, maxchildB = 0, maxamapB = 0, maxrB = 0;
+};
+struct SolveLevel {
+    int offW = 0, nW = 0, smemW = 0;   // doubles per warp
+    int offC = 0, nC = 0, maxfC = 0;
+};
+struct Phase {
+    std::vector<FactorLevel> flev;
+    std::vector<SolveLevel> slev;
+    cudaGraphExec_t g_factor = nullptr, g_fwd = nullptr, g_bwd = nullptr;
+    int64_t n_factor_launches = 0, n_solve_launches = 0;
+};
+
+constexpr int S_MAX = 64;        // S class: f <= 64, 128 threads
+constexpr int SOLVE_WARP_MAX = 64;
+
+}  // namespace
+
+struct b2_solver {
+    Symbolic S;
+    b2_options opt;
+    bool symbolic_only = false;
+    const double* nzval_d = nullptr;
+    int device = 0;
+    // device copies of the symbolic structure
+    DevBuf<FrontDesc> d_desc;
+    DevBuf<int32_t> d_rows, d_child_idx, d_rel, d_amap_src, d_amap_dst, d_perm, d_sched;
+    DevBuf<int64_t> d_cbv_off;
+    DevBuf<uint8_t> d_mask_p;
+    // numeric storage
+    DevBuf<double> d_L, d_ws, d_dvec, d_xp, d_cbv;
+    DevBuf<int32_t> d_counters;
+    int32_t* h_counters = nullptr;   // pinned
+    std::vector<int64_t> cbv_off;
+    int64_t exch_cbv = 0;
+    Phase phase[2];                  // 0 = local (owned subtrees), 1 = shared top tree
+    cudaStream_t cap_stream = nullptr;
+    bool factorized = false;
+    int64_t last_perturbed = 0;
+    std::vector<uint8_t> owned_mask;  // original numbering
+
+    ~b2_solver() {
+        for (auto& p : phase) {
+            if (p.g_factor) cudaGraphExecDestroy(p.g_factor);
+            if (p.g_fwd) cudaGraphExecDestroy(p.g_fwd);
+            if (p.g_bwd) cudaGraphExecDestroy(p.g_bwd);
+        }
+        if (cap_stream) cudaStreamDestroy(cap_stream);
+        if (h_counters) cudaFreeHost(h_counters);
+    }
+};
+
+namespace {
+
+FactorArgs factor_args(b2_solver* s) {
+    FactorArgs a;
+    a.desc = s->d_desc.p; a.child_idx = s->d_child_idx.p; a.rel = s->d_rel.p;
+    a.amap_src = s->d_amap_src.p; a.amap_dst = s->d_amap_dst.p;
+    a.A = s->nzval_d; a.L = s->d_L.p; a.ws = s->d_ws.p; a.dvec = s->d_dvec.p;
+    a.counters = s->d_counters.p; a.eps = s->opt.pivot_eps;
+    return a;
+}
+SolveArgs solve_args(b2_solver* s) {
+    SolveArgs a;
+    a.desc = s->d_desc.p; a.rows = s->d_rows.p; a.child_idx = s->d_child_idx.p; a.rel = s->d_rel.p;
+    a.cbv_off = s->d_cbv_off.p; a.L = s->d_L.p; a.dvec = s->d_dvec.p; a.xp = s->d_xp.p; a.cbv = s->d_cbv.p;
+    return a;
+}
+
+inline size_t smem_front(int f) { return (size_t)f * f * sizeof(double); }
+
+// issue the numeric factorisation of one phase on `st`; returns number of launches
+int64_t enqueue_factor(b2_solver* s, int ph, cudaStream_t st) {
+    FactorArgs a = factor_args(s);
+    a.counters += 2 * ph;   // [0,1] owned subtrees, [2,3] shared top tree
+    const int32_t* sched = s->d_sched.p;
+    int64_t nl = 0;
+    for (const FactorLevel& lv : s->phase[ph].flev) {
+        if (lv.nS) {
+            k_front_smem<128><<<lv.nS, 128, smem_front(lv.maxfS), st>>>(a, sched + lv.offS);
+            ++nl;
+        }
+        if (lv.nM) {
+            k_front_smem<512><<<lv.nM, 512, smem_front(lv.maxfM), st>>>(a, sched + lv.offM);
+            ++nl;
+        }
+        if (lv.nB) {
+            const int32_t* lb = sched + lv.offB;
+            const int nsm = sm_count();
+            k_big_zero<<<dim3(std::max(1, 2 * nsm / lv.nB), lv.nB), 256, 0, st>>>(a, lb);
+            k_big_scatter_A<<<dim3(std::max(1, std::min(nsm, (lv.maxamapB + 255) / 256)), lv.nB), 256, 0, st>>>(a, lb);
+            nl += 2;
+            for (int c = 0; c < lv.maxchildB; ++c) {
+                k_big_extend_add<<<dim3(std::max(1, std::min(2 * nsm / lv.nB + 1, (lv.maxrB * 32 + 255) / 256)), lv.nB), 256, 0, st>>>(a, lb, c);
+                ++nl;
+            }
+            const int nsteps = (lv.maxwB + BIG_NB - 1) / BIG_NB;
+            for (int step = 0; step < nsteps; ++step) {
+                const int kb = step * BIG_NB;
+                k_big_diag<<<lv.nB, 32, 0, st>>>(a, lb, step);
+                ++nl;
+                const int rem = lv.maxfB - kb - BIG_NB;
+                if (rem > 0) {
+                    k_big_panel<<<dim3((rem + BIG_ROWS - 1) / BIG_ROWS, lv.nB), BIG_ROWS, 0, st>>>(a, lb, step);
+                    const int nt = (rem + UT - 1) / UT;
+                    k_big_update<<<dim3(nt, nt, lv.nB), 256, 0, st>>>(a, lb, step);
+                    nl += 2;
+                }
+            }
+        }
+    }
+    return nl;
+}
+
+int64_t enqueue_solve(b2_solver* s, int ph, bool forward, cudaStream_t st) {
+    SolveArgs a = solve_args(s);
+    const int32_t* sched = s->d_sched.p;
+    int64_t nl = 0;
+    const auto& lev = s->phase[ph].slev;
+    const int nlev = (int)lev.size();
+    for (int q = 0; q < nlev; ++q) {
+        const SolveLevel& lv = forward ? lev[q] : lev[nlev - 1 - q];
+        if (lv.nW) {
+            const int grid = (lv.nW + SOLVE_WARPS - 1) / SOLVE_WARPS;
+            const size_t sm = (size_t)SOLVE_WARPS * lv.smemW * sizeof(double);
+            if (forward) k_fwd_warp<<<grid, SOLVE_WARPS * 32, sm, st>>>(a, sched + lv.offW, lv.nW, lv.smemW);
+            else k_bwd_warp<<<grid, SOLVE_WARPS * 32, sm, st>>>(a, sched + lv.offW, lv.nW, lv.smemW);
+            ++nl;
+        }
+        if (lv.nC) {
+            const size_t sm = (size_t)lv.maxfC * sizeof(double);
+            if (forward) k_fwd_cta<<<lv.nC, SOLVE_CTA, sm, st>>>(a, sched + lv.offC);
+            else k_bwd_cta<<<lv.nC, SOLVE_CTA, sm, st>>>(a, sched + lv.offC);
+            ++nl;
+        }
+    }
+    return nl;
+}
+
+int set_smem_attrs() {
+    B2_CUDA(cudaFuncSetAttribute(k_front_smem<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_front(S_MAX)));
+    B2_CUDA(cudaFuncSetAttribute(k_front_smem<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    B2_CUDA(cudaFuncSetAttribute(k_fwd_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    B2_CUDA(cudaFuncSetAttribute(k_bwd_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    B2_CUDA(cudaFuncSetAttribute(k_fwd_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    B2_CUDA(cudaFuncSetAttribute(k_bwd_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    return B2_OK;
+}
+
+// capture `fn(stream)` into an executable graph
+template <typename Fn>
+int capture(b2_solver* s, cudaGraphExec_t* out, Fn fn) {
+    if (*out) { cudaGraphExecDestroy(*out); *out = nullptr; }
+    cudaGraph_t g = nullptr;
+    B2_CUDA(cudaStreamBeginCapture(s->cap_stream, cudaStreamCaptureModeThreadLocal));
+    fn(s->cap_stream);
+    cudaError_t e = cudaStreamEndCapture(s->cap_stream, &g);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaStreamEndCapture", __FILE__, __LINE__);
+    e = cudaGraphInstantiate(out, g, 0);
+    cudaGraphDestroy(g);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaGraphInstantiate", __FILE__, __LINE__);
+    return B2_OK;
+}
+
+void build_schedule(b2_solver* s) {
+    const Symbolic& S = s->S;
+    const int ns = S.nsuper;
+    const int rank = std::max(0, s->opt.part_rank);
+    const int smax = s->opt.small_front_max;
+    std::vector<int32_t> sched;
+    for (int ph = 0; ph < 2; ++ph) {
+        Phase& P = s->phase[ph];
+        P.flev.clear(); P.slev.clear();
+        for (int l = 0; l < S.nlevels; ++l) {
+            std::vector<int32_t> Sx, Mx, Bx, Wx, Cx;
+            FactorLevel fl; SolveLevel sl;
+            for (int q = S.level_ptr[l]; q < S.level_ptr[l + 1]; ++q) {
+                const int sn = S.level_sn[q];
+                const bool mine = (ph == 0) ? (S.owner[sn] == rank) : (S.owner[sn] == -1);
+                if (!mine) continue;
+                const int w = S.sn_first[sn + 1] - S.sn_first[sn];
+                const int f = (int)(S.rows_ptr[sn + 1] - S.rows_ptr[sn]);
+                const int r = f - w;
+                const int nch = S.child_ptr[sn + 1] - S.child_ptr[sn];
+                const int nam = (int)(S.amap_ptr[sn + 1] - S.amap_ptr[sn]);
+                if (f <= S_MAX && f <= smax) { Sx.push_back(sn); fl.maxfS = std::max(fl.maxfS, f); }
+                else if (f <= smax) { Mx.push_back(sn); fl.maxfM = std::max(fl.maxfM, f); }
+                else {
+                    Bx.push_back(sn);
+                    fl.maxfB = std::max(fl.maxfB, f); fl.maxwB = std::max(fl.maxwB, w);
+                    fl.maxchildB = std::max(fl.maxchildB, nch); fl.maxamapB = std::max(fl.maxamapB, nam);
+                }
+                // children sizes for extend-add grid sizing
+                if (f > smax)
+                    for (int c = S.child_ptr[sn]; c < S.child_ptr[sn + 1]; ++c) {
+                        const int cs = S.child_idx[c];
+                        const int rc = (int)(S.rows_ptr[cs + 1] - S.rows_ptr[cs]) - (S.sn_first[cs + 1] - S.sn_first[cs]);
+                        fl.maxrB = std::max(fl.maxrB, rc);
+                    }
+                if (f <= SOLVE_WARP_MAX) { Wx.push_back(sn); sl.smemW = std::max(sl.smemW, f * w + f); }
+                else { Cx.push_back(sn); sl.maxfC = std::max(sl.maxfC, f); }
+                (void)r;
+            }
+            if (Sx.empty() && Mx.empty() && Bx.empty()) continue;
+            fl.offS = (int)sched.size(); fl.nS = (int)Sx.size(); sched.insert(sched.end(), Sx.begin(), Sx.end());
+            fl.offM = (int)sched.size(); fl.nM = (int)Mx.size(); sched.insert(sched.end(), Mx.begin(), Mx.end());
+            fl.offB = (int)sched.size(); fl.nB = (int)Bx.size(); sched.insert(sched.end(), Bx.begin(), Bx.end());
+            sl.offW = (int)sched.size(); sl.nW = (int)Wx.size(); sched.insert(sched.end(), Wx.begin(), Wx.end());
+            sl.offC = (int)sched.size(); sl.nC = (int)Cx.size(); sched.insert(sched.end(), Cx.begin(), Cx.end());
+            P.flev.push_back(fl);
+            P.slev.push_back(sl);
+        }
+    }
+    if (sched.empty()) sched.push_back(0);
+    B2_CUDA_THROW(s->d_sched.upload(sched.data(), sched.size()));
+    (void)ns;
+}
+
+int create_common(int32_t n, int64_t nnz, const int32_t* colptr_h, const int32_t* rowval_h, const double* nzval_d,
+                  const b2_options* opt, const int32_t* user_perm_h, bool symbolic_only, b2_solver** out) {
+    if (!out || !colptr_h || !rowval_h || n <= 0) { set_error("b2_create: invalid argument"); return B2_ERR_INVALID; }
+    if (colptr_h[n] != nnz) { set_error("b2_create: colptr[n] != nnz"); return B2_ERR_INVALID; }
+    b2_solver* s = new b2_solver();
+    if (opt) s->opt = *opt; else b2_options_default(&s->opt);
+    s->symbolic_only = symbolic_only;
+    s->nzval_d = nzval_d;
+    if (s->opt.small_front_max < 8) s->opt.small_front_max = 8;
+    if (s->opt.small_front_max > 168) s->opt.small_front_max = 168;
+    try {
+        AnalysisOptions ao;
+        ao.ordering = s->opt.ordering; ao.nemin = s->opt.nemin; ao.relax_zeros = s->opt.relax_zeros;
+        ao.n_parts = std::max(1, s->opt.n_parts);
+        analyse(n, colptr_h, rowval_h, ao, user_perm_h, s->S);
+    } catch (std::exception& e) {
+        set_error(std::string("b2_create: analysis failed: ") + e.what());
+        delete s;
+        return B2_ERR_SYMBOLIC;
+    }
+    const Symbolic& S = s->S;
+    const int ns = S.nsuper;
+    // contribution-vector offsets: blocks crossing into the shared top tree first (exchange region)
+    {
+        s->cbv_off.assign(ns + 1, 0);
+        int64_t off = 0;
+        const bool multi = s->opt.n_parts > 1;
+        for (int pass = 0; pass < 2; ++pass) {
+            for (int sn = 0; sn < ns; ++sn) {
+                const int p = S.sn_parent[sn];
+                const bool boundary = multi && S.owner[sn] >= 0 && p >= 0 && S.owner[p] == -1;
+                if ((pass == 0) != boundary) continue;
+                s->cbv_off[sn] = off;
+                off += S.rel_ptr[sn + 1] - S.rel_ptr[sn];
+            }
+            if (pass == 0) s->exch_cbv = off;
+        }
+        s->cbv_off[ns] = off;
+    }
+    // rows this rank finalises in the back-substitution (multi-GPU); rank 0 also reports the top tree
+    {
+        s->owned_mask.assign(n, 1);
+        if (s->opt.n_parts > 1) {
+            const int rank = s->opt.part_rank;
+            for (int sn = 0; sn < ns; ++sn) {
+                const bool mine = S.owner[sn] == rank || (S.owner[sn] == -1 && rank == 0);
+                for (int j = S.sn_first[sn]; j < S.sn_first[sn + 1]; ++j) s->owned_mask[S.perm[j]] = mine ? 1 : 0;
+            }
+        }
+    }
+    if (symbolic_only) { *out = s; return B2_OK; }
+
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        set_error("b2_create: no CUDA device (this library has no CPU fallback)");
+        delete s;
+        return B2_ERR_NO_DEVICE;
+    }
+    cudaGetDevice(&s->device);
+    try {
+        std::vector<FrontDesc> desc(ns);
+        for (int sn = 0; sn < ns; ++sn) {
+            FrontDesc& d = desc[sn];
+            d.col0 = S.sn_first[sn];
+            d.w = S.sn_first[sn + 1] - S.sn_first[sn];
+            d.f = (int)(S.rows_ptr[sn + 1] - S.rows_ptr[sn]);
+            d.nchild = S.child_ptr[sn + 1] - S.child_ptr[sn];
+            d.child_off = S.child_ptr[sn];
+            d.amap_cnt = (int)(S.amap_ptr[sn + 1] - S.amap_ptr[sn]);
+            d.rows_off = S.rows_ptr[sn];
+            d.lp_off = S.lp_off[sn];
+            d.cb_off = S.cb_off[sn];
+            d.rel_off = S.rel_ptr[sn];
+            d.amap_off = S.amap_ptr[sn];
+        }
+        std::vector<int32_t> asrc(S.amap_src.size()), adst(S.amap_dst.size());
+        for (int sn = 0; sn < ns; ++sn)
+            for (int64_t q = S.amap_ptr[sn]; q < S.amap_ptr[sn + 1]; ++q) {
+                asrc[q] = (int32_t)S.amap_src[q];
+                adst[q] = (int32_t)(S.amap_dst[q] - S.lp_off[sn]);
+            }
+        std::vector<uint8_t> mask_p(n);
+        for (int j = 0; j < n; ++j) mask_p[j] = s->owned_mask[S.perm[j]];
+        B2_CUDA_THROW(s->d_desc.upload(desc.data(), desc.size()));
+        B2_CUDA_THROW(s->d_rows.upload(S.rows.data(), S.rows.size()));
+        B2_CUDA_THROW(s->d_child_idx.upload(S.child_idx.data(), S.child_idx.size()));
+        B2_CUDA_THROW(s->d_rel.upload(S.rel.data(), S.rel.size()));
+        B2_CUDA_THROW(s->d_amap_src.upload(asrc.data(), asrc.size()));
+        B2_CUDA_THROW(s->d_amap_dst.upload(adst.data(), adst.size()));
+        B2_CUDA_THROW(s->d_perm.upload(S.perm.data(), S.perm.size()));
+        B2_CUDA_THROW(s->d_cbv_off.upload(s->cbv_off.data(), s->cbv_off.size()));
+        B2_CUDA_THROW(s->d_mask_p.upload(mask_p.data(), mask_p.size()));
+        B2_CUDA_THROW(s->d_L.alloc((size_t)S.lp_off[ns]));
+        B2_CUDA_THROW(s->d_ws.alloc((size_t)std::max<int64_t>(1, S.cb_off[ns])));
+        B2_CUDA_THROW(s->d_dvec.alloc(n));
+        B2_CUDA_THROW(s->d_xp.alloc(n));
+        B2_CUDA_THROW(s->d_cbv.alloc((size_t)std::max<int64_t>(1, s->cbv_off[ns])));
+        B2_CUDA_THROW(s->d_counters.alloc(4));
+        B2_CUDA_THROW(cudaMemset(s->d_counters.p, 0, 4 * sizeof(int32_t)));
+        B2_CUDA_THROW(cudaMemset(s->d_ws.p, 0, s->d_ws.bytes()));
+        B2_CUDA_THROW(cudaMemset(s->d_cbv.p, 0, s->d_cbv.bytes()));
+        B2_CUDA_THROW(cudaMallocHost((void**)&s->h_counters, 4 * sizeof(int32_t)));
+        B2_CUDA_THROW(cudaStreamCreateWithFlags(&s->cap_stream, cudaStreamNonBlocking));
+        build_schedule(s);
+        if (set_smem_attrs() != B2_OK) throw std::runtime_error("attr");
+    } catch (std::exception&) {
+        delete s;
+        return B2_ERR_CUDA;
+    }
+    *out = s;
+    return B2_OK;
+}
+
+int run_factor_phase(b2_solver* s, int ph, cudaStream_t st) {
+    Phase& P = s->phase[ph];
+    if (s->opt.use_cuda_graph) {
+        if (!P.g_factor) {
+            int rc = capture(s, &P.g_factor, [&](cudaStream_t cs) { P.n_factor_launches = enqueue_factor(s, ph, cs); });
+            if (rc != B2_OK) return rc;
+        }
+        B2_CUDA(cudaGraphLaunch(P.g_factor, st));
+    } else {
+        P.n_factor_launches = enqueue_factor(s, ph, st);
+        B2_CUDA(cudaGetLastError());
+    }
+    return B2_OK;
+}
+
+int run_solve_phase(b2_solver* s, int ph, bool fwd, cudaStream_t st) {
+    Phase& P = s->phase[ph];
+    cudaGraphExec_t* g = fwd ? &P.g_fwd : &P.g_bwd;
+    if (s->opt.use_cuda_graph) {
+        if (!*g) {
+            int64_t nl = 0;
+            int rc = capture(s, g, [&](cudaStream_t cs) { nl = enqueue_solve(s, ph, fwd, cs); });
+            if (rc != B2_OK) return rc;
+            if (fwd) P.n_solve_launches = 2 * nl;
+        }
+        B2_CUDA(cudaGraphLaunch(*g, st));
+    } else {
+        int64_t nl = enqueue_solve(s, ph, fwd, st);
+        if (fwd) P.n_solve_launches = 2 * nl;
+        B2_CUDA(cudaGetLastError());
+    }
+    return B2_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int b2_options_default(b2_options* opt) {
+    if (!opt) return B2_ERR_INVALID;
+    std::memset(opt, 0, sizeof(*opt));
+    opt->ordering = B2_ORDER_METIS_ND;
+    opt->nemin = 16;
+    opt->relax_zeros = 0.25;
+    opt->pivot_eps = 1e-13;
+    opt->use_cuda_graph = 1;
+    opt->small_front_max = 160;
+    opt->n_parts = 1;
+    opt->part_rank = 0;
+    return B2_OK;
+}
+
+int b2_create(int32_t n, int64_t nnz, const int32_t* colptr_h, const int32_t* rowval_h, const double* nzval_d,
+              const b2_options* opt, const int32_t* user_perm_h, b2_solver** out) {
+    return create_common(n, nnz, colptr_h, rowval_h, nzval_d, opt, user_perm_h, false, out);
+}
+
+int b2_create_symbolic_only(int32_t n, int64_t nnz, const int32_t* colptr_h, const int32_t* rowval_h,
+                            const b2_options* opt, const int32_t* user_perm_h, b2_solver** out) {
+    return create_common(n, nnz, colptr_h, rowval_h, nullptr, opt, user_perm_h, true, out);
+}
+
+int b2_destroy(b2_solver* s) {
+    delete s;
+    return B2_OK;
+}
+
+int b2_set_values_ptr(b2_solver* s, const double* nzval_d) {
+    if (!s) return B2_ERR_INVALID;
+    if (nzval_d != s->nzval_d) {
+        s->nzval_d = nzval_d;
+        for (auto& p : s->phase)
+            if (p.g_factor) { cudaGraphExecDestroy(p.g_factor); p.g_factor = nullptr; }   // pointer is baked into the graph
+    }
+    return B2_OK;
+}
+
+int b2_factorize_local(b2_solver* s, void* stream) {
+    if (!s || s->symbolic_only) { set_error("b2_factorize: solver has no device state"); return B2_ERR_INVALID; }
+    if (!s->nzval_d) { set_error("b2_factorize: value pointer not set"); return B2_ERR_INVALID; }
+    cudaStream_t st = as_stream(stream);
+    B2_CUDA(cudaMemsetAsync(s->d_counters.p, 0, 4 * sizeof(int32_t), st));
+    if (s->opt.n_parts > 1 && s->S.exch_cb > 0) B2_CUDA(cudaMemsetAsync(s->d_ws.p, 0, (size_t)s->S.exch_cb * sizeof(double), st));
+    return run_factor_phase(s, 0, st);
+}
+
+int b2_factorize_top(b2_solver* s, void* stream) {
+    if (!s || s->symbolic_only) return B2_ERR_INVALID;
+    int rc = run_factor_phase(s, 1, as_stream(stream));
+    if (rc == B2_OK) s->factorized = true;
+    return rc;
+}
+
+int b2_factorize(b2_solver* s, void* stream) {
+    int rc = b2_factorize_local(s, stream);
+    if (rc != B2_OK) return rc;
+    if (s->opt.n_parts > 1) { set_error("b2_factorize: multi-part solver needs factorize_local/exchange/factorize_top"); return B2_ERR_INVALID; }
+    s->factorized = true;
+    return B2_OK;
+}
+
+int b2_inertia(b2_solver* s, int64_t* num_pos, int64_t* num_zero, int64_t* num_neg, void* stream) {
+    if (!s || s->symbolic_only || !s->factorized) { set_error("b2_inertia: not factorized"); return B2_ERR_FACTORIZATION; }
+    cudaStream_t st = as_stream(stream);
+    B2_CUDA(cudaMemcpyAsync(s->h_counters, s->d_counters.p, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    B2_CUDA(cudaStreamSynchronize(st));
+    // single-part: everything is in the "local" phase.  Multi-part: this is only this rank's view; the host layer
+    // all-reduces b2_inertia_parts() instead.
+    const int64_t neg = (int64_t)s->h_counters[0] + s->h_counters[2], zero = (int64_t)s->h_counters[1] + s->h_counters[3];
+    s->last_perturbed = zero;
+    if (num_neg) *num_neg = neg;
+    if (num_zero) *num_zero = zero;
+    if (num_pos) *num_pos = (int64_t)s->S.n - neg - zero;
+    return B2_OK;
+}
+
+int b2_inertia_parts(b2_solver* s, int64_t* local_neg, int64_t* local_zero, int64_t* top_neg, int64_t* top_zero, void* stream) {
+    if (!s || s->symbolic_only || !s->factorized) { set_error("b2_inertia_parts: not factorized"); return B2_ERR_FACTORIZATION; }
+    cudaStream_t st = as_stream(stream);
+    B2_CUDA(cudaMemcpyAsync(s->h_counters, s->d_counters.p, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    B2_CUDA(cudaStreamSynchronize(st));
+    if (local_neg) *local_neg = s->h_counters[0];
+    if (local_zero) *local_zero = s->h_counters[1];
+    if (top_neg) *top_neg = s->h_counters[2];
+    if (top_zero) *top_zero = s->h_counters[3];
+    return B2_OK;
+}
+
+int b2_solve_fwd_local(b2_solver* s, double* x_d, void* stream) {
+    if (!s || s->symbolic_only || !x_d) return B2_ERR_INVALID;
+    if (!s->factorized) { set_error("b2_solve: not factorized"); return B2_ERR_SOLVE; }
+    cudaStream_t st = as_stream(stream);
+    const int n = s->S.n;
+    const int grid = std::min(4 * sm_count(), (n + 255) / 256);
+    k_perm_in<<<grid, 256, 0, st>>>(n, s->d_perm.p, x_d, s->d_xp.p);
+    if (s->opt.n_parts > 1 && s->exch_cbv > 0) B2_CUDA(cudaMemsetAsync(s->d_cbv.p, 0, (size_t)s->exch_cbv * sizeof(double), st));
+    return run_solve_phase(s, 0, true, st);
+}
+
+int b2_solve_top(b2_solver* s, double* x_d, void* stream) {
+    if (!s || s->symbolic_only) return B2_ERR_INVALID;
+    (void)x_d;
+    int rc = run_solve_phase(s, 1, true, as_stream(stream));
+    if (rc != B2_OK) return rc;
+    return run_solve_phase(s, 1, false, as_stream(stream));
+}
+
+int b2_solve_bwd_local(b2_solver* s, double* x_d, void* stream) {
+    if (!s || s->symbolic_only || !x_d) return B2_ERR_INVALID;
+    cudaStream_t st = as_stream(stream);
+    int rc = run_solve_phase(s, 0, false, st);
+    if (rc != B2_OK) return rc;
+    const int n = s->S.n;
+    const int grid = std::min(4 * sm_count(), (n + 255) / 256);
+    if (s->opt.n_parts > 1) k_perm_out_masked<<<grid, 256, 0, st>>>(n, s->d_perm.p, s->d_mask_p.p, s->d_xp.p, x_d);
+    else k_perm_out<<<grid, 256, 0, st>>>(n, s->d_perm.p, s->d_xp.p, x_d);
+    B2_CUDA(cudaGetLastError());
+    return B2_OK;
+}
+
+int b2_solve(b2_solver* s, double* x_d, int32_t nrhs, void* stream) {
+    if (!s || s->symbolic_only || !x_d || nrhs < 1) { set_error("b2_solve: invalid argument"); return B2_ERR_INVALID; }
+    if (s->opt.n_parts > 1) { set_error("b2_solve: multi-part solver needs the phased solve"); return B2_ERR_INVALID; }
+    for (int c = 0; c < nrhs; ++c) {
+        double* x = x_d + (size_t)c * s->S.n;
+        int rc = b2_solve_fwd_local(s, x, stream);
+        if (rc != B2_OK) return rc;
+        rc = b2_solve_bwd_local(s, x, stream);
+        if (rc != B2_OK) return rc;
+    }
+    return B2_OK;
+}
+
+int b2_improve(b2_solver* s, int32_t* changed) {
+    if (!s) return B2_ERR_INVALID;
+    // Static pivoting has one knob: the perturbation threshold.  Raise it (like ma97's u -> u^0.75, ma97.jl:103-111)
+    // up to 1e-8; the caller re-factorises.
+    int32_t ch = 0;
+    if (s->opt.pivot_eps < 1e-8) {
+        s->opt.pivot_eps = std::min(1e-8, std::max(s->opt.pivot_eps * 100.0, 1e-13));
+        for (auto& p : s->phase)
+            if (p.g_factor) { cudaGraphExecDestroy(p.g_factor); p.g_factor = nullptr; }
+        ch = 1;
+    }
+    if (changed) *changed = ch;
+    return B2_OK;
+}
+
+int b2_get_stats(b2_solver* s, b2_stats* st) {
+    if (!s || !st) return B2_ERR_INVALID;
+    std::memset(st, 0, sizeof(*st));
+    const Symbolic& S = s->S;
+    st->n = S.n; st->nnz_a = S.nnz_a; st->nnz_l = S.nnz_l; st->flops = S.flops;
+    st->n_supernodes = S.nsuper; st->n_levels = S.nlevels; st->max_front = S.max_front;
+    const int smax = s->opt.small_front_max;
+    for (int sn = 0; sn < S.nsuper; ++sn) {
+        const int f = (int)(S.rows_ptr[sn + 1] - S.rows_ptr[sn]);
+        if (f <= smax) st->n_small_fronts++; else st->n_big_fronts++;
+    }
+    st->factor_bytes = (int64_t)S.lp_off[S.nsuper] * 8;
+    st->workspace_bytes = (int64_t)(S.cb_off[S.nsuper] + s->cbv_off[S.nsuper]) * 8;
+    st->sep_rows = S.top_rows;
+    st->n_factor_launches = s->phase[0].n_factor_launches + s->phase[1].n_factor_launches;
+    st->n_solve_launches = s->phase[0].n_solve_launches + s->phase[1].n_solve_launches;
+    st->n_perturbed = s->last_perturbed;
+    return B2_OK;
+}
+
+int b2_get_perm(b2_solver* s, int32_t* perm_h) {
+    if (!s || !perm_h) return B2_ERR_INVALID;
+    std::memcpy(perm_h, s->S.perm.data(), (size_t)s->S.n * sizeof(int32_t));
+    return B2_OK;
+}
+
+int b2_exchange_buffer(b2_solver* s, double** buf_d, int64_t* n_factor_doubles, int64_t* n_solve_doubles) {
+    if (!s || s->symbolic_only) return B2_ERR_INVALID;
+    if (buf_d) *buf_d = s->d_ws.p;
+    if (n_factor_doubles) *n_factor_doubles = s->S.exch_cb;
+    if (n_solve_doubles) *n_solve_doubles = s->exch_cbv;
+    return B2_OK;
+}
+
+int b2_exchange_vector(b2_solver* s, double** buf_d, int64_t* n_doubles) {
+    if (!s || s->symbolic_only) return B2_ERR_INVALID;
+    if (buf_d) *buf_d = s->d_cbv.p;
+    if (n_doubles) *n_doubles = s->exch_cbv;
+    return B2_OK;
+}
+
+int b2_owned_mask(b2_solver* s, uint8_t* owned_h) {
+    if (!s || !owned_h) return B2_ERR_INVALID;
+    std::memcpy(owned_h, s->owned_mask.data(), s->owned_mask.size());
+    return B2_OK;
+}
+
+int b2_symbolic_query(b2_solver* s, b2_symbolic_sizes* sz) {
+    if (!s || !sz) return B2_ERR_INVALID;
+    const Symbolic& S = s->S;
+    sz->n = S.n; sz->n_supernodes = S.nsuper; sz->n_rows = (int64_t)S.rows.size();
+    sz->n_children = (int64_t)S.child_idx.size(); sz->n_rel = (int64_t)S.rel.size();
+    sz->n_amap = (int64_t)S.amap_src.size(); sz->n_levels = S.nlevels;
+    sz->lval_size = S.lp_off[S.nsuper]; sz->cb_size = S.cb_off[S.nsuper];
+    return B2_OK;
+}
+
+int b2_symbolic_export(b2_solver* s, int32_t* perm, int32_t* sn_first, int32_t* sn_parent, int32_t* sn_level,
+                       int64_t* rows_ptr, int32_t* rows, int64_t* lp_off, int64_t* cb_off,
+                       int64_t* rel_ptr, int32_t* rel, int64_t* amap_ptr, int64_t* amap_src, int64_t* amap_dst) {
+    if (!s) return B2_ERR_INVALID;
+    const Symbolic& S = s->S;
+    auto cp = [](auto* dst, const auto& v) { if (dst) std::memcpy(dst, v.data(), v.size() * sizeof(v[0])); };
+    cp(perm, S.perm); cp(sn_first, S.sn_first); cp(sn_parent, S.sn_parent); cp(sn_level, S.sn_level);
+    cp(rows_ptr, S.rows_ptr); cp(rows, S.rows); cp(lp_off, S.lp_off); cp(cb_off, S.cb_off);
+    cp(rel_ptr, S.rel_ptr); cp(rel, S.rel); cp(amap_ptr, S.amap_ptr); cp(amap_src, S.amap_src); cp(amap_dst, S.amap_dst);
+    return B2_OK;
+}
+
+int b2_symbolic_owner(b2_solver* s, int32_t* owner) {
+    if (!s || !owner) return B2_ERR_INVALID;
+    std::memcpy(owner, s->S.owner.data(), s->S.owner.size() * sizeof(int32_t));
+    return B2_OK;
+}
+
+}  // extern "C"
+
+// =========================================================================================================
+// b2d_*: dense LDL^T (DenseCondensedKKTSystem back-end; replaces cusolverDnDsytrf/Xsytrs, cusolver.jl:150-187,
+// and dsytrf/dsytrs, src/LinearSolvers/lapack.jl:164-172).  The dense matrix is one "big front" with w = f = N:
+// the same blocked right-looking kernels (k_big_diag / k_big_panel / k_big_update with the DMMA trailing update).
+// =========================================================================================================
+struct b2d_solver {
+    int32_t N = 0, lda = 0;
+    const double* A_d = nullptr;
+    b2_options opt;
+    DevBuf<double> fact, dvec;
+    DevBuf<FrontDesc> desc;
+    DevBuf<int32_t> list, counters;
+    int32_t* h_counters = nullptr;
+    cudaGraphExec_t g_factor = nullptr;
+    cudaStream_t cap_stream = nullptr;
+    bool factorized = false;
+    ~b2d_solver() {
+        if (g_factor) cudaGraphExecDestroy(g_factor);
+        if (cap_stream) cudaStreamDestroy(cap_stream);
+        if (h_counters) cudaFreeHost(h_counters);
+    }
+};
+
+namespace {
+__global__ void k_copy_lower(int N, int lda, const double* __restrict__ A, double* __restrict__ F) {
+    const int j = blockIdx.y;
+    for (int i = j + blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x)
+        F[(size_t)j * N + i] = A[(size_t)j * lda + i];
+}
+
+void enqueue_dense_factor(b2d_solver* s, cudaStream_t st) {
+    FactorArgs a;
+    a.desc = s->desc.p; a.child_idx = nullptr; a.rel = nullptr; a.amap_src = nullptr; a.amap_dst = nullptr;
+    a.A = nullptr; a.L = s->fact.p; a.ws = nullptr; a.dvec = s->dvec.p; a.counters = s->counters.p; a.eps = s->opt.pivot_eps;
+    const int N = s->N;
+    cudaMemsetAsync(s->counters.p, 0, 4 * sizeof(int32_t), st);
+    k_copy_lower<<<dim3(std::max(1, std::min(8, (N + 255) / 256)), N), 256, 0, st>>>(N, s->lda, s->A_d, s->fact.p);
+    const int nsteps = (N + BIG_NB - 1) / BIG_NB;
+    for (int step = 0; step < nsteps; ++step) {
+        const int kb = step * BIG_NB;
+        k_big_diag<<<1, 32, 0, st>>>(a, s->list.p, step);
+        const int rem = N - kb - BIG_NB;
+        if (rem > 0) {
+            k_big_panel<<<dim3((rem + BIG_ROWS - 1) / BIG_ROWS, 1), BIG_ROWS, 0, st>>>(a, s->list.p, step);
+            const int nt = (rem + UT - 1) / UT;
+            k_big_update<<<dim3(nt, nt, 1), 256, 0, st>>>(a, s->list.p, step);
+        }
+    }
+}
+}  // namespace
+
+extern "C" {
+
+int b2d_create(int32_t N, int32_t lda, const double* A_d, const b2_options* opt, b2d_solver** out) {
+    if (!out || N <= 0 || lda < N || !A_d) { set_error("b2d_create: invalid argument"); return B2_ERR_INVALID; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        set_error("b2d_create: no CUDA device (this library has no CPU fallback)");
+        return B2_ERR_NO_DEVICE;
+    }
+    auto* s = new b2d_solver();
+    s->N = N; s->lda = lda; s->A_d = A_d;
+    if (opt) s->opt = *opt; else b2_options_default(&s->opt);
+    FrontDesc d;
+    std::memset(&d, 0, sizeof(d));
+    d.col0 = 0; d.w = N; d.f = N;
+    int32_t zero = 0;
+    if (s->fact.alloc((size_t)N * N) != cudaSuccess || s->dvec.alloc(N) != cudaSuccess || s->desc.upload(&d, 1) != cudaSuccess ||
+        s->list.upload(&zero, 1) != cudaSuccess || s->counters.alloc(4) != cudaSuccess ||
+        cudaMallocHost((void**)&s->h_counters, 4 * sizeof(int32_t)) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&s->cap_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaMemset(s->fact.p, 0, s->fact.bytes()) != cudaSuccess) {
+        delete s;
+        return cuda_fail(cudaGetLastError(), "b2d_create allocation", __FILE__, __LINE__);
+    }
+    if (set_smem_attrs() != B2_OK) { delete s; return B2_ERR_CUDA; }
+    *out = s;
+    return B2_OK;
+}
+
+int b2d_destroy(b2d_solver* s) { delete s; return B2_OK; }
+
+int b2d_factorize(b2d_solver* s, void* stream) {
+    if (!s) return B2_ERR_INVALID;
+    cudaStream_t st = as_stream(stream);
+    if (s->opt.use_cuda_graph) {
+        if (!s->g_factor) {
+            cudaGraph_t g = nullptr;
+            B2_CUDA(cudaStreamBeginCapture(s->cap_stream, cudaStreamCaptureModeThreadLocal));
+            enqueue_dense_factor(s, s->cap_stream);
+            cudaError_t e = cudaStreamEndCapture(s->cap_stream, &g);
+            if (e != cudaSuccess) return cuda_fail(e, "cudaStreamEndCapture", __FILE__, __LINE__);
+            e = cudaGraphInstantiate(&s->g_factor, g, 0);
+            cudaGraphDestroy(g);
+            if (e != cudaSuccess) return cuda_fail(e, "cudaGraphInstantiate", __FILE__, __LINE__);
+        }
+        B2_CUDA(cudaGraphLaunch(s->g_factor, st));
+    } else {
+        enqueue_dense_factor(s, st);
+        B2_CUDA(cudaGetLastError());
+    }
+    s->factorized = true;
+    return B2_OK;
+}
+
+int b2d_inertia(b2d_solver* s, int64_t* num_pos, int64_t* num_zero, int64_t* num_neg, void* stream) {
+    if (!s || !s->factorized) { set_error("b2d_inertia: not factorized"); return B2_ERR_FACTORIZATION; }
+    cudaStream_t st = as_stream(stream);
+    B2_CUDA(cudaMemcpyAsync(s->h_counters, s->counters.p, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    B2_CUDA(cudaStreamSynchronize(st));
+    const int64_t neg = s->h_counters[0], zero = s->h_counters[1];
+    if (num_neg) *num_neg = neg;
+    if (num_zero) *num_zero = zero;
+    if (num_pos) *num_pos = (int64_t)s->N - neg - zero;
+    return B2_OK;
+}
+
+int b2d_solve(b2d_solver* s, double* x_d, int32_t nrhs, void* stream) {
+    if (!s || !x_d || nrhs < 1) { set_error("b2d_solve: invalid argument"); return B2_ERR_INVALID; }
+    if (!s->factorized) { set_error("b2d_solve: not factorized"); return B2_ERR_SOLVE; }
+    cudaStream_t st = as_stream(stream);
+    for (int c = 0; c < nrhs; ++c) {
+        SolveArgs a;
+        a.desc = s->desc.p; a.rows = nullptr; a.child_idx = nullptr; a.rel = nullptr; a.cbv_off = nullptr;
+        a.L = s->fact.p; a.dvec = s->dvec.p; a.xp = x_d + (size_t)c * s->N; a.cbv = nullptr;
+        const size_t sm = (size_t)s->N * sizeof(double);
+        k_fwd_cta<<<1, SOLVE_CTA, sm, st>>>(a, s->list.p);
+        k_bwd_cta<<<1, SOLVE_CTA, sm, st>>>(a, s->list.p);
+    }
+    B2_CUDA(cudaGetLastError());
+    return B2_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,845 @@
+"""CPU ORACLE -- TEST INFRASTRUCTURE ONLY.
+
+A numpy/scipy restatement of MadNLP's per-iteration KKT hot path (assembly ->
+symmetric-indefinite factorisation + inertia -> solve), used ONLY as the checker
+in ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
+``--impl reference`` legs.  Nothing in the product package (``madnlp.jl_b200/``)
+imports this file; the product path fails loudly when the CUDA library is missing.
+
+Every function cites the reference file:line (relative to the MadNLP.jl tree
+@ e1028096, v0.10.1) it follows.  Indices are 0-based here (the reference is
+1-based); value layouts are identical.
+
+Pinned against (tests/test_oracle_golden.py):
+  * the reference's only known-answer vector for factor+solve
+    (lib/MadNLPTests/src/MadNLPTests.jl:24-51): 2x2 system, x = [0.85427.., 1.45728..],
+    inertia (2,0,0);
+  * the reference's self-consistency identity ``K * solve_kkt(K, 1) == 1`` +
+    ``is_inertia_correct`` on HS15 for every KKT formulation
+    (lib/MadNLPTests/src/MadNLPTests.jl:53-110, test/kkt_test.jl:27-48);
+  * the HS15 worked example of SURVEY.md Appendix A.
+Beyond these the reference holds no golden numbers for this path (factor/solve
+arithmetic lives in LAPACK/UMFPACK binaries outside the tree): step directions on
+the larger configurations are "parity unpinned" by the reference and defined by
+this oracle (LAPACK ``dsytrf/dsytrs`` through scipy -- the same routine
+``LapackCPUSolver`` calls, src/LinearSolvers/lapack.jl:164-172 -- and SuperLU
+standing in for UMFPACK's unsymmetric LU, src/LinearSolvers/umfpack.jl:28-55).
+"""
+from __future__ import annotations
+
+import numpy as np
+import scipy.linalg.lapack as _lapack
+import scipy.sparse as sp
+import scipy.sparse.linalg as spla
+
+
+# --------------------------------------------------------------------------
+# matrix tools  (src/matrixtools.jl)
+# --------------------------------------------------------------------------
+def force_lower_triangular(I, J):
+    """src/matrixtools.jl:129-137 -- swap (i,j) so that i >= j, in place."""
+    sw = J > I
+    tmp = J[sw].copy()
+    J[sw] = I[sw]
+    I[sw] = tmp
+
+
+def coo_to_csc(I, J, m, n):
+    """src/matrixtools.jl:55-95.
+
+    Returns (colptr, rowval, map) with ``map[k]`` = position in the CSC value
+    vector of COO entry k.  Duplicates share a slot (``sparse()`` sums them) and
+    rows are sorted inside each column, exactly as Julia's ``sparse(I,J,V)``.
+    """
+    I = np.asarray(I, dtype=np.int64)
+    J = np.asarray(J, dtype=np.int64)
+    key = J * m + I
+    ukey, inv = np.unique(key, return_inverse=True)
+    rowval = (ukey % m).astype(np.int32)
+    cols = ukey // m
+    colptr = np.zeros(n + 1, dtype=np.int32)
+    np.add.at(colptr, cols + 1, 1)
+    colptr = np.cumsum(colptr).astype(np.int32)
+    return colptr, rowval, inv.astype(np.int64)
+
+
+def transfer(nz, V, cmap):
+    """src/matrixtools.jl:79-88 -- ``nz .= 0; nz[map[k]] += V[k]`` in COO order."""
+    nz[:] = 0.0
+    np.add.at(nz, cmap, V)
+    return nz
+
+
+def csc_to_scipy(colptr, rowval, nz, shape):
+    return sp.csc_matrix((nz, rowval, colptr), shape=shape)
+
+
+def tril_to_full(colptr, rowval, nz, n):
+    """src/matrixtools.jl:40-46 / umfpack.jl:28-35 -- symmetric expansion."""
+    L = csc_to_scipy(colptr, rowval, nz, (n, n))
+    return (L + sp.tril(L, -1).T).tocsc()
+
+
+# --------------------------------------------------------------------------
+# callback stand-in: only the fields the KKT constructors read
+# (src/Callbacks/nlpmodels.jl:369-406)
+# --------------------------------------------------------------------------
+class Callback:
+    def __init__(self, nvar, ncon, jac_I, jac_J, hess_I, hess_J,
+                 ind_ineq, ind_lb, ind_ub):
+        self.nvar = int(nvar)
+        self.ncon = int(ncon)
+        self.jac_I = np.asarray(jac_I, dtype=np.int64)
+        self.jac_J = np.asarray(jac_J, dtype=np.int64)
+        self.hess_I = np.asarray(hess_I, dtype=np.int64)
+        self.hess_J = np.asarray(hess_J, dtype=np.int64)
+        self.ind_ineq = np.asarray(ind_ineq, dtype=np.int64)
+        all_c = np.arange(self.ncon)
+        self.ind_eq = np.setdiff1d(all_c, self.ind_ineq)
+        self.ind_lb = np.asarray(ind_lb, dtype=np.int64)
+        self.ind_ub = np.asarray(ind_ub, dtype=np.int64)
+        self.nnzj = len(self.jac_I)
+        self.nnzh = len(self.hess_I)
+
+
+# --------------------------------------------------------------------------
+# UnreducedKKTVector  (src/KKT/rhs.jl:90-129)
+# --------------------------------------------------------------------------
+class UnreducedKKTVector:
+    """values = [x (n_tot) | y (m) | zl (nlb) | zu (nub)], all views of one buffer."""
+
+    def __init__(self, n, m, nlb, nub, ind_lb, ind_ub):
+        self.values = np.zeros(n + m + nlb + nub)
+        self.n, self.m, self.nlb, self.nub = n, m, nlb, nub
+        self.ind_lb, self.ind_ub = ind_lb, ind_ub
+
+    @classmethod
+    def for_kkt(cls, kkt):
+        return cls(len(kkt.pr_diag), len(kkt.du_diag), len(kkt.l_diag),
+                   len(kkt.u_diag), kkt.ind_lb, kkt.ind_ub)
+
+    def full(self):
+        return self.values
+
+    def primal(self):
+        return self.values[: self.n]
+
+    def dual(self):
+        return self.values[self.n: self.n + self.m]
+
+    def primal_dual(self):
+        return self.values[: self.n + self.m]
+
+    def dual_lb(self):
+        return self.values[self.n + self.m: self.n + self.m + self.nlb]
+
+    def dual_ub(self):
+        return self.values[self.n + self.m + self.nlb:]
+
+    def copy(self):
+        o = UnreducedKKTVector(self.n, self.m, self.nlb, self.nub, self.ind_lb, self.ind_ub)
+        o.values[:] = self.values
+        return o
+
+
+# --------------------------------------------------------------------------
+# generic KKT pieces  (src/KKT/KKTsystem.jl:210-256, src/IPM/kernels.jl)
+# --------------------------------------------------------------------------
+def set_aug_diagonal_(kkt):
+    """src/IPM/kernels.jl:22-27  (_set_aug_diagonal!)."""
+    kkt.pr_diag[:] = kkt.reg
+    kkt.pr_diag[kkt.ind_lb] -= kkt.l_lower / kkt.l_diag
+    kkt.pr_diag[kkt.ind_ub] -= kkt.u_lower / kkt.u_diag
+
+
+def regularize_diagonal(kkt, primal, dual):
+    """src/KKT/KKTsystem.jl:222-226."""
+    kkt.reg += primal
+    kkt.pr_diag += primal
+    kkt.du_diag -= dual
+
+
+def reduce_rhs(kkt, d):
+    """src/IPM/kernels.jl:182-195."""
+    xp = d.primal()
+    xp[kkt.ind_lb] -= d.dual_lb() / kkt.l_diag
+    xp[kkt.ind_ub] -= d.dual_ub() / kkt.u_diag
+
+
+def finish_aug_solve(kkt, d):
+    """src/IPM/kernels.jl:198-204."""
+    xp = d.primal()
+    dlb = d.dual_lb()
+    dub = d.dual_ub()
+    dlb[:] = (-dlb + kkt.l_lower * xp[kkt.ind_lb]) / kkt.l_diag
+    dub[:] = (dub - kkt.u_lower * xp[kkt.ind_ub]) / kkt.u_diag
+
+
+def kktmul_(w, x, kkt, alpha, beta):
+    """src/IPM/kernels.jl:161-180  (_kktmul!)."""
+    w.primal()[:] += alpha * kkt.reg * x.primal()
+    w.dual()[:] += alpha * kkt.du_diag * x.dual()
+    wp = w.primal()
+    wp[kkt.ind_lb] -= alpha * x.dual_lb()
+    wp[kkt.ind_ub] += alpha * x.dual_ub()
+    xp = x.primal()
+    w.dual_lb()[:] = beta * w.dual_lb() + alpha * (xp[kkt.ind_lb] * kkt.l_lower - x.dual_lb() * kkt.l_diag)
+    w.dual_ub()[:] = beta * w.dual_ub() + alpha * (xp[kkt.ind_ub] * kkt.u_lower + x.dual_ub() * kkt.u_diag)
+
+
+def is_inertia_correct_default(kkt, num_pos, num_zero, num_neg):
+    """src/KKT/KKTsystem.jl:242-244."""
+    return num_zero == 0 and num_pos == kkt.num_variables()
+
+
+# --------------------------------------------------------------------------
+# linear solvers (CPU oracles for A9/A10/A11)
+# --------------------------------------------------------------------------
+def num_neg_ev(n, D, ipiv):
+    """src/LinearSolvers/lapack.jl:247-268 -- Bunch-Kaufman inertia from ipiv.
+
+    ``ipiv`` is LAPACK's 1-based pivot vector (negative entries mark 2x2 blocks).
+    """
+    numneg = 0
+    t = 0.0
+    for k in range(n):
+        d = D[k, k]
+        if ipiv[k] < 0:
+            if t == 0:
+                t = abs(D[k + 1, k])
+                d = (d / t) * D[k + 1, k + 1] - t
+            else:
+                d = t
+                t = 0.0
+        if d < 0:
+            numneg += 1
+        if d == 0:
+            return -1
+    return numneg
+
+
+class LapackCPUSolver:
+    """src/LinearSolvers/lapack.jl + lapack_common.jl, BUNCHKAUFMAN algorithm.
+
+    ``A`` is the dense KKT matrix kept BY REFERENCE (lapack.jl:40); only its lower
+    triangle is read (``dsytrf('L')``, lapack.jl:164-167).
+    """
+    input_type = "dense"
+
+    def __init__(self, A):
+        self.A = A
+        self.n = A.shape[0]
+        self.fact = None
+        self.ipiv = None
+        self.info = 0
+
+    def factorize(self):
+        fact = np.array(self.A, order="F", copy=True)      # lapack_common.jl:28 transfer_matrix!
+        ldu, ipiv, info = _lapack.dsytrf(fact, lower=1, overwrite_a=1)
+        self.fact, self.ipiv, self.info = ldu, ipiv, info
+        return self
+
+    def is_inertia(self):
+        return True
+
+    def inertia(self):
+        """lapack.jl:240-245; returns (num_pos, num_zero, num_neg)."""
+        # scipy returns 0-based ipiv with 2x2 blocks flagged by repeated negative entries
+        # in the LAPACK convention shifted; rebuild LAPACK's 1-based signed vector.
+        ipiv_l = _to_lapack_ipiv(self.ipiv, self.fact)
+        numneg = num_neg_ev(self.n, self.fact, ipiv_l)
+        numzero = 1 if self.info > 0 else 0
+        numpos = self.n - numneg - numzero
+        return (numpos, numzero, numneg)
+
+    def solve(self, x):
+        """lapack_common.jl:75-81 + lapack.jl:169-172; in place."""
+        sol, info = _lapack.dsytrs(self.fact, self.ipiv, x, lower=1)
+        x[:] = sol
+        return x
+
+    def improve(self):
+        return False
+
+    def introduce(self):
+        return "Lapack-CPU (BUNCHKAUFMAN) [scipy dsytrf/dsytrs]"
+
+
+def _to_lapack_ipiv(ipiv, fact):
+    """scipy's f2py wrapper returns LAPACK's ipiv unchanged (1-based, negative = 2x2)."""
+    return np.asarray(ipiv)
+
+
+class UmfpackStandInSolver:
+    """Stand-in for src/LinearSolvers/umfpack.jl: expand tril->full (umfpack.jl:28-35),
+    unsymmetric sparse LU (here SuperLU; UMFPACK is absent from this image), no inertia
+    (umfpack.jl:57-58).  The matrix is kept by reference through (colptr,rowval,nzval).
+    """
+    input_type = "csc"
+
+    def __init__(self, colptr, rowval, nzval, n):
+        self.colptr, self.rowval, self.nzval, self.n = colptr, rowval, nzval, n
+        self.lu = None
+
+    def factorize(self):
+        full = tril_to_full(self.colptr, self.rowval, self.nzval, self.n)
+        try:
+            self.lu = spla.splu(full, permc_spec="MMD_AT_PLUS_A", diag_pivot_thresh=0.1)
+        except RuntimeError:            # singular: soft failure (umfpack.jl:41-44)
+            self.lu = None
+        return self
+
+    def is_inertia(self):
+        return False
+
+    def inertia(self):
+        raise RuntimeError("InertiaException")     # umfpack.jl:57-58
+
+    def solve(self, x):
+        if self.lu is None:                        # umfpack.jl:46-55: leave rhs unchanged
+            return x
+        x[:] = self.lu.solve(x)
+        return x
+
+    def improve(self):
+        return False
+
+    def introduce(self):
+        return "umfpack stand-in (SuperLU)"
+
+
+class DenseLDLInertiaSolver:
+    """Inertia *truth* for sparse matrices small enough to densify: eigenvalue signs.
+    Used to pin the product's inertia triple (A10); factor/solve through dsytrf."""
+    input_type = "csc"
+
+    def __init__(self, colptr, rowval, nzval, n):
+        self.colptr, self.rowval, self.nzval, self.n = colptr, rowval, nzval, n
+        self.inner = None
+
+    def factorize(self):
+        full = tril_to_full(self.colptr, self.rowval, self.nzval, self.n).toarray()
+        self.dense = full
+        self.inner = LapackCPUSolver(full).factorize()
+        return self
+
+    def is_inertia(self):
+        return True
+
+    def inertia(self):
+        return self.inner.inertia()
+
+    def solve(self, x):
+        return self.inner.solve(x)
+
+    def improve(self):
+        return False
+
+
+# --------------------------------------------------------------------------
+# SparseKKTSystem  (src/KKT/Sparse/augmented.jl)
+# --------------------------------------------------------------------------
+class SparseKKTSystem:
+    """Augmented (reduced) KKT in COO -> lower CSC; value vector
+    V = [pr_diag(n_tot) | hess(nnzh) | jac(nnzj) | slack -1 (ns) | du_diag(m)]
+    with aliasing views (augmented.jl:77-107)."""
+
+    def __init__(self, cb: Callback, linear_solver=UmfpackStandInSolver):
+        n, m = cb.nvar, cb.ncon
+        ns = len(cb.ind_ineq)
+        hI, hJ = cb.hess_I.copy(), cb.hess_J.copy()
+        force_lower_triangular(hI, hJ)                      # augmented.jl:65
+        n_jac, n_hess = cb.nnzj, len(hI)
+        n_tot = n + ns
+        self.n, self.m, self.ns, self.n_tot = n, m, ns, n_tot
+        L = n_tot + m + n_hess + n_jac + ns                 # augmented.jl:75
+        I = np.zeros(L, dtype=np.int64)
+        J = np.zeros(L, dtype=np.int64)
+        self.V = np.zeros(L)
+        o1 = n_tot
+        o2 = o1 + n_hess
+        o3 = o2 + n_jac
+        o4 = o3 + ns
+        I[:o1] = np.arange(n_tot); J[:o1] = np.arange(n_tot)
+        I[o1:o2] = hI; J[o1:o2] = hJ
+        I[o2:o3] = cb.jac_I + n_tot; J[o2:o3] = cb.jac_J
+        I[o3:o4] = cb.ind_ineq + n_tot; J[o3:o4] = np.arange(n, n + ns)
+        I[o4:] = np.arange(n_tot, n_tot + m); J[o4:] = np.arange(n_tot, n_tot + m)
+        self.aug_I, self.aug_J = I, J
+        self.pr_diag = self.V[:o1]
+        self.hess = self.V[o1:o2]
+        self.jac = self.V[o2:o4]            # callback part + slack part
+        self.jac_callback = self.V[o2:o3]
+        self.du_diag = self.V[o4:]
+        nlb, nub = len(cb.ind_lb), len(cb.ind_ub)
+        self.reg = np.zeros(n_tot)
+        self.l_diag = np.zeros(nlb); self.u_diag = np.zeros(nub)
+        self.l_lower = np.zeros(nlb); self.u_lower = np.zeros(nub)
+        self.ind_ineq, self.ind_lb, self.ind_ub = cb.ind_ineq, cb.ind_lb, cb.ind_ub
+        N = n_tot + m
+        self.N = N
+        self.aug_colptr, self.aug_rowval, self.aug_csc_map = coo_to_csc(I, J, N, N)
+        self.aug_nz = np.zeros(len(self.aug_rowval))
+        # jac_raw (m x n_tot) and hess_raw (n_tot x n_tot)   augmented.jl:109-122
+        self.jac_I = np.concatenate([cb.jac_I, cb.ind_ineq])
+        self.jac_J = np.concatenate([cb.jac_J, np.arange(n, n + ns)])
+        self.jac_colptr, self.jac_rowval, self.jac_csc_map = coo_to_csc(self.jac_I, self.jac_J, m, n_tot)
+        self.jac_nz = np.zeros(len(self.jac_rowval))
+        self.hess_colptr, self.hess_rowval, self.hess_csc_map = coo_to_csc(hI, hJ, n_tot, n_tot)
+        self.hess_nz = np.zeros(len(self.hess_rowval))
+        self.linear_solver = linear_solver(self.aug_colptr, self.aug_rowval, self.aug_nz, N)
+
+    def num_variables(self):
+        return len(self.pr_diag)
+
+    def initialize(self):
+        """Sparse/utils.jl:52-62."""
+        self.reg[:] = 1.0; self.pr_diag[:] = 1.0; self.du_diag[:] = 0.0
+        self.hess[:] = 0.0; self.l_lower[:] = 0.0; self.u_lower[:] = 0.0
+        self.l_diag[:] = 1.0; self.u_diag[:] = 1.0; self.hess_nz[:] = 0.0
+
+    def get_jacobian(self):
+        return self.jac_callback
+
+    def get_hessian(self):
+        return self.hess
+
+    def compress_jacobian(self):
+        """Sparse/utils.jl:36-40."""
+        if self.ns:
+            self.jac[-self.ns:] = -1.0
+        transfer(self.jac_nz, self.jac, self.jac_csc_map)
+
+    def compress_hessian(self):
+        """Sparse/utils.jl:48-50."""
+        transfer(self.hess_nz, self.hess, self.hess_csc_map)
+
+    def build_kkt(self):
+        """augmented.jl:146-148."""
+        transfer(self.aug_nz, self.V, self.aug_csc_map)
+
+    def is_inertia_correct(self, p, z, n):
+        return is_inertia_correct_default(self, p, z, n)
+
+    def jac_com(self):
+        return csc_to_scipy(self.jac_colptr, self.jac_rowval, self.jac_nz, (self.m, self.n_tot))
+
+    def hess_com(self):
+        return csc_to_scipy(self.hess_colptr, self.hess_rowval, self.hess_nz, (self.n_tot, self.n_tot))
+
+    def solve_kkt(self, w: UnreducedKKTVector):
+        """src/IPM/factorization.jl:41-46."""
+        reduce_rhs(self, w)
+        self.linear_solver.solve(w.primal_dual())
+        finish_aug_solve(self, w)
+        return w
+
+    def mul(self, w, x, alpha=1.0, beta=0.0):
+        """src/IPM/factorization.jl:231-237."""
+        H = self.hess_com()
+        Hs = H + sp.tril(H, -1).T
+        Jc = self.jac_com()
+        w.primal()[:] = alpha * (Hs @ x.primal()) + beta * w.primal()
+        w.primal()[:] += alpha * (Jc.T @ x.dual())
+        w.dual()[:] = alpha * (Jc @ x.primal()) + beta * w.dual()
+        kktmul_(w, x, self, alpha, beta)
+        return w
+
+
+# --------------------------------------------------------------------------
+# SparseCondensedKKTSystem  (src/KKT/Sparse/condensed.jl)
+# --------------------------------------------------------------------------
+def build_condensed_aug_symbolic(H_colptr, H_rowval, n, Jt_colptr, Jt_rowval, m):
+    """src/KKT/Sparse/condensed.jl:201-301.
+
+    Pattern of tril(H) U diag U tril(Jt Jt') as lower CSC, plus
+      dptr[(dst, src)]            -- pr_diag[src] -> nz[dst]
+      hptr[(dst, src)]            -- H.nz[src]    -> nz[dst]
+      jptr[(dst, (col, k, l))]    -- D[col]*Jt.nz[k]*Jt.nz[l] -> nz[dst]
+    The reference sorts the (row,col) key list with ``sortperm`` (stable) -- the order
+    of sources inside one destination slot is therefore: diag, hess (by index), then
+    Jt triples in (col, j, k) enumeration order.  We reproduce that order exactly since
+    it fixes the floating-point summation order of _build_condensed_aug_coord!.
+    """
+    nnzH = len(H_rowval)
+    # counts per Jt column  (condensed.jl:158-165)
+    cnts = np.diff(Jt_colptr).astype(np.int64)
+    nnzjtsj = int(np.sum(cnts * (cnts + 1) // 2))
+    tot = n + nnzH + nnzjtsj
+    kind = np.empty(tot, dtype=np.int64)     # -1 diag, 0 hess, >0: Jt column + 1
+    s1 = np.empty(tot, dtype=np.int64)
+    s2 = np.empty(tot, dtype=np.int64)
+    row = np.empty(tot, dtype=np.int64)
+    col = np.empty(tot, dtype=np.int64)
+    # diag entries (condensed.jl:231-240)
+    kind[:n] = -1; s1[:n] = np.arange(n); s2[:n] = 0
+    row[:n] = np.arange(n); col[:n] = np.arange(n)
+    # hess entries (condensed.jl:167-175)
+    hcols = np.repeat(np.arange(n), np.diff(H_colptr))
+    kind[n:n + nnzH] = 0; s1[n:n + nnzH] = np.arange(nnzH); s2[n:n + nnzH] = 0
+    row[n:n + nnzH] = H_rowval; col[n:n + nnzH] = hcols
+    # Jt pairs (condensed.jl:177-190): for column i, for j in col range, for k>=j
+    p = n + nnzH
+    for i in range(m):
+        a, b = int(Jt_colptr[i]), int(Jt_colptr[i + 1])
+        c = b - a
+        if c == 0:
+            continue
+        jj, kk = np.triu_indices(c)          # j<=k, row-major == reference loop order
+        cnt = len(jj)
+        kind[p:p + cnt] = i + 1
+        s1[p:p + cnt] = a + jj
+        s2[p:p + cnt] = a + kk
+        col[p:p + cnt] = Jt_rowval[a + jj]    # c1
+        row[p:p + cnt] = Jt_rowval[a + kk]    # c2
+        p += cnt
+    assert p == tot
+    # sort by (col,row), stable  (condensed.jl:251)
+    order = np.lexsort((row, col))            # lexsort is stable; last key primary
+    kind, s1, s2, row, col = kind[order], s1[order], s2[order], row[order], col[order]
+    newslot = np.ones(tot, dtype=bool)
+    newslot[1:] = (row[1:] != row[:-1]) | (col[1:] != col[:-1])
+    guide = np.cumsum(newslot) - 1            # 0-based slot id
+    rowval = row[newslot].astype(np.int32)
+    ucol = col[newslot]
+    colptr = np.zeros(n + 1, dtype=np.int64)
+    np.add.at(colptr, ucol + 1, 1)
+    colptr = np.cumsum(colptr).astype(np.int32)
+    b = kind == -1
+    dptr = np.stack([guide[b], s1[b]], axis=1)
+    b = kind == 0
+    hptr = np.stack([guide[b], s1[b]], axis=1)
+    b = kind > 0
+    jptr = np.stack([guide[b], kind[b] - 1, s1[b], s2[b]], axis=1)
+    return colptr, rowval, dptr, hptr, jptr
+
+
+def build_condensed_aug_coord(nz, pr_diag, H_nz, Jt_nz, diag_buffer, dptr, hptr, jptr):
+    """src/KKT/Sparse/condensed.jl:328-345 -- same three accumulation passes in the
+    same order (hess, diag, JtDJ), sequential adds inside each pass."""
+    nz[:] = 0.0
+    np.add.at(nz, hptr[:, 0], H_nz[hptr[:, 1]])
+    np.add.at(nz, dptr[:, 0], pr_diag[dptr[:, 1]])
+    np.add.at(nz, jptr[:, 0], diag_buffer[jptr[:, 1]] * Jt_nz[jptr[:, 2]] * Jt_nz[jptr[:, 3]])
+    return nz
+
+
+class SparseCondensedKKTSystem:
+    """src/KKT/Sparse/condensed.jl:8-153, 354-366."""
+
+    def __init__(self, cb: Callback, linear_solver=None):
+        n, m = cb.nvar, cb.ncon
+        ns = len(cb.ind_ineq)
+        if ns != m:
+            raise ValueError("SparseCondensedKKTSystem does not support equality constrained NLPs.")  # condensed.jl:68-70
+        hI, hJ = cb.hess_I.copy(), cb.hess_J.copy()
+        force_lower_triangular(hI, hJ)
+        self.n, self.m, self.ns, self.n_tot = n, m, ns, n + ns
+        nlb, nub = len(cb.ind_lb), len(cb.ind_ub)
+        self.reg = np.zeros(n + ns); self.pr_diag = np.zeros(n + ns); self.du_diag = np.zeros(m)
+        self.l_diag = np.zeros(nlb); self.u_diag = np.zeros(nub)
+        self.l_lower = np.zeros(nlb); self.u_lower = np.zeros(nub)
+        self.buffer = np.zeros(m); self.buffer2 = np.zeros(m); self.diag_buffer = np.zeros(m)
+        self.hess = np.zeros(len(hI)); self.jac = np.zeros(cb.nnzj)
+        self.ind_ineq, self.ind_lb, self.ind_ub = cb.ind_ineq, cb.ind_lb, cb.ind_ub
+        # jt_coo = (n x m) with I=jac_J, J=jac_I  (condensed.jl:105-110)
+        self.jt_colptr, self.jt_rowval, self.jt_csc_map = coo_to_csc(cb.jac_J, cb.jac_I, n, m)
+        self.jt_nz = np.zeros(len(self.jt_rowval))
+        self.hess_colptr, self.hess_rowval, self.hess_csc_map = coo_to_csc(hI, hJ, n, n)
+        self.hess_nz = np.zeros(len(self.hess_rowval))
+        (self.aug_colptr, self.aug_rowval, self.dptr, self.hptr, self.jptr) = build_condensed_aug_symbolic(
+            self.hess_colptr, self.hess_rowval, n, self.jt_colptr, self.jt_rowval, m)
+        self.aug_nz = np.zeros(len(self.aug_rowval))
+        self.N = n
+        if linear_solver is None:
+            linear_solver = DenseLDLInertiaSolver
+        self.linear_solver = linear_solver(self.aug_colptr, self.aug_rowval, self.aug_nz, n)
+
+    def num_variables(self):
+        return len(self.pr_diag)
+
+    def initialize(self):
+        self.reg[:] = 1.0; self.pr_diag[:] = 1.0; self.du_diag[:] = 0.0
+        self.hess[:] = 0.0; self.l_lower[:] = 0.0; self.u_lower[:] = 0.0
+        self.l_diag[:] = 1.0; self.u_diag[:] = 1.0; self.hess_nz[:] = 0.0
+
+    def get_jacobian(self):
+        return self.jac
+
+    def get_hessian(self):
+        return self.hess
+
+    def compress_jacobian(self):
+        """condensed.jl:145-148."""
+        transfer(self.jt_nz, self.jac, self.jt_csc_map)
+
+    def compress_hessian(self):
+        transfer(self.hess_nz, self.hess, self.hess_csc_map)
+
+    def build_kkt(self):
+        """condensed.jl:354-366."""
+        n, m = self.n, self.m
+        Ss = self.pr_diag[n:n + m]
+        Sd = self.du_diag
+        self.diag_buffer[:] = Ss / (1.0 - Sd * Ss)
+        build_condensed_aug_coord(self.aug_nz, self.pr_diag, self.hess_nz, self.jt_nz,
+                                  self.diag_buffer, self.dptr, self.hptr, self.jptr)
+
+    def is_inertia_correct(self, p, z, ng):
+        """condensed.jl:138-140."""
+        return z == 0 and p == self.n
+
+    def jt_csc(self):
+        return csc_to_scipy(self.jt_colptr, self.jt_rowval, self.jt_nz, (self.n, self.m))
+
+    def hess_com(self):
+        return csc_to_scipy(self.hess_colptr, self.hess_rowval, self.hess_nz, (self.n, self.n))
+
+    def solve_kkt(self, w: UnreducedKKTVector):
+        """src/IPM/factorization.jl:143-167."""
+        n, m = self.n, self.m
+        full = w.full()
+        wx = full[:n]; ws = full[n:n + m]; wz = full[n + m:n + 2 * m]
+        Ss = self.pr_diag[n:n + m]
+        reduce_rhs(self, w)
+        self.buffer[:] = self.diag_buffer * (wz + ws / Ss)
+        Jt = self.jt_csc()
+        wx[:] += Jt @ self.buffer
+        self.linear_solver.solve(wx)
+        self.buffer2[:] = Jt.T @ wx
+        wz[:] = -self.buffer + self.diag_buffer * self.buffer2
+        ws[:] = (ws + wz) / Ss
+        finish_aug_solve(self, w)
+        return w
+
+    def mul(self, w, x, alpha=1.0, beta=0.0):
+        """src/IPM/factorization.jl:303-324."""
+        n, m = self.n, self.m
+        xf, wf = x.full(), w.full()
+        xx = xf[:n]; xs = xf[n:n + m]; xz = xf[n + m:n + 2 * m]
+        wx = wf[:n]; ws = wf[n:n + m]; wz = wf[n + m:n + 2 * m]
+        H = self.hess_com(); Hs = H + sp.tril(H, -1).T
+        Jt = self.jt_csc()
+        wx[:] = alpha * (Hs @ xx) + beta * wx
+        wx[:] += alpha * (Jt @ xz)
+        wz[:] = alpha * (Jt.T @ xx) + beta * wz
+        wz[:] -= alpha * xs
+        ws[:] = beta * ws - alpha * xz
+        kktmul_(w, x, self, alpha, beta)
+        return w
+
+
+# --------------------------------------------------------------------------
+# DenseCondensedKKTSystem  (src/KKT/Dense/condensed.jl)
+# --------------------------------------------------------------------------
+class DenseCondensedKKTSystem:
+    """Dense/condensed.jl:10-191.  hess: n x n (both triangles), jac: m x n."""
+
+    def __init__(self, cb: Callback, linear_solver=LapackCPUSolver):
+        n, m = cb.nvar, cb.ncon
+        ns = len(cb.ind_ineq)
+        n_eq = m - ns
+        self.n, self.m, self.ns, self.n_eq = n, m, ns, n_eq
+        nlb, nub = len(cb.ind_lb), len(cb.ind_ub)
+        N = n + n_eq
+        self.N = N
+        self.aug_com = np.zeros((N, N), order="F")
+        self.hess = np.zeros((n, n), order="F")
+        self.jac = np.zeros((m, n), order="F")
+        self.jac_ineq = np.zeros((ns, n), order="F")
+        self.reg = np.zeros(n + ns); self.pr_diag = np.zeros(n + ns); self.du_diag = np.zeros(m)
+        self.l_diag = np.ones(nlb); self.u_diag = np.ones(nub)
+        self.l_lower = np.zeros(nlb); self.u_lower = np.zeros(nub)
+        self.pd_buffer = np.zeros(N); self.diag_buffer = np.zeros(ns); self.buffer = np.zeros(m)
+        self.ind_eq, self.ind_ineq = cb.ind_eq, cb.ind_ineq
+        self.ind_lb, self.ind_ub = cb.ind_lb, cb.ind_ub
+        self.linear_solver = linear_solver(self.aug_com)
+
+    def num_variables(self):
+        return self.n
+
+    def initialize(self):
+        """KKTsystem.jl:210-216."""
+        self.reg[:] = 1.0; self.pr_diag[:] = 1.0; self.du_diag[:] = 0.0; self.hess[:] = 0.0
+
+    def get_jacobian(self):
+        return self.jac
+
+    def get_hessian(self):
+        return self.hess
+
+    def compress_jacobian(self):
+        pass
+
+    def compress_hessian(self):
+        pass
+
+    def build_kkt(self):
+        """Dense/condensed.jl:157-186 (+ helpers :120-155)."""
+        n, ns, n_eq = self.n, self.ns, self.n_eq
+        self.aug_com[:] = 0.0
+        Ss = self.pr_diag[n:n + ns]
+        Sd = self.du_diag[self.ind_ineq]
+        self.diag_buffer[:] = Ss / (1.0 - Sd * Ss)
+        self.jac_ineq[:] = self.jac[self.ind_ineq, :] * np.sqrt(self.diag_buffer)[:, None]
+        W = self.jac_ineq.T @ self.jac_ineq
+        self.aug_com[:n, :n] = W
+        # _build_condensed_kkt_system!  (:120-143)
+        self.aug_com[:n, :n] += self.hess
+        self.aug_com[np.arange(n), np.arange(n)] += self.pr_diag[:n]
+        if n_eq:
+            Je = self.jac[self.ind_eq, :]
+            self.aug_com[n:, :n] = Je
+            self.aug_com[:n, n:] = Je.T
+            self.aug_com[n + np.arange(n_eq), n + np.arange(n_eq)] = self.du_diag[self.ind_eq]
+
+    def is_inertia_correct(self, p, z, ng):
+        """Dense/condensed.jl:189-191."""
+        return z == 0 and ng == self.n_eq
+
+    def solve_kkt(self, w: UnreducedKKTVector):
+        """src/IPM/factorization.jl:190-229."""
+        n, ns, n_eq, m = self.n, self.ns, self.n_eq, self.m
+        full = w.full()
+        wx = full[:n]; ws = full[n:n + ns]
+        i_eq = self.ind_eq + n + ns
+        i_in = self.ind_ineq + n + ns
+        x = self.pd_buffer
+        Ss = self.pr_diag[n:n + ns]
+        reduce_rhs(self, w)
+        self.buffer[:] = 0.0
+        self.buffer[self.ind_ineq] = self.diag_buffer * (full[i_in] + ws / Ss)
+        x[:n] = self.jac.T @ self.buffer
+        x[:n] += wx
+        x[n:] = full[i_eq]
+        self.linear_solver.solve(x)
+        wx[:] = x[:n]
+        dual = w.dual()
+        wz_old = full[i_in].copy()
+        dual[:] = self.jac @ wx
+        full[i_eq] = x[n:]
+        # wz .*= diag_buffer  acts on the freshly written J*wx entries of the ineq rows
+        full[i_in] *= self.diag_buffer
+        dual[:] -= self.buffer
+        ws[:] = (ws + full[i_in]) / Ss
+        finish_aug_solve(self, w)
+        return w
+
+    def mul(self, w, x, alpha=1.0, beta=0.0):
+        """src/IPM/factorization.jl:326-344 (AbstractDenseKKTSystem)."""
+        n, ns, m = self.n, self.ns, self.m
+        wp, xp = w.primal(), x.primal()
+        wx = wp[:n]; ws = wp[n:]
+        xx = xp[:n]; xs = xp[n:]
+        wy, xy = w.dual(), x.dual()
+        Hs = np.tril(self.hess) + np.tril(self.hess, -1).T      # _symv!('L', ...)
+        wx[:] = alpha * (Hs @ xx) + beta * wx
+        if m > 0:
+            wx[:] += alpha * (self.jac.T @ xy)
+            wy[:] = alpha * (self.jac @ xx) + beta * wy
+        ws[:] = beta * ws - alpha * xy[self.ind_ineq]
+        wy[self.ind_ineq] -= alpha * xs
+        kktmul_(w, x, self, alpha, beta)
+        return w
+
+
+# --------------------------------------------------------------------------
+# Richardson refinement  (src/LinearSolvers/backsolve.jl:27-76)
+# --------------------------------------------------------------------------
+def solve_refine(x, kkt, b, w, tol=1e-8, max_iter=10):
+    """Returns (ok, n_iter, residual_ratio); richardson_tol = tol^(5/4),
+    acceptable = tol^(5/8) (backsolve.jl:25)."""
+    r_tol = tol ** (5 / 4)
+    r_acc = tol ** (5 / 8)
+    norm_b = np.linalg.norm(b.full(), np.inf)
+    ratio = 0.0
+    x.full()[:] = 0.0
+    it = 0
+    if norm_b != 0:
+        w.full()[:] = b.full()
+        while True:
+            kkt.solve_kkt(w)
+            x.full()[:] += w.full()
+            w.full()[:] = b.full()
+            kkt.mul(w, x, -1.0, 1.0)
+            norm_w = np.linalg.norm(w.full(), np.inf)
+            norm_x = np.linalg.norm(x.full(), np.inf)
+            ratio = norm_w / (min(norm_x, 1e6 * norm_b) + norm_b)
+            it += 1
+            if it >= max_iter or ratio < r_tol:
+                break
+    return ratio < r_acc, it, ratio
+
+
+# --------------------------------------------------------------------------
+# fixtures restated from lib/MadNLPTests
+# --------------------------------------------------------------------------
+class HS15Model:
+    """lib/MadNLPTests/src/Instances/hs15.jl:1-104."""
+    nvar, ncon = 2, 2
+    x0 = np.zeros(2)
+    y0 = np.zeros(2)
+    lvar = np.array([-np.inf, -np.inf]); uvar = np.array([0.5, np.inf])
+    lcon = np.array([1.0, 0.0]); ucon = np.array([np.inf, np.inf])
+    jac_I = np.array([0, 0, 1, 1]); jac_J = np.array([0, 1, 0, 1])
+    hess_I = np.array([0, 1, 1]); hess_J = np.array([0, 0, 1])
+
+    @staticmethod
+    def jac_coord(x):
+        return np.array([x[1], x[0], 1.0, 2 * x[1]])
+
+    @staticmethod
+    def hess_coord(x, y, obj_weight=1.0):
+        H = np.array([obj_weight * (-400.0 * x[1] + 1200.0 * x[0] ** 2 + 2.0),
+                      obj_weight * (-400.0 * x[0]),
+                      obj_weight * 200.0])
+        H[1] += y[0] * 1.0
+        H[2] += y[1] * 2.0
+        return H
+
+    @staticmethod
+    def jac_dense(x):
+        return np.array([[x[1], x[0]], [1.0, 2 * x[1]]])
+
+    @staticmethod
+    def hess_dense(x, y, obj_weight=1.0):
+        h = HS15Model.hess_coord(x, y, obj_weight)
+        return np.array([[h[0], h[1]], [h[1], h[2]]])
+
+    @classmethod
+    def callback(cls):
+        """Index sets as create_callback derives them (nlpmodels.jl:369-406): both
+        constraints are inequalities -> 2 slacks with bounds lcon/ucon."""
+        ind_ineq = np.array([0, 1])
+        xl = np.concatenate([cls.lvar, cls.lcon[ind_ineq]])
+        xu = np.concatenate([cls.uvar, cls.ucon[ind_ineq]])
+        ind_lb = np.where(np.isfinite(xl))[0]
+        ind_ub = np.where(np.isfinite(xu))[0]
+        return Callback(2, 2, cls.jac_I, cls.jac_J, cls.hess_I, cls.hess_J, ind_ineq, ind_lb, ind_ub)
+
+
+def test_kkt_system(kkt, model, dense=False):
+    """lib/MadNLPTests/src/MadNLPTests.jl:53-110 restated; returns (x, y, inertia)."""
+    kkt.initialize()
+    x0, y0 = model.x0, model.y0
+    if dense:
+        kkt.get_jacobian()[:] = model.jac_dense(x0)
+        kkt.get_hessian()[:] = model.hess_dense(x0, y0)
+    else:
+        kkt.get_jacobian()[:] = model.jac_coord(x0)
+        kkt.get_hessian()[:] = model.hess_coord(x0, y0)
+    kkt.compress_jacobian()
+    kkt.compress_hessian()
+    kkt.l_lower[:] = 1e-3
+    kkt.u_lower[:] = 1e-3
+    set_aug_diagonal_(kkt)
+    kkt.build_kkt()
+    kkt.linear_solver.factorize()
+    x = UnreducedKKTVector.for_kkt(kkt)
+    x.full()[:] = 1.0
+    kkt.solve_kkt(x)
+    y = x.copy()
+    y.full()[:] = 0.0
+    kkt.mul(y, x)
+    inertia = kkt.linear_solver.inertia() if kkt.linear_solver.is_inertia() else None
+    return x, y, inertia
