@@ -61,7 +61,10 @@ typedef struct b2_options {
     int32_t small_front_max; /* fronts with order <= this run in the fused shared-memory kernel */
     int32_t n_parts;         /* multi-GPU: number of ranks sharing the elimination tree (1 = off) */
     int32_t part_rank;       /* multi-GPU: this rank                                        */
-    int32_t reserved[8];
+    int32_t kkt_n_primal;    /* > 0: the matrix is an augmented KKT system [[H, J'],[J, -D]] whose first kkt_n_primal
+                                rows are primal; the ordering then eliminates every dual row only after one of its
+                                primal neighbours, so that a zero (2,2) block never yields a structurally zero pivot */
+    int32_t reserved[7];
 } b2_options;
 
 int b2_options_default(b2_options* opt);

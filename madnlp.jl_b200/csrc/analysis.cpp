@@ -9,6 +9,7 @@
 #include "analysis.hpp"
 
 #include <algorithm>
+#include <climits>
 #include <cstdio>
 #include <cstring>
 #include <numeric>
@@ -227,6 +228,32 @@ void analyse(int32_t n, const int32_t* colptr, const int32_t* rowval, const Anal
     }
     std::vector<int32_t> iperm(n);
     for (int32_t i = 0; i < n; ++i) iperm[perm0[i]] = i;
+
+    // ---- 1b. augmented-KKT constraint: a dual row that would be eliminated before all of its (primal) neighbours is
+    //          moved to just after its earliest neighbour (its pivot is then -a^2/d instead of the raw, possibly zero,
+    //          diagonal entry).  Quasi-definite / condensed matrices do not need this (kkt_n_primal = 0).
+    if (opt.kkt_n_primal > 0 && opt.kkt_n_primal < n && opt.ordering != 3) {
+        const int32_t np_ = opt.kkt_n_primal;
+        std::vector<int32_t> first_nb(n, INT32_MAX);
+        for (int32_t j = 0; j < n; ++j)
+            for (int32_t p = colptr[j]; p < colptr[j + 1]; ++p) {
+                const int32_t i = rowval[p];
+                if (i == j) continue;
+                first_nb[i] = std::min(first_nb[i], iperm[j]);
+                first_nb[j] = std::min(first_nb[j], iperm[i]);
+            }
+        std::vector<std::pair<int64_t, int32_t>> key(n);
+        for (int32_t v = 0; v < n; ++v) {
+            int64_t k = 2 * (int64_t)iperm[v];
+            if (v >= np_ && first_nb[v] != INT32_MAX && iperm[v] < first_nb[v]) k = 2 * (int64_t)first_nb[v] + 1;
+            key[v] = {k, iperm[v]};
+        }
+        std::vector<int32_t> ord(n);
+        std::iota(ord.begin(), ord.end(), 0);
+        std::sort(ord.begin(), ord.end(), [&](int32_t a, int32_t b) { return key[a] < key[b]; });
+        perm0 = ord;
+        for (int32_t i = 0; i < n; ++i) iperm[perm0[i]] = i;
+    }
 
     // ---- 2. etree + postorder
     std::vector<int64_t> rptr;

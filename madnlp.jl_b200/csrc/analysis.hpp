@@ -14,6 +14,7 @@ struct AnalysisOptions {
     int nemin = 16;
     double relax_zeros = 0.25;
     int n_parts = 1;           // multi-GPU partition count
+    int kkt_n_primal = 0;      // augmented-KKT hint: dual rows are ordered after one primal neighbour
 };
 
 // One front per supernode.  Pivot columns [first, first+w) in the PERMUTED numbering; the front has

@@ -250,6 +250,7 @@ int create_common(int32_t n, int64_t nnz, const int32_t* colptr_h, const int32_t
         AnalysisOptions ao;
         ao.ordering = s->opt.ordering; ao.nemin = s->opt.nemin; ao.relax_zeros = s->opt.relax_zeros;
         ao.n_parts = std::max(1, s->opt.n_parts);
+        ao.kkt_n_primal = s->opt.kkt_n_primal;
         analyse(n, colptr_h, rowval_h, ao, user_perm_h, s->S);
     } catch (std::exception& e) {
         set_error(std::string("b2_create: analysis failed: ") + e.what());

@@ -1,0 +1,110 @@
+"""Replay of the linear-algebra call order of one MadNLP IPM iteration (`regular!`, src/IPM/solver.jl:216-298):
+
+    eval_jac_wrapper!  -> compress_jacobian!      (values arrive in kkt.jac)
+    eval_lag_hess_wrapper! -> compress_hessian!   (values arrive in kkt.hess)
+    set_aug_diagonal!                             (src/IPM/kernels.jl:4-27)
+    inertia_correction!(InertiaBased)             (src/IPM/solver.jl:611-670):
+        factorize_wrapper! = build_kkt! + factorize!   ; inertia ; is_inertia_correct
+        solve_refine_wrapper! (Richardson)             ; on failure improve! and retry (factorization.jl:1-19)
+        while !ok: regularize_diagonal!(dw, dc) ; factorize_wrapper! ; inertia ; solve_refine
+
+The model callbacks themselves are out of scope: an iterate supplies their outputs.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import torch
+
+from .kkt import UnreducedKKTVector
+from .richardson import RichardsonIterator
+
+
+@dataclass
+class InertiaOptions:
+    # src/IPM/options.jl:168-175
+    first_hessian_perturbation: float = 1e-4
+    min_hessian_perturbation: float = 1e-20
+    max_hessian_perturbation: float = 1e20
+    perturb_inc_fact_first: float = 1e2
+    perturb_inc_fact: float = 8.0
+    perturb_dec_fact: float = 1 / 3
+    jacobian_regularization_value: float = 1e-8
+    jacobian_regularization_exponent: float = 0.25
+
+
+class IPMLinearAlgebra:
+    """Owns the work vectors of MadNLPSolver that the hot path touches (d, p, _w4) and drives one iteration."""
+
+    def __init__(self, kkt, tol=1e-8):
+        self.kkt = kkt
+        self.iterator = RichardsonIterator(kkt, tol=tol)
+        self.d = UnreducedKKTVector.for_kkt(kkt)
+        self.p = UnreducedKKTVector.for_kkt(kkt)
+        self.w = UnreducedKKTVector.for_kkt(kkt)
+        self.opt = InertiaOptions()
+        self.del_w_last = 0.0
+        self.cnt = dict(factorizations=0, backsolves=0, regularized=0, failed=0)
+
+    def load_iterate(self, it, non_blocking=True):
+        """Copy one iterate's callback outputs / diagonal inputs into the KKT buffers (H2D when `it` holds pinned
+        host tensors, D2D when it holds device tensors)."""
+        k = self.kkt
+        k.get_jacobian().copy_(it["jac"], non_blocking=non_blocking)
+        k.get_hessian().copy_(it["hess"], non_blocking=non_blocking)
+        k.reg.copy_(it["reg"], non_blocking=non_blocking)
+        k.du_diag.copy_(it["du_diag"], non_blocking=non_blocking)
+        k.l_diag.copy_(it["l_diag"], non_blocking=non_blocking)
+        k.u_diag.copy_(it["u_diag"], non_blocking=non_blocking)
+        k.l_lower.copy_(it["l_lower"], non_blocking=non_blocking)
+        k.u_lower.copy_(it["u_lower"], non_blocking=non_blocking)
+        self.p.values.copy_(it["rhs"], non_blocking=non_blocking)
+
+    def _factorize_wrapper(self):
+        self.kkt.build_kkt()
+        self.kkt.linear_solver.factorize()
+        self.cnt["factorizations"] += 1
+
+    def _solve_refine_wrapper(self):
+        ok = self.iterator.solve_refine(self.d, self.p, self.w)
+        if not ok and self.kkt.linear_solver.improve():
+            self.kkt.linear_solver.factorize()
+            ok = self.iterator.solve_refine(self.d, self.p, self.w)
+        self.cnt["backsolves"] += self.iterator.ir
+        return ok
+
+    def step(self, mu=1e-2):
+        """One `regular!` linear-algebra pass; returns True when a step direction was obtained."""
+        k = self.kkt
+        k.compress_jacobian()
+        k.compress_hessian()
+        k.set_aug_diagonal_()
+        # inertia_correction!(InertiaBased)
+        o = self.opt
+        n_trial = 0
+        del_w = del_c = del_w_prev = del_c_prev = 0.0
+        self._factorize_wrapper()
+        inertia = k.linear_solver.inertia()
+        ok = self._solve_refine_wrapper() if k.is_inertia_correct(*inertia) else False
+        while not ok:
+            if n_trial == 0:
+                del_w = o.first_hessian_perturbation if self.del_w_last == 0.0 else max(
+                    o.min_hessian_perturbation, o.perturb_dec_fact * self.del_w_last)
+            else:
+                del_w *= o.perturb_inc_fact_first if self.del_w_last == 0.0 else o.perturb_inc_fact
+                if del_w > o.max_hessian_perturbation:
+                    self.cnt["failed"] += 1
+                    return False
+            del_c = (o.jacobian_regularization_value * mu ** o.jacobian_regularization_exponent
+                     if k.should_regularize_dual(*inertia) else 0.0)
+            k.regularize_diagonal(del_w - del_w_prev, del_c - del_c_prev)
+            del_w_prev, del_c_prev = del_w, del_c
+            self._factorize_wrapper()
+            inertia = k.linear_solver.inertia()
+            ok = self._solve_refine_wrapper() if k.is_inertia_correct(*inertia) else False
+            n_trial += 1
+            self.cnt["regularized"] += 1
+        if del_w != 0.0:
+            self.del_w_last = del_w
+        self.last_inertia = inertia
+        return True

@@ -1,0 +1,57 @@
+"""RichardsonIterator.solve_refine!  (src/LinearSolvers/backsolve.jl:27-76) on device vectors.
+
+Same loop, same stopping rule: residual_ratio = ||b - K x||_inf / (min(||x||_inf, 1e6 ||b||_inf) + ||b||_inf),
+stop when ratio < tol^(5/4) or after richardson_max_iter (=10) steps, accept when ratio < tol^(5/8)
+(backsolve.jl:25).  The two norms are reduced on the device and fetched with ONE 16-byte D2H copy per step
+(the reference syncs twice per step through `norm`).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import capi
+from .capi import lib, check, ptr
+
+
+class RichardsonIterator:
+    def __init__(self, kkt, tol=1e-8, richardson_max_iter=10):
+        self.kkt = kkt
+        self.richardson_max_iter = richardson_max_iter
+        self.richardson_tol = tol ** (5 / 4)
+        self.richardson_acceptable_tol = tol ** (5 / 8)
+        self._norms = torch.zeros(2, dtype=torch.float64, device="cuda")
+        self._norms_h = torch.zeros(2, dtype=torch.float64).pin_memory()
+        self.ir = 0
+        self.residual_ratio = 0.0
+
+    def _norm_pair(self, w, x, stream):
+        n = w.values.numel()
+        check(lib.b2_norm_inf(n, ptr(w.values), ptr(self._norms[0:1]), stream))
+        check(lib.b2_norm_inf(n, ptr(x.values), ptr(self._norms[1:2]), stream))
+        self._norms_h.copy_(self._norms, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return float(self._norms_h[0]), float(self._norms_h[1])
+
+    def solve_refine(self, x, b, w) -> bool:
+        kkt = self.kkt
+        stream = capi.stream_ptr(getattr(kkt, "stream", None))
+        n = b.values.numel()
+        check(lib.b2_norm_inf(n, ptr(b.values), ptr(self._norms[0:1]), stream))
+        norm_b = float(self._norms[0].item())
+        residual_ratio = 0.0
+        x.values.zero_()
+        self.ir = 0
+        if norm_b != 0.0:
+            check(lib.b2_copy(n, ptr(b.values), ptr(w.values), stream))
+            while True:
+                kkt.solve_kkt(w)
+                check(lib.b2_axpy(n, 1.0, ptr(w.values), ptr(x.values), stream))
+                check(lib.b2_copy(n, ptr(b.values), ptr(w.values), stream))
+                kkt.mul(w, x, -1.0, 1.0)
+                norm_w, norm_x = self._norm_pair(w, x, stream)
+                residual_ratio = norm_w / (min(norm_x, 1e6 * norm_b) + norm_b)
+                self.ir += 1
+                if self.ir >= self.richardson_max_iter or residual_ratio < self.richardson_tol:
+                    break
+        self.residual_ratio = residual_ratio
+        return residual_ratio < self.richardson_acceptable_tol

@@ -340,11 +340,13 @@ class IPMIterate:
     mu: float
 
 
-def ipm_iterates(model: ACOPF, st: NLPStructure, n_iter: int, seed: int = 0, y_scale: float = 1.0):
+def ipm_iterates(model: ACOPF, st: NLPStructure, n_iter: int, seed: int = 0, y_scale: float = 1.0,
+                 eq_box=(1e-5, 1e-4)):
     """A sequence of iterates with the barrier parameter decreasing 1e-1 -> 1e-9.
     Bound distances and multipliers follow the central-path relation  z * dist ~ mu  with log-uniform
-    distances; relaxed equalities sit in a 2e-8-wide box, which is what makes late condensed systems
-    ill-conditioned in practice (D up to ~1e8+)."""
+    distances; relaxed equalities sit in a narrow box (`eq_box` = range of distances to its faces), which is
+    what makes condensed systems ill-conditioned in practice: D = Sigma_s spans ~[1e-9, 1e9] over the sequence
+    (SURVEY.md 8d asks for D log-uniform in [1e-8, 1e8])."""
     rng = np.random.default_rng(seed)
     n, m = st.nvar, st.ncon
     ns = len(st.ind_ineq)
@@ -373,8 +375,8 @@ def ipm_iterates(model: ACOPF, st: NLPStructure, n_iter: int, seed: int = 0, y_s
             eq_rows[1 + 4 * nbr:1 + 7 * nbr] = False     # angle + thermal are genuine inequalities
             tight_lb = is_slack_lb.copy(); tight_lb[is_slack_lb] = eq_rows[st.ind_lb[is_slack_lb] - n]
             tight_ub = is_slack_ub.copy(); tight_ub[is_slack_ub] = eq_rows[st.ind_ub[is_slack_ub] - n]
-            dl[tight_lb] = dist(int(tight_lb.sum()), 2e-9, 2e-8)
-            du[tight_ub] = dist(int(tight_ub.sum()), 2e-9, 2e-8)
+            dl[tight_lb] = dist(int(tight_lb.sum()), eq_box[0], eq_box[1])
+            du[tight_ub] = dist(int(tight_ub.sum()), eq_box[0], eq_box[1])
         zl = mu / dl * np.exp(0.3 * rng.standard_normal(nlb))
         zu = mu / du * np.exp(0.3 * rng.standard_normal(nub))
         rhs = rng.standard_normal(n_tot + m + nlb + nub)

@@ -1,0 +1,102 @@
+"""CPU-side checks of the C-ABI library: it loads, exports every symbol include/b200kkt.h declares, refuses to
+compute without a GPU (no fallback), and its host-side (symbolic) entry points agree with the oracle."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import madnlp_oracle as o
+import madnlp_jl_b200 as pkg
+
+capi = pkg.capi
+lib = capi.lib
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    txt = open(os.path.join(ROOT, "include", "b200kkt.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(b2d?_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_every_declared_symbol_is_exported_and_bound():
+    syms = _header_symbols()
+    assert len(syms) >= 50
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/b200kkt.h but not exported by libb200kkt.so"
+        assert s in capi.PROTOTYPES, f"{s} has no ctypes prototype in capi.py"
+    for s in capi.PROTOTYPES:
+        assert s in syms, f"{s} bound in capi.py but not declared in the header"
+
+
+def test_no_cpu_fallback_without_device():
+    if capi.device_count() > 0:
+        pytest.skip("a GPU is visible")
+    colptr = np.array([0, 2, 3], dtype=np.int32); rowval = np.array([0, 1, 1], dtype=np.int32)
+    h = C.c_void_p()
+    opt = capi.default_options()
+    rc = lib.b2_create(2, 3, colptr.ctypes.data, rowval.ctypes.data, None, C.byref(opt), None, C.byref(h))
+    assert rc == capi.B2_ERR_NO_DEVICE and "no CPU fallback" in capi.last_error()
+    with pytest.raises(capi.B2Error):
+        capi.require_device()
+    # a symbolic-only handle refuses every numeric call
+    capi.check(lib.b2_create_symbolic_only(2, 3, colptr.ctypes.data, rowval.ctypes.data, C.byref(opt), None, C.byref(h)))
+    assert lib.b2_factorize(h, None) == capi.B2_ERR_INVALID
+    assert lib.b2_solve(h, None, 1, None) == capi.B2_ERR_INVALID
+    lib.b2_destroy(h)
+
+
+def test_options_default_and_errors():
+    opt = capi.default_options()
+    assert opt.ordering == capi.ORDER_METIS_ND and opt.use_cuda_graph == 1 and opt.n_parts == 1
+    h = C.c_void_p()
+    colptr = np.array([0, 1, 5], dtype=np.int32); rowval = np.array([0, 1], dtype=np.int32)
+    assert lib.b2_create_symbolic_only(2, 2, colptr.ctypes.data, rowval.ctypes.data, C.byref(opt), None, C.byref(h)) == capi.B2_ERR_INVALID
+    with pytest.raises(TypeError):
+        capi.default_options(no_such_option=1)
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_coo_to_csc_matches_oracle(seed):
+    """b2_coo_to_csc vs the restated src/matrixtools.jl:55-95 incl. duplicates, empty columns, unsorted input."""
+    rng = np.random.default_rng(seed)
+    m, n, nnz = 17, 13, 90
+    I = rng.integers(0, m, nnz); J = rng.integers(0, n - 2, nnz)      # last two columns empty
+    I[:5] = I[5:10]; J[:5] = J[5:10]                                   # guaranteed duplicates
+    cp0, rv0, mp0 = o.coo_to_csc(I, J, m, n)
+    I32, J32 = I.astype(np.int32), J.astype(np.int32)
+    cp = np.zeros(n + 1, dtype=np.int32); rv = np.zeros(nnz, dtype=np.int32); mp = np.zeros(nnz, dtype=np.int64)
+    k = C.c_int64(0)
+    capi.check(lib.b2_coo_to_csc(m, n, nnz, I32.ctypes.data, J32.ctypes.data, cp.ctypes.data, rv.ctypes.data, mp.ctypes.data, C.byref(k)))
+    assert k.value == len(rv0)
+    assert (cp == cp0).all() and (rv[:k.value] == rv0).all() and (mp == mp0).all()
+    # empty input
+    capi.check(lib.b2_coo_to_csc(3, 3, 0, None, None, cp.ctypes.data, rv.ctypes.data, mp.ctypes.data, C.byref(k)))
+    assert k.value == 0 and (cp[:4] == 0).all()
+    # out-of-range index is rejected
+    bad = np.array([99], dtype=np.int32)
+    assert lib.b2_coo_to_csc(3, 3, 1, bad.ctypes.data, bad.ctypes.data, cp.ctypes.data, rv.ctypes.data, mp.ctypes.data, C.byref(k)) == capi.B2_ERR_INVALID
+
+
+@pytest.mark.parametrize("case", ["hs15", "case30_synth", "case300_synth"])
+def test_condensed_symbolic_matches_oracle(case):
+    """b2_condensed_symbolic (pattern + map sizes) vs the restated build_condensed_aug_symbolic (condensed.jl:201-301)."""
+    if case == "hs15":
+        cb = o.HS15Model.callback()
+    else:
+        model, st = pkg.workloads.acopf_case(case)
+        cb = o.Callback(st.nvar, st.ncon, st.jac_I, st.jac_J, st.hess_I, st.hess_J, st.ind_ineq, st.ind_lb, st.ind_ub)
+    k = o.SparseCondensedKKTSystem(cb)
+    h = C.c_void_p(); nnz = C.c_int64(0)
+    capi.check(lib.b2_condensed_symbolic(k.n, k.m, k.hess_colptr.ctypes.data, k.hess_rowval.ctypes.data,
+                                         k.jt_colptr.ctypes.data, k.jt_rowval.ctypes.data, C.byref(h), C.byref(nnz)))
+    assert nnz.value == len(k.aug_rowval)
+    cp = np.zeros(k.n + 1, dtype=np.int32); rv = np.zeros(nnz.value, dtype=np.int32)
+    capi.check(lib.b2_condensed_pattern(h, cp.ctypes.data, rv.ctypes.data))
+    assert (cp == k.aug_colptr).all() and (rv == k.aug_rowval).all()
+    a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
+    capi.check(lib.b2_condensed_plan_sizes(h, C.byref(a), C.byref(b), C.byref(c)))
+    assert (a.value, b.value, c.value) == (len(k.dptr), len(k.hptr), len(k.jptr))
+    lib.b2_condensed_plan_destroy(h)

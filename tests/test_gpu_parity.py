@@ -1,0 +1,336 @@
+"""Parity of the CUDA hot path with the CPU oracle, through the C ABI (via the host mirror of MadNLP's interface).
+
+Bars: assembly = BIT-EXACT (integer/index work + fixed summation order); factor/solve = fp64 within
+the stated tolerance (step direction rel. inf-norm <= 1e-8 on well-conditioned systems, <= 1e-6 on the ill-conditioned
+IPM iterates after Richardson refinement), inertia triple IDENTICAL to the oracle (LAPACK Bunch-Kaufman / eigenvalues).
+"""
+import numpy as np
+import pytest
+
+import madnlp_oracle as o
+import madnlp_jl_b200 as pkg
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+W = pkg.workloads
+
+
+def _need_gpu():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+
+
+def _dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def _cb(st):
+    return o.Callback(st.nvar, st.ncon, st.jac_I, st.jac_J, st.hess_I, st.hess_J, st.ind_ineq, st.ind_lb, st.ind_ub)
+
+
+def _load(kkt_gpu, kkt_cpu, it, dense=False):
+    """put one iterate into both the oracle and the device KKT system and assemble"""
+    for k, put in ((kkt_cpu, lambda dst, v: dst.__setitem__(slice(None), v)),
+                   (kkt_gpu, lambda dst, v: dst.copy_(_dev(v)))):
+        k.initialize()
+        put(k.get_jacobian(), it.jac); put(k.get_hessian(), it.hess)
+        put(k.reg, it.reg + 1e-8); put(k.du_diag, it.du_diag)
+        put(k.l_diag, it.l_diag); put(k.u_diag, it.u_diag); put(k.l_lower, it.l_lower); put(k.u_lower, it.u_lower)
+        k.compress_jacobian(); k.compress_hessian()
+    o.set_aug_diagonal_(kkt_cpu); kkt_cpu.build_kkt()
+    kkt_gpu.set_aug_diagonal_(); kkt_gpu.build_kkt()
+
+
+# ------------------------------------------------------------------------------------------------ assembly
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_transfer_bit_exact(seed):
+    """A5 build_kkt!(::SparseKKTSystem) = transfer! (src/matrixtools.jl:79-88): duplicates, empty slots, ragged."""
+    _need_gpu()
+    from madnlp_jl_b200 import kkt as K
+    import ctypes as C
+    rng = np.random.default_rng(seed)
+    m, n, nnz = 301, 257, 5000
+    I = rng.integers(0, m, nnz); J = rng.integers(0, n, nnz)
+    I[:500] = I[500:1000]; J[:500] = J[500:1000]
+    V = rng.standard_normal(nnz) * 10.0 ** rng.integers(-8, 8, nnz)
+    cp0, rv0, mp0 = o.coo_to_csc(I, J, m, n)
+    ref = np.zeros(len(rv0)); o.transfer(ref, V, mp0)
+    cp, rv, mp = K.coo_to_csc(I, J, m, n)
+    plan = K._transfer_plan(mp, len(rv))
+    out = torch.full((len(rv),), 7.0, dtype=torch.float64, device="cuda")
+    pkg.capi.check(pkg.capi.lib.b2_transfer(plan.h, out.data_ptr(), _dev(V).data_ptr(), None))
+    torch.cuda.synchronize()
+    assert (out.cpu().numpy() == ref).all()
+
+
+@pytest.mark.parametrize("case", ["hs15", "case30_synth", "case300_synth"])
+def test_condensed_assembly_bit_exact(case):
+    """A7 build_kkt!(::SparseCondensedKKTSystem) incl. compress_* and set_aug_diagonal (A1, A3, A4): bit-exact."""
+    _need_gpu()
+    from madnlp_jl_b200 import kkt as K
+    if case == "hs15":
+        cb = o.HS15Model.callback()
+        it = W.IPMIterate(jac=o.HS15Model.jac_coord(np.array([0.3, 0.7])), hess=o.HS15Model.hess_coord(np.array([0.3, 0.7]), np.array([0.5, -0.2])),
+                          reg=np.zeros(4), du_diag=np.array([-1e-3, -2e-3]), l_diag=-np.array([0.3, 0.7]), u_diag=-np.array([0.2]),
+                          l_lower=np.array([1e-2, 3e-3]), u_lower=np.array([5e-2]), rhs=np.ones(9), mu=0.1)
+    else:
+        model, st = W.acopf_case(case)
+        cb = _cb(st)
+        it = W.ipm_iterates(model, st, 1, seed=11)[0]
+        it.du_diag[:] = -1e-6
+    kc = o.SparseCondensedKKTSystem(cb)
+    kg = K.SparseCondensedKKTSystem(cb)
+    assert (kg.aug_com.colptr == kc.aug_colptr).all() and (kg.aug_com.rowval == kc.aug_rowval).all()
+    _load(kg, kc, it)
+    torch.cuda.synchronize()
+    assert (kg.pr_diag.cpu().numpy() == kc.pr_diag).all()
+    assert (kg.jt_csc.nzval.cpu().numpy() == kc.jt_nz).all()
+    assert (kg.hess_com.nzval.cpu().numpy() == kc.hess_nz).all()
+    assert (kg.diag_buffer.cpu().numpy() == kc.diag_buffer).all()
+    assert (kg.aug_com.nzval.cpu().numpy() == kc.aug_nz).all()
+
+
+def test_augmented_assembly_bit_exact():
+    """A5 on the SparseKKTSystem value vector layout [pr_diag|hess|jac|-1|du_diag] (augmented.jl:77-107)."""
+    _need_gpu()
+    from madnlp_jl_b200 import kkt as K
+    model, st = W.acopf_case("case30_synth", relax_equality=False)
+    cb = _cb(st)
+    it = W.ipm_iterates(model, st, 1, seed=5)[0]
+    kc = o.SparseKKTSystem(cb, o.DenseLDLInertiaSolver)
+    kg = K.SparseKKTSystem(cb)
+    _load(kg, kc, it)
+    torch.cuda.synchronize()
+    assert (kg.V.cpu().numpy() == kc.V).all()
+    assert (kg.aug_com.nzval.cpu().numpy() == kc.aug_nz).all()
+    assert (kg.jac_com.nzval.cpu().numpy() == kc.jac_nz).all()
+
+
+# ------------------------------------------------------------------------------------------------ factor / solve
+def test_2x2_known_answer_through_sparse_and_dense_solver():
+    """The reference's KAT (MadNLPTests.jl:24-51) for both input types (:csc and :dense)."""
+    _need_gpu()
+    from madnlp_jl_b200.linear_solvers import B200SparseSolver, B200DenseSolver, DeviceCSC
+    sol = np.array([0.8542713567839195, 1.4572864321608041])
+    csc = DeviceCSC(2, 2, np.array([0, 2, 3], dtype=np.int32), np.array([0, 1, 1], dtype=np.int32), _dev(np.array([1.0, 0.1, 2.0])))
+    M = B200SparseSolver(csc)
+    assert isinstance(M.introduce(), str)
+    M.improve()
+    M.factorize()
+    assert M.inertia() == (2, 0, 0)
+    x = M.solve_linear_system(_dev(np.array([1.0, 3.0])))
+    assert np.abs(x.cpu().numpy() - sol).max() < 1e-14
+    A = _dev(np.array([[1.0, 0.1], [0.0, 2.0]]))          # memory = column-major [[1,0],[.1,2]] (lower triangle filled)
+    D = B200DenseSolver(A)
+    D.factorize()
+    assert D.inertia() == (2, 0, 0)
+    x = D.solve_linear_system(_dev(np.array([1.0, 3.0])))
+    assert np.abs(x.cpu().numpy() - sol).max() < 1e-14
+
+
+HS15_EXPECTED = np.array([0.24987493746873435, 0.00497512437810945, -1.0, -0.7501250625312657, -0.9989999999999999,
+                          -0.7493749374687343, -1.001, -1.0007501250625312, 0.9997501250625312])
+
+
+@pytest.mark.parametrize("kind", ["sparse", "condensed", "dense_condensed"])
+def test_hs15_kkt_system_like_reference(kind):
+    """test/kkt_test.jl:27-48 / MadNLPTests.test_kkt_system (MadNLPTests.jl:53-110) on the device."""
+    _need_gpu()
+    from madnlp_jl_b200 import kkt as K
+    cb = o.HS15Model.callback()
+    typ = dict(sparse=K.SparseKKTSystem, condensed=K.SparseCondensedKKTSystem, dense_condensed=K.DenseCondensedKKTSystem)[kind]
+    kkt = K.create_kkt_system(typ, cb)
+    n = kkt.num_variables()
+    kkt.initialize()
+    if kind == "dense_condensed":
+        kkt.set_dense(hess_np=o.HS15Model.hess_dense(o.HS15Model.x0, o.HS15Model.y0), jac_np=o.HS15Model.jac_dense(o.HS15Model.x0))
+    else:
+        kkt.get_jacobian().copy_(_dev(o.HS15Model.jac_coord(o.HS15Model.x0)))
+        kkt.get_hessian().copy_(_dev(o.HS15Model.hess_coord(o.HS15Model.x0, o.HS15Model.y0)))
+    kkt.compress_jacobian(); kkt.compress_hessian()
+    kkt.l_lower.fill_(1e-3); kkt.u_lower.fill_(1e-3)
+    kkt.set_aug_diagonal_()
+    kkt.build_kkt()
+    kkt.linear_solver.factorize()
+    x = K.UnreducedKKTVector.for_kkt(kkt)
+    x.values.fill_(1.0)
+    out1 = kkt.solve_kkt(x)
+    assert out1 is x
+    y = x.copy(); y.values.zero_()
+    out2 = kkt.mul(y, x)
+    assert out2 is y
+    assert np.allclose(y.values.cpu().numpy(), 1.0, rtol=np.sqrt(np.finfo(float).eps), atol=0)
+    assert np.abs(x.values.cpu().numpy() - HS15_EXPECTED).max() < 1e-12
+    ni, mi, pi = kkt.linear_solver.inertia()
+    assert kkt.is_inertia_correct(ni, mi, pi)
+    kkt.regularize_diagonal(1.0, 1.0)
+    assert n in (2, 4)
+
+
+def _refined_direction_cpu(kc, rhs):
+    b = o.UnreducedKKTVector.for_kkt(kc); b.full()[:] = rhs
+    x = o.UnreducedKKTVector.for_kkt(kc); w = o.UnreducedKKTVector.for_kkt(kc)
+    ok, nit, ratio = o.solve_refine(x, kc, b, w)
+    return x.full().copy(), ok, ratio
+
+
+def _refined_direction_gpu(kg, rhs):
+    from madnlp_jl_b200 import kkt as K
+    from madnlp_jl_b200.richardson import RichardsonIterator
+    b = K.UnreducedKKTVector.for_kkt(kg); b.values.copy_(_dev(rhs))
+    x = K.UnreducedKKTVector.for_kkt(kg); w = K.UnreducedKKTVector.for_kkt(kg)
+    itr = RichardsonIterator(kg)
+    ok = itr.solve_refine(x, b, w)
+    return x.values.cpu().numpy(), ok, itr.residual_ratio
+
+
+@pytest.mark.parametrize("case,seed", [("case30_synth", 1), ("case300_synth", 2), ("case1354_pegase", 3)])
+def test_condensed_opf_step_direction_and_inertia(case, seed):
+    """configs[2]-style: condensed AC-OPF KKT, step direction vs the oracle (dsytrf-based) and identical inertia."""
+    _need_gpu()
+    from madnlp_jl_b200 import kkt as K
+    model, st = W.acopf_case(case)
+    cb = _cb(st)
+    its = W.ipm_iterates(model, st, 3, seed=seed)
+    big = st.nvar > 4000
+    kc = o.SparseCondensedKKTSystem(cb, o.UmfpackStandInSolver if big else o.DenseLDLInertiaSolver)
+    kg = K.SparseCondensedKKTSystem(cb)
+    for it in its:
+        _load(kg, kc, it)
+        kc.linear_solver.factorize(); kg.linear_solver.factorize()
+        inertia = kg.linear_solver.inertia()
+        if not big:
+            assert inertia == kc.linear_solver.inertia()
+        assert kg.is_inertia_correct(*inertia)
+        dc, okc, rc = _refined_direction_cpu(kc, it.rhs)
+        dg, okg, rg = _refined_direction_gpu(kg, it.rhs)
+        assert okc and okg and rg < 1e-8
+        assert np.abs(dg - dc).max() / np.abs(dc).max() <= 1e-6
+        # unrefined single solve of the condensed system itself, well inside fp64 backward stability
+        b = np.random.default_rng(seed).standard_normal(kg.n)
+        xg = kg.linear_solver.solve_linear_system(_dev(b)).cpu().numpy()
+        Kfull = o.tril_to_full(kc.aug_colptr, kc.aug_rowval, kc.aug_nz, kc.n)
+        res = np.abs(Kfull @ xg - b).max() / (abs(Kfull).max() * np.abs(xg).max() + np.abs(b).max())
+        assert res < 1e-12
+
+
+def test_negative_curvature_is_counted():
+    """A10: an indefinite condensed matrix must report the same (pos, zero, neg) as the oracle and fail is_inertia_correct."""
+    _need_gpu()
+    from madnlp_jl_b200 import kkt as K
+    model, st = W.acopf_case("case300_synth")
+    cb = _cb(st)
+    # large multipliers + loose slack boxes -> the indefinite Lagrangian Hessian dominates J'DJ (oracle: 237 negatives)
+    it = W.ipm_iterates(model, st, 1, seed=9, y_scale=1e3, eq_box=(1e-1, 1.0))[0]
+    kc = o.SparseCondensedKKTSystem(cb, o.DenseLDLInertiaSolver)
+    kg = K.SparseCondensedKKTSystem(cb)
+    _load(kg, kc, it)
+    kc.linear_solver.factorize(); kg.linear_solver.factorize()
+    ref = kc.linear_solver.inertia()
+    assert ref[2] > 0
+    assert kg.linear_solver.inertia() == ref
+    assert not kg.is_inertia_correct(*ref)
+
+
+def test_augmented_kkt_solve_and_inertia():
+    """SparseKKTSystem (true indefinite LDL^T, inertia (n_tot, 0, m)) on a small AC-OPF with equalities kept."""
+    _need_gpu()
+    from madnlp_jl_b200 import kkt as K
+    model, st = W.acopf_case("case300_synth", relax_equality=False)
+    cb = _cb(st)
+    it = W.ipm_iterates(model, st, 1, seed=4)[0]
+    it.du_diag[:] = -1e-8
+    kc = o.SparseKKTSystem(cb, o.DenseLDLInertiaSolver)
+    kg = K.SparseKKTSystem(cb)
+    _load(kg, kc, it)
+    kc.linear_solver.factorize(); kg.linear_solver.factorize()
+    assert kg.linear_solver.inertia() == kc.linear_solver.inertia() == (kg.n_tot, 0, kg.m)
+    dc, okc, rc = _refined_direction_cpu(kc, it.rhs)
+    dg, okg, rg = _refined_direction_gpu(kg, it.rhs)
+    assert okc and okg
+    assert np.abs(dg - dc).max() / np.abs(dc).max() <= 1e-6
+
+
+def test_big_front_path_3d_grid():
+    """Fronts beyond the shared-memory classes (HBM-resident, blocked DMMA update): 3-D augmented KKT, config 5 style."""
+    _need_gpu()
+    from madnlp_jl_b200.linear_solvers import B200SparseSolver, DeviceCSC
+    N, n_tot, m, I, J, V = W.augmented_grid_kkt(14, 14, 14)
+    cp, rv, mp = o.coo_to_csc(I, J, N, N)
+    nz = np.zeros(len(rv)); o.transfer(nz, V, mp)
+    csc = DeviceCSC(N, N, cp, rv, _dev(nz))
+    M = B200SparseSolver(csc, B200SparseSolver.default_options(kkt_n_primal=n_tot))
+    st = M.stats()
+    assert st["n_big_fronts"] > 0 and st["max_front"] > 168
+    M.factorize()
+    assert M.inertia() == (n_tot, 0, m)
+    b = np.random.default_rng(0).standard_normal(N)
+    x = M.solve_linear_system(_dev(b)).cpu().numpy()
+    Kf = o.tril_to_full(cp, rv, nz, N)
+    import scipy.sparse.linalg as spla
+    xr = spla.splu(Kf.tocsc()).solve(b)
+    assert np.abs(Kf @ x - b).max() / (abs(Kf).max() * np.abs(x).max() + np.abs(b).max()) < 1e-12
+    assert np.abs(x - xr).max() / np.abs(xr).max() < 1e-7
+    # smaller shared-memory limit forces more fronts through the big path; results must not change materially
+    M2 = B200SparseSolver(csc, B200SparseSolver.default_options(kkt_n_primal=n_tot, small_front_max=40, use_cuda_graph=0))
+    M2.factorize()
+    assert M2.inertia() == (n_tot, 0, m)
+    x2 = M2.solve_linear_system(_dev(b)).cpu().numpy()
+    assert np.abs(x2 - x).max() / np.abs(x).max() < 1e-9
+
+
+@pytest.mark.parametrize("n_eq", [0, 24])
+def test_dense_condensed_qp(n_eq):
+    """configs[1] structure at a size the oracle finishes in seconds: DenseCondensedKKTSystem assembly (A8),
+    dense LDL^T + inertia (neg == n_eq) and solve_kkt vs LAPACK dsytrf/dsytrs."""
+    _need_gpu()
+    from madnlp_jl_b200 import kkt as K
+    qp = W.dense_qp(n=320, m=130, n_eq=n_eq, seed=3)
+    it = W.dense_qp_iterate(qp, mu=1e-3, seed=4)
+    ns = qp.m - n_eq
+    cb = o.Callback(qp.n, qp.m, [], [], [], [], qp.ind_ineq, qp.ind_lb, qp.ind_ub)
+    kc = o.DenseCondensedKKTSystem(cb)
+    kg = K.DenseCondensedKKTSystem(cb)
+    for k in (kc, kg):
+        k.initialize()
+    kc.hess[:] = qp.P; kc.jac[:] = qp.A
+    kg.set_dense(hess_np=qp.P, jac_np=qp.A)
+    for name in ("reg", "du_diag", "l_diag", "u_diag", "l_lower", "u_lower"):
+        getattr(kc, name)[:] = it[name]
+        getattr(kg, name).copy_(_dev(it[name]))
+    o.set_aug_diagonal_(kc); kc.build_kkt()
+    kg.set_aug_diagonal_(); kg.build_kkt()
+    N = qp.n + n_eq
+    aug = kg.aug_com.cpu().numpy().T                     # back to the mathematical (row, col) view
+    assert np.abs(np.tril(aug) - np.tril(kc.aug_com)).max() / np.abs(kc.aug_com).max() < 1e-13
+    kc.linear_solver.factorize(); kg.linear_solver.factorize()
+    assert kg.linear_solver.inertia() == kc.linear_solver.inertia() == (qp.n, 0, n_eq)
+    assert kg.is_inertia_correct(*kg.linear_solver.inertia())
+    dc, okc, rc = _refined_direction_cpu(kc, it["rhs"])
+    dg, okg, rg = _refined_direction_gpu(kg, it["rhs"])
+    assert okc and okg
+    assert np.abs(dg - dc).max() / np.abs(dc).max() <= 1e-8
+    assert ns == kg.ns and N == kg.N
+
+
+def test_ipm_replay_regularises_like_the_reference():
+    """inertia_correction!(InertiaBased) replay (src/IPM/solver.jl:611-670): a nonconvex iterate must trigger the
+    primal regularisation schedule 1e-4, x100, x8 ... until the inertia is correct, then return a direction."""
+    _need_gpu()
+    from madnlp_jl_b200 import kkt as K
+    from madnlp_jl_b200.ipm import IPMLinearAlgebra
+    model, st = W.acopf_case("case30_synth")
+    cb = _cb(st)
+    kg = K.SparseCondensedKKTSystem(cb)
+    kg.initialize()
+    la = IPMLinearAlgebra(kg)
+    good = W.ipm_iterates(model, st, 1, seed=2)[0]
+    bad = W.ipm_iterates(model, st, 1, seed=2, y_scale=1e2, eq_box=(1e-1, 1.0))[0]
+    for it, expect_reg in ((good, False), (bad, True)):
+        d = {k: _dev(getattr(it, k)) for k in ("jac", "hess", "reg", "du_diag", "l_diag", "u_diag", "l_lower", "u_lower", "rhs")}
+        before = la.cnt["regularized"]
+        la.load_iterate(d)
+        assert la.step(mu=it.mu)
+        assert (la.cnt["regularized"] > before) == expect_reg
+        assert kg.is_inertia_correct(*la.last_inertia)

@@ -1,0 +1,95 @@
+"""Pins the CPU oracle (oracle/madnlp_oracle.py) against everything the reference's own tests hold for this path
+ before it is trusted as the checker for the CUDA path."""
+import numpy as np
+import pytest
+
+import madnlp_oracle as o
+
+
+def test_2x2_known_answer_vector():
+    """lib/MadNLPTests/src/MadNLPTests.jl:24-51 (test_linear_solver): the reference's only explicit KAT."""
+    row, col, val = np.array([0, 1, 1]), np.array([0, 0, 1]), np.array([1.0, 0.1, 2.0])
+    b = np.array([1.0, 3.0])
+    sol = np.array([0.8542713567839195, 1.4572864321608041])
+    A = np.zeros((2, 2), order="F")
+    A[row, col] = val
+    M = o.LapackCPUSolver(A).factorize()
+    assert M.inertia() == (2, 0, 0)
+    x = M.solve(b.copy())
+    assert np.abs(x - sol).max() < 1e-4 or np.abs(x - sol).max() / np.abs(sol).max() < 1e-4   # solcmp, MadNLPTests.jl:18-22
+    assert np.abs(x - sol).max() < 1e-15
+    # same matrix through the sparse stand-in (matrix_test.jl:33-39 runs the KAT for Umfpack too)
+    cp, rv, mp = o.coo_to_csc(row, col, 2, 2)
+    nz = np.zeros(len(rv)); o.transfer(nz, val, mp)
+    U = o.UmfpackStandInSolver(cp, rv, nz, 2).factorize()
+    assert np.abs(U.solve(b.copy()) - sol).max() < 1e-14
+
+
+HS15_EXPECTED = np.array([0.24987493746873435, 0.00497512437810945, -1.0, -0.7501250625312657,
+                          -0.9989999999999999, -0.7493749374687343, -1.001, -1.0007501250625312,
+                          0.9997501250625312])
+
+
+@pytest.mark.parametrize("kind", ["sparse", "sparse_umfpack", "condensed", "dense_condensed"])
+def test_hs15_kkt_identity(kind):
+    """test/kkt_test.jl:27-48 -> test_kkt_system (MadNLPTests.jl:53-110): K * solve_kkt(K, 1) == 1 and inertia."""
+    cb = o.HS15Model.callback()
+    if kind == "sparse":
+        kkt = o.SparseKKTSystem(cb, o.DenseLDLInertiaSolver)
+    elif kind == "sparse_umfpack":
+        kkt = o.SparseKKTSystem(cb, o.UmfpackStandInSolver)
+    elif kind == "condensed":
+        kkt = o.SparseCondensedKKTSystem(cb)
+    else:
+        kkt = o.DenseCondensedKKTSystem(cb)
+    x, y, inertia = o.test_kkt_system(kkt, o.HS15Model, dense=(kind == "dense_condensed"))
+    assert np.allclose(y.full(), 1.0, rtol=np.sqrt(np.finfo(float).eps), atol=0)
+    assert np.abs(x.full() - HS15_EXPECTED).max() < 1e-14
+    if inertia is not None:
+        assert kkt.is_inertia_correct(*inertia)
+    if kind == "sparse":
+        assert inertia == (4, 0, 2)
+        assert len(kkt.aug_I) == 15 and len(kkt.aug_rowval) == 13       # 2 duplicate COO positions (Appendix A)
+        dense = o.tril_to_full(kkt.aug_colptr, kkt.aug_rowval, kkt.aug_nz, 6).toarray()
+        assert np.allclose(np.diag(dense), [2.999, 201.0, 0.999, 0.999, 0.0, 0.0])
+        assert dense[4, 2] == -1.0 and dense[5, 0] == 1.0 and dense[5, 3] == -1.0
+    if kind == "condensed":
+        assert inertia == (2, 0, 0)
+        dense = o.tril_to_full(kkt.aug_colptr, kkt.aug_rowval, kkt.aug_nz, 2).toarray()
+        assert np.allclose(dense, [[3.998, 0.0], [0.0, 201.0]])
+
+
+def test_bunch_kaufman_inertia_with_2x2_blocks():
+    """num_neg_ev (src/LinearSolvers/lapack.jl:247-268) against eigenvalue signs on matrices that force 2x2 pivots."""
+    rng = np.random.default_rng(0)
+    for n in (4, 9, 30):
+        A = rng.standard_normal((n, n)); A = A + A.T
+        A[np.diag_indices(n)] = 0.0                     # zero diagonal => 2x2 pivots
+        M = o.LapackCPUSolver(np.asfortranarray(A)).factorize()
+        ev = np.linalg.eigvalsh(A)
+        assert (M.ipiv < 0).any()
+        assert M.inertia() == (int((ev > 0).sum()), 0, int((ev < 0).sum()))
+
+
+def test_condensed_matches_full_system():
+    """Every formulation eliminates the same unreduced system (SURVEY.md fact 2 / test/madnlp_dense.jl:44-48)."""
+    import madnlp_jl_b200 as pkg
+    W = pkg.workloads
+    model, st = W.acopf_case("case30_synth")
+    it = W.ipm_iterates(model, st, 1, seed=3)[0]
+    cb = o.Callback(st.nvar, st.ncon, st.jac_I, st.jac_J, st.hess_I, st.hess_J, st.ind_ineq, st.ind_lb, st.ind_ub)
+    sols = []
+    for K in (o.SparseKKTSystem, o.SparseCondensedKKTSystem):
+        kkt = K(cb, o.DenseLDLInertiaSolver)
+        kkt.initialize()
+        kkt.get_jacobian()[:] = it.jac; kkt.get_hessian()[:] = it.hess
+        kkt.compress_jacobian(); kkt.compress_hessian()
+        kkt.reg[:] = 1e-8; kkt.du_diag[:] = 0.0
+        kkt.l_diag[:] = it.l_diag; kkt.u_diag[:] = it.u_diag; kkt.l_lower[:] = it.l_lower; kkt.u_lower[:] = it.u_lower
+        o.set_aug_diagonal_(kkt); kkt.build_kkt(); kkt.linear_solver.factorize()
+        b = o.UnreducedKKTVector.for_kkt(kkt); b.full()[:] = it.rhs
+        x = o.UnreducedKKTVector.for_kkt(kkt); w = o.UnreducedKKTVector.for_kkt(kkt)
+        ok, nit, ratio = o.solve_refine(x, kkt, b, w)
+        assert ok and ratio < 1e-8
+        sols.append(x.full().copy())
+    assert np.abs(sols[0] - sols[1]).max() / np.abs(sols[0]).max() < 1e-6
