@@ -119,7 +119,7 @@ int64_t enqueue_factor(b2_solver* s, int ph, cudaStream_t st) {
                 const int kb = step * BIG_NB;
                 k_big_diag<<<lv.nB, 32, 0, st>>>(a, lb, step);
                 ++nl;
-                const int rem = lv.maxfB - kb - BIG_NB;
+                const int rem = lv.maxfB - kb - 1;      // rows below the (possibly partial) pivot block, upper bound
                 if (rem > 0) {
                     k_big_panel<<<dim3((rem + BIG_ROWS - 1) / BIG_ROWS, lv.nB), BIG_ROWS, 0, st>>>(a, lb, step);
                     const int nt = (rem + UT - 1) / UT;
@@ -656,7 +656,7 @@ void enqueue_dense_factor(b2d_solver* s, cudaStream_t st) {
     for (int step = 0; step < nsteps; ++step) {
         const int kb = step * BIG_NB;
         k_big_diag<<<1, 32, 0, st>>>(a, s->list.p, step);
-        const int rem = N - kb - BIG_NB;
+        const int rem = N - kb - std::min(BIG_NB, N - kb);
         if (rem > 0) {
             k_big_panel<<<dim3((rem + BIG_ROWS - 1) / BIG_ROWS, 1), BIG_ROWS, 0, st>>>(a, s->list.p, step);
             const int nt = (rem + UT - 1) / UT;

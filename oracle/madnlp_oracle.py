@@ -284,7 +284,10 @@ class UmfpackStandInSolver:
     def factorize(self):
         full = tril_to_full(self.colptr, self.rowval, self.nzval, self.n)
         try:
-            self.lu = spla.splu(full, permc_spec="MMD_AT_PLUS_A", diag_pivot_thresh=0.1)
+            # UMFPACK picks its "symmetric strategy" for such matrices: AMD on A+A' and diagonal pivots preferred with
+            # sym_pivot_tolerance = 0.001; SuperLU's closest setting is MMD(A'+A) + SymmetricMode + diag threshold 1e-3.
+            self.lu = spla.splu(full, permc_spec="MMD_AT_PLUS_A", diag_pivot_thresh=1e-3,
+                                options=dict(SymmetricMode=True))
         except RuntimeError:            # singular: soft failure (umfpack.jl:41-44)
             self.lu = None
         return self
