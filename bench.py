@@ -170,7 +170,12 @@ def run_b200(args, rank, world, local_rank):
         solver_cls = lambda csc, opt: DistributedSparseSolver(csc, opt, rank=rank, world=world)   # noqa: E731
     else:
         solver_cls = None
-    kkt = K.create_kkt_system(K.SparseCondensedKKTSystem, cb, solver_cls)
+    opt = pkg.capi.default_options()
+    if os.environ.get("B2_FUSE_MAX"):
+        opt.fuse_max_fronts = int(os.environ["B2_FUSE_MAX"])
+    if os.environ.get("B2_NEMIN"):
+        opt.nemin = int(os.environ["B2_NEMIN"])
+    kkt = K.create_kkt_system(K.SparseCondensedKKTSystem, cb, solver_cls, opt)
     kkt.initialize()
     la = IPMLinearAlgebra(kkt)
     stats = kkt.linear_solver.stats()

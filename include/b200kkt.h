@@ -64,7 +64,9 @@ typedef struct b2_options {
     int32_t kkt_n_primal;    /* > 0: the matrix is an augmented KKT system [[H, J'],[J, -D]] whose first kkt_n_primal
                                 rows are primal; the ordering then eliminates every dual row only after one of its
                                 primal neighbours, so that a zero (2,2) block never yields a structurally zero pivot */
-    int32_t reserved[7];
+    int32_t fuse_max_fronts; /* bottom elimination subtrees with at most this many (warp-class) fronts run inside ONE
+                                CTA of a single launch (0 = plain level-by-level schedule)                      */
+    int32_t reserved[6];
 } b2_options;
 
 int b2_options_default(b2_options* opt);
@@ -135,7 +137,12 @@ int b2_symbolic_query(b2_solver* s, b2_symbolic_sizes* sz);
 int b2_symbolic_export(b2_solver* s, int32_t* perm, int32_t* sn_first, int32_t* sn_parent, int32_t* sn_level,
                        int64_t* rows_ptr, int32_t* rows, int64_t* lp_off, int64_t* cb_off,
                        int64_t* rel_ptr, int32_t* rel, int64_t* amap_ptr, int64_t* amap_src, int64_t* amap_dst);
-int b2_symbolic_owner(b2_solver* s, int32_t* owner);   /* n_supernodes entries: rank, or -1 for the shared top tree */
+int b2_symbolic_owner(b2_solver* s, int32_t* owner);
+/* test/debug: copy the numeric factor (lval_size doubles, panel layout of b2_symbolic_export) and D (n doubles, permuted
+ * order) to the host; synchronises the device. */
+int b2_debug_get_factor(b2_solver* s, double* lval_h, double* dvec_h);
+/* test/debug: re-factor one warp-class front `reps` times with clock64() stamps at its 8 phase boundaries */
+int b2_debug_profile_front(b2_solver* s, int32_t sn, int32_t reps, int64_t* stamps_h);   /* n_supernodes entries: rank, or -1 for the shared top tree */
 
 /* ------------------------------------------------------------------ dense LDL^T */
 typedef struct b2d_solver b2d_solver;

@@ -33,6 +33,7 @@ struct FactorArgs {
     const int32_t* amap_dst;
     const double* A;      // caller's CSC values (aliased)
     double* L;            // factor panels
+    double* Lt;           // row-major copies of the warp-class panels (backward solve), same offsets
     double* ws;           // update blocks
     double* dvec;         // D, permuted order
     int32_t* counters;    // [0] = #negative pivots, [1] = #perturbed pivots

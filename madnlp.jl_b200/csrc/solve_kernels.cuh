@@ -16,6 +16,7 @@ struct SolveArgs {
     const int32_t* rel;
     const int64_t* cbv_off;   // per supernode offset of its contribution vector
     const double* L;
+    const double* Lt;         // row-major panel copies (warp-class fronts)
     const double* dvec;
     double* xp;
     double* cbv;

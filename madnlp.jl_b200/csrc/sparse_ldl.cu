@@ -10,29 +10,32 @@
 #include "common.cuh"
 #include "front_kernels.cuh"
 #include "solve_kernels.cuh"
+#include "warp_kernels.cuh"
 
 using namespace b2;
 
 namespace {
 
-struct FactorLevel {
-    int offS = 0, nS = 0, maxfS = 0;
-    int offM = 0, nM = 0, maxfM = 0;
-    int offB = 0, nB = 0, maxfB = 0, maxwB = 0, maxchildB = 0, maxamapB = 0, maxrB = 0;
+struct WarpLaunch {          // one launch of the team-per-front kernels (offsets into d_sched)
+    int n_cta = 0, cta_ptr_off = 0, stage_off_off = 0, stage_cnt_off = 0;
+    int nw = 1;              // warps per team: 1 (order <= 32) or 2 (order <= 64)
+    int maxf = 0;            // largest front in the launch (sizes the shared-memory assembly area)
 };
-struct SolveLevel {
-    int offW = 0, nW = 0, smemW = 0;   // doubles per warp
-    int offC = 0, nC = 0, maxfC = 0;
+struct LevelSched {
+    WarpLaunch W, W2;                               // fronts of order <= 32 / <= 64
+    int offM = 0, nM = 0, maxfM = 0;                // shared-memory CTA class
+    int offB = 0, nB = 0, maxfB = 0, maxwB = 0, maxchildB = 0, maxamapB = 0, maxrB = 0;   // HBM-resident class
+    int offC = 0, nC = 0, maxfC = 0;                // M and B fronts together, for the CTA solve kernels
 };
 struct Phase {
-    std::vector<FactorLevel> flev;
-    std::vector<SolveLevel> slev;
+    WarpLaunch fused;                               // bottom subtrees, one CTA each (n_cta == 0: none)
+    std::vector<LevelSched> lev;
     cudaGraphExec_t g_factor = nullptr, g_fwd = nullptr, g_bwd = nullptr;
     int64_t n_factor_launches = 0, n_solve_launches = 0;
+    int64_t n_fused_fronts = 0;
 };
 
-constexpr int S_MAX = 64;        // S class: f <= 64, 128 threads
-constexpr int SOLVE_WARP_MAX = 64;
+constexpr int W_MAX = 64;        // team-per-front classes: f <= 32 (one warp), f <= 64 (two warps)
 
 }  // namespace
 
@@ -47,8 +50,9 @@ struct b2_solver {
     DevBuf<int32_t> d_rows, d_child_idx, d_rel, d_amap_src, d_amap_dst, d_perm, d_sched;
     DevBuf<int64_t> d_cbv_off;
     DevBuf<uint8_t> d_mask_p;
+    DevBuf<ChildRec> d_childrec;
     // numeric storage
-    DevBuf<double> d_L, d_ws, d_dvec, d_xp, d_cbv;
+    DevBuf<double> d_L, d_Lt, d_ws, d_dvec, d_xp, d_cbv;
     DevBuf<int32_t> d_counters;
     int32_t* h_counters = nullptr;   // pinned
     std::vector<int64_t> cbv_off;
@@ -76,18 +80,27 @@ FactorArgs factor_args(b2_solver* s) {
     FactorArgs a;
     a.desc = s->d_desc.p; a.child_idx = s->d_child_idx.p; a.rel = s->d_rel.p;
     a.amap_src = s->d_amap_src.p; a.amap_dst = s->d_amap_dst.p;
-    a.A = s->nzval_d; a.L = s->d_L.p; a.ws = s->d_ws.p; a.dvec = s->d_dvec.p;
+    a.A = s->nzval_d; a.L = s->d_L.p; a.Lt = s->d_Lt.p; a.ws = s->d_ws.p; a.dvec = s->d_dvec.p;
     a.counters = s->d_counters.p; a.eps = s->opt.pivot_eps;
     return a;
 }
 SolveArgs solve_args(b2_solver* s) {
     SolveArgs a;
     a.desc = s->d_desc.p; a.rows = s->d_rows.p; a.child_idx = s->d_child_idx.p; a.rel = s->d_rel.p;
-    a.cbv_off = s->d_cbv_off.p; a.L = s->d_L.p; a.dvec = s->d_dvec.p; a.xp = s->d_xp.p; a.cbv = s->d_cbv.p;
+    a.cbv_off = s->d_cbv_off.p; a.L = s->d_L.p; a.Lt = s->d_Lt.p; a.dvec = s->d_dvec.p; a.xp = s->d_xp.p; a.cbv = s->d_cbv.p;
     return a;
 }
 
 inline size_t smem_front(int f) { return (size_t)f * f * sizeof(double); }
+
+WarpSched warp_sched(b2_solver* s, const WarpLaunch& L) {
+    WarpSched w;
+    w.cta_ptr = s->d_sched.p + L.cta_ptr_off;
+    w.stage_off = s->d_sched.p + L.stage_off_off;
+    w.stage_cnt = s->d_sched.p + L.stage_cnt_off;
+    w.list = s->d_sched.p;
+    return w;
+}
 
 // issue the numeric factorisation of one phase on `st`; returns number of launches
 int64_t enqueue_factor(b2_solver* s, int ph, cudaStream_t st) {
@@ -95,11 +108,21 @@ int64_t enqueue_factor(b2_solver* s, int ph, cudaStream_t st) {
     a.counters += 2 * ph;   // [0,1] owned subtrees, [2,3] shared top tree
     const int32_t* sched = s->d_sched.p;
     int64_t nl = 0;
-    for (const FactorLevel& lv : s->phase[ph].flev) {
-        if (lv.nS) {
-            k_front_smem<128><<<lv.nS, 128, smem_front(lv.maxfS), st>>>(a, sched + lv.offS);
-            ++nl;
+    const Phase& P = s->phase[ph];
+    auto warp_launch = [&](const WarpLaunch& L) {
+        if (L.nw == 1) {
+            const size_t sm = (size_t)FW_WARPS * TeamSmem<1>::doubles(L.maxf) * sizeof(double);
+            k_factor_warp<1><<<L.n_cta, FW_WARPS * 32, sm, st>>>(a, s->d_childrec.p, warp_sched(s, L), L.maxf);
+        } else {
+            const size_t sm = (size_t)TeamSmem<2>::doubles(L.maxf) * sizeof(double);
+            k_factor_warp<2><<<L.n_cta, 64, sm, st>>>(a, s->d_childrec.p, warp_sched(s, L), L.maxf);
         }
+        ++nl;
+    };
+    if (P.fused.n_cta) warp_launch(P.fused);
+    for (const LevelSched& lv : P.lev) {
+        if (lv.W.n_cta) warp_launch(lv.W);
+        if (lv.W2.n_cta) warp_launch(lv.W2);
         if (lv.nM) {
             k_front_smem<512><<<lv.nM, 512, smem_front(lv.maxfM), st>>>(a, sched + lv.offM);
             ++nl;
@@ -136,17 +159,23 @@ int64_t enqueue_solve(b2_solver* s, int ph, bool forward, cudaStream_t st) {
     SolveArgs a = solve_args(s);
     const int32_t* sched = s->d_sched.p;
     int64_t nl = 0;
-    const auto& lev = s->phase[ph].slev;
-    const int nlev = (int)lev.size();
-    for (int q = 0; q < nlev; ++q) {
-        const SolveLevel& lv = forward ? lev[q] : lev[nlev - 1 - q];
-        if (lv.nW) {
-            const int grid = (lv.nW + SOLVE_WARPS - 1) / SOLVE_WARPS;
-            const size_t sm = (size_t)SOLVE_WARPS * lv.smemW * sizeof(double);
-            if (forward) k_fwd_warp<<<grid, SOLVE_WARPS * 32, sm, st>>>(a, sched + lv.offW, lv.nW, lv.smemW);
-            else k_bwd_warp<<<grid, SOLVE_WARPS * 32, sm, st>>>(a, sched + lv.offW, lv.nW, lv.smemW);
-            ++nl;
+    const Phase& P = s->phase[ph];
+    auto warp_launch = [&](const WarpLaunch& L) {
+        if (L.nw == 1) {
+            if (forward) k_fwd_warp2<1><<<L.n_cta, FW_WARPS * 32, 0, st>>>(a, s->d_childrec.p, warp_sched(s, L));
+            else k_bwd_warp2<1><<<L.n_cta, FW_WARPS * 32, 0, st>>>(a, warp_sched(s, L));
+        } else {
+            if (forward) k_fwd_warp2<2><<<L.n_cta, 64, 0, st>>>(a, s->d_childrec.p, warp_sched(s, L));
+            else k_bwd_warp2<2><<<L.n_cta, 64, 0, st>>>(a, warp_sched(s, L));
         }
+        ++nl;
+    };
+    if (forward && P.fused.n_cta) warp_launch(P.fused);
+    const int nlev = (int)P.lev.size();
+    for (int q = 0; q < nlev; ++q) {
+        const LevelSched& lv = forward ? P.lev[q] : P.lev[nlev - 1 - q];
+        if (lv.W.n_cta) warp_launch(lv.W);
+        if (lv.W2.n_cta) warp_launch(lv.W2);
         if (lv.nC) {
             const size_t sm = (size_t)lv.maxfC * sizeof(double);
             if (forward) k_fwd_cta<<<lv.nC, SOLVE_CTA, sm, st>>>(a, sched + lv.offC);
@@ -154,14 +183,14 @@ int64_t enqueue_solve(b2_solver* s, int ph, bool forward, cudaStream_t st) {
             ++nl;
         }
     }
+    if (!forward && P.fused.n_cta) warp_launch(P.fused);
     return nl;
 }
 
 int set_smem_attrs() {
-    B2_CUDA(cudaFuncSetAttribute(k_front_smem<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_front(S_MAX)));
     B2_CUDA(cudaFuncSetAttribute(k_front_smem<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    B2_CUDA(cudaFuncSetAttribute(k_fwd_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    B2_CUDA(cudaFuncSetAttribute(k_bwd_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    B2_CUDA(cudaFuncSetAttribute(k_factor_warp<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    B2_CUDA(cudaFuncSetAttribute(k_factor_warp<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     B2_CUDA(cudaFuncSetAttribute(k_fwd_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     B2_CUDA(cudaFuncSetAttribute(k_bwd_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     return B2_OK;
@@ -187,53 +216,149 @@ void build_schedule(b2_solver* s) {
     const int ns = S.nsuper;
     const int rank = std::max(0, s->opt.part_rank);
     const int smax = s->opt.small_front_max;
+    const int wmax = std::min(W_MAX, smax);
+    const int w1max = std::min(32, smax);     // one-warp teams; fused subtrees are built from these only
+    const int fuse_max = s->opt.fuse_max_fronts;
     std::vector<int32_t> sched;
+    auto fdim = [&](int sn, int& w, int& f) {
+        w = S.sn_first[sn + 1] - S.sn_first[sn];
+        f = (int)(S.rows_ptr[sn + 1] - S.rows_ptr[sn]);
+    };
+    // a warp launch whose CTA c processes the stage lists given in `ctas[c]`
+    auto emit_warp_launch = [&](const std::vector<std::vector<std::vector<int32_t>>>& ctas, int nw) {
+        WarpLaunch L;
+        L.nw = nw;
+        L.n_cta = (int)ctas.size();
+        std::vector<int32_t> cta_ptr(1, 0), st_off, st_cnt;
+        for (const auto& stages : ctas) {
+            for (const auto& fr : stages) {
+                st_off.push_back((int32_t)sched.size());
+                st_cnt.push_back((int32_t)fr.size());
+                for (int32_t sn : fr) {
+                    int w, f; fdim(sn, w, f);
+                    L.maxf = std::max(L.maxf, f);
+                    sched.push_back(sn);
+                }
+            }
+            cta_ptr.push_back((int32_t)st_off.size());
+        }
+        L.cta_ptr_off = (int)sched.size(); sched.insert(sched.end(), cta_ptr.begin(), cta_ptr.end());
+        L.stage_off_off = (int)sched.size(); sched.insert(sched.end(), st_off.begin(), st_off.end());
+        L.stage_cnt_off = (int)sched.size(); sched.insert(sched.end(), st_cnt.begin(), st_cnt.end());
+        return L;
+    };
     for (int ph = 0; ph < 2; ++ph) {
         Phase& P = s->phase[ph];
-        P.flev.clear(); P.slev.clear();
-        for (int l = 0; l < S.nlevels; ++l) {
-            std::vector<int32_t> Sx, Mx, Bx, Wx, Cx;
-            FactorLevel fl; SolveLevel sl;
-            for (int q = S.level_ptr[l]; q < S.level_ptr[l + 1]; ++q) {
-                const int sn = S.level_sn[q];
-                const bool mine = (ph == 0) ? (S.owner[sn] == rank) : (S.owner[sn] == -1);
-                if (!mine) continue;
-                const int w = S.sn_first[sn + 1] - S.sn_first[sn];
-                const int f = (int)(S.rows_ptr[sn + 1] - S.rows_ptr[sn]);
-                const int r = f - w;
+        P.lev.clear(); P.fused = WarpLaunch(); P.n_fused_fronts = 0;
+        std::vector<char> mine(ns, 0);
+        for (int sn = 0; sn < ns; ++sn) mine[sn] = (ph == 0) ? (S.owner[sn] == rank) : (S.owner[sn] == -1);
+        // ---- bottom subtrees that can run inside one CTA: all fronts warp-class, at most fuse_max fronts
+        std::vector<int32_t> cnt(ns, 0);
+        std::vector<char> okw(ns, 0);
+        for (int sn = 0; sn < ns; ++sn) {          // children have smaller ids
+            if (!mine[sn]) continue;
+            int w, f; fdim(sn, w, f);
+            bool ok = f <= w1max;
+            int c = 1;
+            for (int q = S.child_ptr[sn]; q < S.child_ptr[sn + 1]; ++q) {
+                const int ch = S.child_idx[q];
+                if (!mine[ch]) { continue; }       // (cannot happen inside one phase except across the top boundary)
+                ok = ok && okw[ch];
+                c += cnt[ch];
+            }
+            cnt[sn] = c;
+            okw[sn] = ok && fuse_max > 0 && c <= fuse_max;
+        }
+        std::vector<int32_t> root_of(ns, -1);
+        std::vector<int32_t> roots;
+        for (int sn = ns - 1; sn >= 0; --sn) {     // parents first
+            if (!mine[sn] || !okw[sn]) continue;
+            const int p = S.sn_parent[sn];
+            if (p >= 0 && mine[p] && okw[p]) root_of[sn] = root_of[p];
+            else { root_of[sn] = sn; roots.push_back(sn); }
+        }
+        std::reverse(roots.begin(), roots.end());
+        if (!roots.empty()) {
+            std::vector<int32_t> ridx(ns, -1);
+            for (size_t k = 0; k < roots.size(); ++k) ridx[roots[k]] = (int32_t)k;
+            std::vector<std::vector<std::vector<int32_t>>> ctas(roots.size());
+            for (int sn = 0; sn < ns; ++sn) {
+                if (root_of[sn] < 0) continue;
+                auto& stages = ctas[ridx[root_of[sn]]];
+                const int lv = S.sn_level[sn];
+                if ((int)stages.size() <= lv) stages.resize(lv + 1);
+                stages[lv].push_back(sn);
+                P.n_fused_fronts++;
+            }
+            for (auto& stages : ctas) {            // drop empty levels (cannot occur: levels are contiguous in a subtree)
+                std::vector<std::vector<int32_t>> t;
+                for (auto& v : stages) if (!v.empty()) t.push_back(std::move(v));
+                stages.swap(t);
+            }
+            // longest subtrees first: better tail behaviour when there are more subtrees than resident CTAs
+            std::stable_sort(ctas.begin(), ctas.end(), [](const auto& a, const auto& b) {
+                size_t na = 0, nb = 0;
+                for (auto& v : a) na += v.size();
+                for (auto& v : b) nb += v.size();
+                return na > nb;
+            });
+            P.fused = emit_warp_launch(ctas, 1);
+        }
+        // ---- the rest, level by level (levels recomputed above the fused subtrees)
+        std::vector<int32_t> ulev(ns, -1);
+        int nul = 0;
+        for (int sn = 0; sn < ns; ++sn) {
+            if (!mine[sn] || root_of[sn] >= 0) continue;
+            int lv = 0;
+            for (int q = S.child_ptr[sn]; q < S.child_ptr[sn + 1]; ++q) {
+                const int ch = S.child_idx[q];
+                if (mine[ch] && root_of[ch] < 0) lv = std::max(lv, ulev[ch] + 1);
+            }
+            ulev[sn] = lv;
+            nul = std::max(nul, lv + 1);
+        }
+        std::vector<std::vector<int32_t>> by_level(nul);
+        for (int sn = 0; sn < ns; ++sn) if (ulev[sn] >= 0) by_level[ulev[sn]].push_back(sn);
+        for (int l = 0; l < nul; ++l) {
+            std::vector<int32_t> Wx, W2x, Mx, Bx;
+            LevelSched lv;
+            for (int sn : by_level[l]) {
+                int w, f; fdim(sn, w, f);
                 const int nch = S.child_ptr[sn + 1] - S.child_ptr[sn];
                 const int nam = (int)(S.amap_ptr[sn + 1] - S.amap_ptr[sn]);
-                if (f <= S_MAX && f <= smax) { Sx.push_back(sn); fl.maxfS = std::max(fl.maxfS, f); }
-                else if (f <= smax) { Mx.push_back(sn); fl.maxfM = std::max(fl.maxfM, f); }
+                if (f <= wmax && wmax > 32) W2x.push_back(sn);      // above the fused subtrees fronts are few: two-warp teams
+                else if (f <= w1max) Wx.push_back(sn);
+                else if (f <= smax) { Mx.push_back(sn); lv.maxfM = std::max(lv.maxfM, f); }
                 else {
                     Bx.push_back(sn);
-                    fl.maxfB = std::max(fl.maxfB, f); fl.maxwB = std::max(fl.maxwB, w);
-                    fl.maxchildB = std::max(fl.maxchildB, nch); fl.maxamapB = std::max(fl.maxamapB, nam);
-                }
-                // children sizes for extend-add grid sizing
-                if (f > smax)
+                    lv.maxfB = std::max(lv.maxfB, f); lv.maxwB = std::max(lv.maxwB, w);
+                    lv.maxchildB = std::max(lv.maxchildB, nch); lv.maxamapB = std::max(lv.maxamapB, nam);
                     for (int c = S.child_ptr[sn]; c < S.child_ptr[sn + 1]; ++c) {
-                        const int cs = S.child_idx[c];
-                        const int rc = (int)(S.rows_ptr[cs + 1] - S.rows_ptr[cs]) - (S.sn_first[cs + 1] - S.sn_first[cs]);
-                        fl.maxrB = std::max(fl.maxrB, rc);
+                        int cw, cf; fdim(S.child_idx[c], cw, cf);
+                        lv.maxrB = std::max(lv.maxrB, cf - cw);
                     }
-                if (f <= SOLVE_WARP_MAX) { Wx.push_back(sn); sl.smemW = std::max(sl.smemW, f * w + f); }
-                else { Cx.push_back(sn); sl.maxfC = std::max(sl.maxfC, f); }
-                (void)r;
+                }
+                if (f > wmax) lv.maxfC = std::max(lv.maxfC, f);
             }
-            if (Sx.empty() && Mx.empty() && Bx.empty()) continue;
-            fl.offS = (int)sched.size(); fl.nS = (int)Sx.size(); sched.insert(sched.end(), Sx.begin(), Sx.end());
-            fl.offM = (int)sched.size(); fl.nM = (int)Mx.size(); sched.insert(sched.end(), Mx.begin(), Mx.end());
-            fl.offB = (int)sched.size(); fl.nB = (int)Bx.size(); sched.insert(sched.end(), Bx.begin(), Bx.end());
-            sl.offW = (int)sched.size(); sl.nW = (int)Wx.size(); sched.insert(sched.end(), Wx.begin(), Wx.end());
-            sl.offC = (int)sched.size(); sl.nC = (int)Cx.size(); sched.insert(sched.end(), Cx.begin(), Cx.end());
-            P.flev.push_back(fl);
-            P.slev.push_back(sl);
+            auto level_launch = [&](const std::vector<int32_t>& X, int nw) {
+                std::vector<std::vector<std::vector<int32_t>>> ctas;
+                const size_t per = (nw == 1) ? FW_WARPS : 1;
+                for (size_t k = 0; k < X.size(); k += per) {
+                    std::vector<int32_t> fr(X.begin() + k, X.begin() + std::min(X.size(), k + per));
+                    ctas.push_back({fr});
+                }
+                return emit_warp_launch(ctas, nw);
+            };
+            if (!Wx.empty()) lv.W = level_launch(Wx, 1);
+            if (!W2x.empty()) lv.W2 = level_launch(W2x, 2);
+            lv.offM = (int)sched.size(); lv.nM = (int)Mx.size(); sched.insert(sched.end(), Mx.begin(), Mx.end());
+            lv.offB = (int)sched.size(); lv.nB = (int)Bx.size(); sched.insert(sched.end(), Bx.begin(), Bx.end());
+            lv.offC = lv.offM; lv.nC = lv.nM + lv.nB;        // M and B lists are adjacent
+            P.lev.push_back(lv);
         }
     }
     if (sched.empty()) sched.push_back(0);
     B2_CUDA_THROW(s->d_sched.upload(sched.data(), sched.size()));
-    (void)ns;
 }
 
 int create_common(int32_t n, int64_t nnz, const int32_t* colptr_h, const int32_t* rowval_h, const double* nzval_d,
@@ -329,7 +454,20 @@ int create_common(int32_t n, int64_t nnz, const int32_t* colptr_h, const int32_t
         B2_CUDA_THROW(s->d_perm.upload(S.perm.data(), S.perm.size()));
         B2_CUDA_THROW(s->d_cbv_off.upload(s->cbv_off.data(), s->cbv_off.size()));
         B2_CUDA_THROW(s->d_mask_p.upload(mask_p.data(), mask_p.size()));
+        {
+            std::vector<ChildRec> cr(std::max<size_t>(1, S.child_idx.size()));
+            for (size_t q = 0; q < S.child_idx.size(); ++q) {
+                const int c = S.child_idx[q];
+                cr[q].cb_off = S.cb_off[c];
+                cr[q].rel_off = S.rel_ptr[c];
+                cr[q].cbv_off = s->cbv_off[c];
+                cr[q].rc = (int32_t)(S.rel_ptr[c + 1] - S.rel_ptr[c]);
+                cr[q].sn = c;
+            }
+            B2_CUDA_THROW(s->d_childrec.upload(cr.data(), cr.size()));
+        }
         B2_CUDA_THROW(s->d_L.alloc((size_t)S.lp_off[ns]));
+        B2_CUDA_THROW(s->d_Lt.alloc((size_t)S.lp_off[ns]));
         B2_CUDA_THROW(s->d_ws.alloc((size_t)std::max<int64_t>(1, S.cb_off[ns])));
         B2_CUDA_THROW(s->d_dvec.alloc(n));
         B2_CUDA_THROW(s->d_xp.alloc(n));
@@ -397,6 +535,7 @@ int b2_options_default(b2_options* opt) {
     opt->pivot_eps = 1e-13;
     opt->use_cuda_graph = 1;
     opt->small_front_max = 160;
+    opt->fuse_max_fronts = 16;
     opt->n_parts = 1;
     opt->part_rank = 0;
     return B2_OK;
@@ -604,6 +743,34 @@ int b2_symbolic_export(b2_solver* s, int32_t* perm, int32_t* sn_first, int32_t* 
     cp(perm, S.perm); cp(sn_first, S.sn_first); cp(sn_parent, S.sn_parent); cp(sn_level, S.sn_level);
     cp(rows_ptr, S.rows_ptr); cp(rows, S.rows); cp(lp_off, S.lp_off); cp(cb_off, S.cb_off);
     cp(rel_ptr, S.rel_ptr); cp(rel, S.rel); cp(amap_ptr, S.amap_ptr); cp(amap_src, S.amap_src); cp(amap_dst, S.amap_dst);
+    return B2_OK;
+}
+
+int b2_debug_profile_front(b2_solver* s, int32_t sn, int32_t reps, int64_t* stamps_h) {
+    if (!s || s->symbolic_only || sn < 0 || sn >= s->S.nsuper || reps < 1 || reps > 64) return B2_ERR_INVALID;
+    const int f = (int)(s->S.rows_ptr[sn + 1] - s->S.rows_ptr[sn]);
+    if (f > W_MAX) { set_error("b2_debug_profile_front: front is not team-class"); return B2_ERR_INVALID; }
+    DevBuf<long long> prof;
+    B2_CUDA(prof.alloc(8 * reps));
+    FactorArgs a = factor_args(s);
+    a.counters += 2;   // scratch counters: do not disturb the inertia of the real factorisation
+    if (f <= 32) {
+        B2_CUDA(cudaFuncSetAttribute(k_factor_team_profile<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        k_factor_team_profile<1><<<1, 32, (size_t)TeamSmem<1>::doubles(f) * sizeof(double)>>>(a, s->d_childrec.p, sn, f, prof.p, reps);
+    } else {
+        B2_CUDA(cudaFuncSetAttribute(k_factor_team_profile<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        k_factor_team_profile<2><<<1, 64, (size_t)TeamSmem<2>::doubles(f) * sizeof(double)>>>(a, s->d_childrec.p, sn, f, prof.p, reps);
+    }
+    B2_CUDA(cudaDeviceSynchronize());
+    B2_CUDA(cudaMemcpy(stamps_h, prof.p, 8 * reps * sizeof(long long), cudaMemcpyDeviceToHost));
+    return B2_OK;
+}
+
+int b2_debug_get_factor(b2_solver* s, double* lval_h, double* dvec_h) {
+    if (!s || s->symbolic_only) return B2_ERR_INVALID;
+    B2_CUDA(cudaDeviceSynchronize());
+    if (lval_h) B2_CUDA(cudaMemcpy(lval_h, s->d_L.p, s->d_L.bytes(), cudaMemcpyDeviceToHost));
+    if (dvec_h) B2_CUDA(cudaMemcpy(dvec_h, s->d_dvec.p, s->d_dvec.bytes(), cudaMemcpyDeviceToHost));
     return B2_OK;
 }
 

@@ -1,0 +1,356 @@
+// Latency-oriented kernels for small fronts (order f <= 64): ONE WARP PER FRONT.
+//
+// On AC-OPF-like KKT systems every front is tiny (<= ~50) and the factorisation holds only ~2e7 flops: wall time is
+// the dependent-latency chain, not bandwidth or flops.  These kernels therefore
+//   * keep a front private to one warp (shared memory slice + registers), so a pivot step costs one __syncwarp
+//     instead of two __syncthreads;
+//   * take the reciprocal of each pivot with rcp.approx + 2 Newton steps (the only division on the critical path);
+//   * carry the triangular-solve recurrences through warp shuffles (chain per pivot: SHFL + DFMA) with the factor
+//     entries prefetched from shared memory, independent of the recurrence;
+//   * run through a STAGED schedule: a CTA owns a list of stages (local levels of an elimination subtree); its warps
+//     sweep the fronts of a stage, __syncthreads(), next stage.  Whole bottom subtrees thus execute inside one
+//     kernel launch; data handed from child to parent front travels through global memory (same SM, ordered by
+//     the barrier), so no pointer in here is const/__restrict__ for buffers written by these kernels.
+#pragma once
+#include "front_kernels.cuh"
+#include "solve_kernels.cuh"
+
+namespace b2 {
+
+constexpr int FW_WARPS = 4;
+
+struct ChildRec {          // one per (parent, child) edge, contiguous per parent, ascending child id
+    int64_t cb_off;        // child's update block in the workspace (ld = rc)
+    int64_t rel_off;       // child's relative indices into the parent front
+    int64_t cbv_off;       // child's contribution vector (solve)
+    int32_t rc;            // order of the child's update block
+    int32_t sn;
+};
+static_assert(sizeof(ChildRec) == 32, "ChildRec must be 32 bytes");
+
+struct WarpSched {
+    const int32_t* cta_ptr;     // [nCTA+1] stage ranges
+    const int32_t* stage_off;   // [nstage] offset into list
+    const int32_t* stage_cnt;   // [nstage]
+    const int32_t* list;        // supernode ids
+};
+
+__device__ __forceinline__ double fast_rcp(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = fma(r, fma(-x, r, 1.0), r);
+    r = fma(r, fma(-x, r, 1.0), r);
+    return r;
+}
+
+// ------------------------------------------------------------------------------------------------ factor
+// A front is owned by a TEAM of NW warps (NW = 1: order <= 32, NW = 2: order <= 64); thread `tid` of the team owns
+// ROW tid of the front and keeps it in registers as a sliding window: after pivot k, a[j] holds column k+1+j.
+// Per pivot the only shared-memory traffic is the broadcast of the pivot column (double-buffered, one team barrier).
+// Global loads are issued in independent batches (memory-level parallelism instead of one L2 round trip per element).
+#define B2_STAMP(idx) do { if (prof) { team_sync<NW>(team); if (tid == 0) prof[idx] = clock64(); } } while (0)
+
+template <int NW>
+__device__ __forceinline__ void team_sync(int team) {
+    if (NW == 1) __syncwarp();
+    else asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "r"(NW * 32) : "memory");
+}
+
+// shared-memory slice of one team:
+//   F[maxf*maxf] assembly area, later the finished panel | colbuf[2][2*FMAX] | rel[MAXC][FMAX] ints | recs[MAXC] |
+//   stage[STAGE] children's update blocks landed by cp.async
+constexpr int MAXC = 8;                                // children staged per round
+template <int NW>
+struct TeamSmem {
+    static constexpr int FMAX = 32 * NW;
+    static constexpr int STAGE = (NW == 1) ? 1024 : 8192;   // doubles; one child always fits (rc^2 <= (FMAX-1)^2)
+    static __host__ __device__ int doubles(int maxf) {
+        return maxf * maxf + 4 * FMAX + (MAXC * FMAX) / 2 + MAXC * 4 + STAGE;
+    }
+};
+
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+template <int NW>
+__device__ __forceinline__ void front_factor_team(const FactorArgs& a, const ChildRec* childrec, int s, double* sm_team,
+                                                  int tid, int team, int maxf, int& nneg, int& npert, long long* prof = nullptr) {
+    constexpr int FMAX = 32 * NW, TEAM = 32 * NW, STAGE = TeamSmem<NW>::STAGE;
+    double* F = sm_team;
+    double* colbuf = F + maxf * maxf;                  // [2][2*FMAX]
+    int* relst = (int*)(colbuf + 4 * FMAX);            // [MAXC][FMAX]
+    ChildRec* recs = (ChildRec*)(relst + MAXC * FMAX); // [MAXC]
+    double* stage = (double*)(recs + MAXC);            // [STAGE]
+    B2_STAMP(0);
+    const FrontDesc d = a.desc[s];
+    const int f = d.f, w = d.w, r = f - w;
+    B2_STAMP(1);
+    for (int i = tid; i < f * f; i += TEAM) F[i] = 0.0;
+    for (int i = tid; i < 4 * FMAX; i += TEAM) colbuf[i] = 0.0;
+    team_sync<NW>(team);
+    B2_STAMP(2);
+    {   // original matrix entries: panel layout pos + col*f == assembly-area layout
+        const int32_t* src = a.amap_src + d.amap_off;
+        const int32_t* dst = a.amap_dst + d.amap_off;
+        for (int t0 = 0; t0 < d.amap_cnt; t0 += 4 * TEAM) {
+            int sd[4], dd[4]; double v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int t = t0 + tid + u * TEAM;
+                sd[u] = (t < d.amap_cnt) ? src[t] : -1;
+                dd[u] = (t < d.amap_cnt) ? dst[t] : 0;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = (sd[u] >= 0) ? __ldg(a.A + sd[u]) : 0.0;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) if (sd[u] >= 0) F[dd[u]] = v[u];
+        }
+    }
+    team_sync<NW>(team);
+    B2_STAMP(3);
+    // ---- extend-add of the children (ascending id): rounds of <= MAXC children whose update blocks fit the stage;
+    //      every block of a round is landed in shared memory by cp.async in ONE memory round trip.
+    for (int c0 = 0; c0 < d.nchild;) {
+        const int nrec = min(MAXC, d.nchild - c0);
+        if (tid < nrec) recs[tid] = childrec[d.child_off + c0 + tid];
+        team_sync<NW>(team);
+        int nc = 0, tot = 0;
+        while (nc < nrec) { const int rc = recs[nc].rc; if (nc > 0 && tot + rc * rc > STAGE) break; tot += rc * rc; ++nc; }
+        int off = 0;
+        for (int c = 0; c < nc; ++c) {
+            const int rc = recs[c].rc;
+            const double* CB = a.ws + recs[c].cb_off;
+            for (int e = tid; e < rc * rc; e += TEAM) cp_async8(stage + off + e, CB + e);
+            if (tid < rc) cp_async4(relst + c * FMAX + tid, a.rel + recs[c].rel_off + tid);
+            off += rc * rc;
+        }
+        cp_async_wait_all();
+        team_sync<NW>(team);
+        off = 0;
+        for (int c = 0; c < nc; ++c) {
+            const int rc = recs[c].rc;
+            const int* rl = relst + c * FMAX;
+            const double* cs = stage + off;
+            if (tid < rc) {
+                const int ri = rl[tid];
+                for (int j0 = 0; j0 <= tid; j0 += 8) {         // row tid of the child block, 8 columns per batch
+                    double v[8], g[8]; int ix[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) { const int j = j0 + u; ix[u] = (j <= tid) ? ri + rl[j] * f : -1; }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) { const int j = j0 + u; v[u] = (ix[u] >= 0) ? cs[j * rc + tid] : 0.0; g[u] = (ix[u] >= 0) ? F[ix[u]] : 0.0; }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) if (ix[u] >= 0) F[ix[u]] = g[u] + v[u];
+                }
+            }
+            team_sync<NW>(team);
+            off += rc * rc;
+        }
+        c0 += nc;
+    }
+    B2_STAMP(4);
+    // row `tid` of the front into registers: a[j] = F(tid, j)
+    double av[FMAX + 1];
+#pragma unroll
+    for (int j = 0; j < FMAX; ++j) av[j] = (j < f && tid < f) ? F[tid + j * f] : 0.0;
+    av[FMAX] = 0.0;
+    for (int k = 0; k < w; ++k) {
+        double* cb = colbuf + (k & 1) * 2 * FMAX;
+        cb[tid] = av[0];
+        team_sync<NW>(team);
+        double dk = cb[k];
+        if (!(fabs(dk) >= a.eps)) { dk = (dk < 0.0) ? -a.eps : a.eps; if (tid == 0) ++npert; }
+        else if (dk < 0.0 && tid == 0) ++nneg;
+        const double dinv = fast_rcp(dk);
+        const double l = av[0] * dinv;
+        if (tid < f) F[tid + k * f] = (tid == k) ? dk : l;    // finished column k of the panel (rows < k: scratch)
+        const double* ub = cb + k + 1;
+#pragma unroll
+        for (int j0 = 0; j0 < FMAX; j0 += 8) {
+            if (k + 1 + j0 < f) {                       // team-uniform
+#pragma unroll
+                for (int j = j0; j < j0 + 8; ++j) av[j] = fma(-l, ub[j], av[j + 1]);
+            }
+        }
+    }
+    B2_STAMP(5);
+    team_sync<NW>(team);
+    // panel: column-major (forward solve, parent-independent) and row-major copy (backward solve)
+    {
+        double* Lp = a.L + d.lp_off;
+        for (int e = tid; e < f * w; e += TEAM) Lp[e] = F[e];
+        if (tid < f) {
+            double* Lt = a.Lt + d.lp_off + (size_t)tid * w;
+            for (int k = 0; k < w; ++k) Lt[k] = F[tid + k * f];
+        }
+        if (tid < w) a.dvec[d.col0 + tid] = F[tid + tid * f];
+    }
+    B2_STAMP(6);
+    // update block: av[j] now holds column w+j of row tid
+    if (tid >= w && tid < f) {
+        double* CBo = a.ws + d.cb_off;
+        const int ir = tid - w;
+#pragma unroll
+        for (int j = 0; j < FMAX; ++j) if (j <= ir) CBo[(size_t)j * r + ir] = av[j];
+    }
+    team_sync<NW>(team);
+    B2_STAMP(7);
+}
+
+// debug: re-factor ONE front with clock64() stamps at the phase boundaries (children's update blocks must be valid)
+template <int NW>
+__global__ void k_factor_team_profile(FactorArgs a, const ChildRec* childrec, int sn, int maxf, long long* prof, int reps) {
+    extern __shared__ double sm[];
+    int nneg = 0, npert = 0;
+    for (int r = 0; r < reps; ++r) front_factor_team<NW>(a, childrec, sn, sm, threadIdx.x, 0, maxf, nneg, npert, prof + 8 * r);
+}
+
+// teams per CTA: FW_WARPS one-warp teams, or ONE two-warp team (its staging area is large)
+template <int NW> struct TeamsPerCta { static constexpr int value = (NW == 1) ? FW_WARPS : 1; };
+
+template <int NW>
+__global__ void __launch_bounds__(TeamsPerCta<NW>::value * NW * 32) k_factor_warp(FactorArgs a, const ChildRec* childrec, WarpSched ws, int maxf) {
+    extern __shared__ double sm[];
+    constexpr int NTEAM = TeamsPerCta<NW>::value;
+    const int team = threadIdx.x / (32 * NW), tid = threadIdx.x % (32 * NW);
+    double* smt = sm + (size_t)team * TeamSmem<NW>::doubles(maxf);
+    const int s0 = ws.cta_ptr[blockIdx.x], s1 = ws.cta_ptr[blockIdx.x + 1];
+    int nneg = 0, npert = 0;
+    for (int st = s0; st < s1; ++st) {
+        const int off = ws.stage_off[st], cnt = ws.stage_cnt[st];
+        for (int q = team; q < cnt; q += NTEAM) front_factor_team<NW>(a, childrec, ws.list[off + q], smt, tid, team, maxf, nneg, npert);
+        if (s1 - s0 > 1) __syncthreads();
+    }
+    if (tid == 0) {
+        if (nneg) atomicAdd(a.counters + 0, nneg);
+        if (npert) atomicAdd(a.counters + 1, npert);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ solves
+// Forward:  thread = row i of the front; y_i in a register; the recurrence y_i -= L(i,k) y_k is carried by a
+//           shared-memory broadcast of y_k (double-buffered) -- L(i,k) streams from the column-major panel, prefetched
+//           8 pivots ahead, independent of the recurrence.
+// Backward: thread = pivot column j; t_j in a register; L(i,j) streams from the ROW-major panel copy `Lt`.
+template <int NW>
+__device__ __forceinline__ void front_fwd_team(const SolveArgs& a, const ChildRec* childrec, int s, double* sm_team, int tid, int team) {
+    constexpr int FMAX = 32 * NW;
+    double* ys = sm_team;                              // [FMAX] assembly of the front's rhs
+    double* yb = sm_team + FMAX;                       // [2][8] broadcast slots
+    const FrontDesc d = a.desc[s];
+    const int f = d.f, w = d.w;
+    ys[tid] = (tid < w) ? a.xp[d.col0 + tid] : 0.0;
+    team_sync<NW>(team);
+    for (int c = 0; c < d.nchild; ++c) {
+        const ChildRec rec = childrec[d.child_off + c];
+        if (tid < rec.rc) ys[a.rel[rec.rel_off + tid]] += a.cbv[rec.cbv_off + tid];
+        team_sync<NW>(team);
+    }
+    double y = ys[tid];
+    const double* Lp = a.L + d.lp_off;
+    for (int k0 = 0; k0 < w; k0 += 8) {
+        double l[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { const int k = k0 + u; l[u] = (k < w && tid > k && tid < f) ? Lp[(size_t)k * f + tid] : 0.0; }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int k = k0 + u;
+            if (k < w) {                                // team-uniform
+                double yk;
+                if (NW == 1) yk = __shfl_sync(0xffffffffu, y, k);
+                else {
+                    double* slot = yb + ((k & 1) * 8);
+                    if (tid == k) slot[0] = y;
+                    team_sync<NW>(team);
+                    yk = slot[0];
+                }
+                y = fma(-l[u], yk, y);
+            }
+        }
+    }
+    if (tid < f) { if (tid < w) a.xp[d.col0 + tid] = y; else a.cbv[a.cbv_off[s] + tid - w] = y; }
+    team_sync<NW>(team);
+}
+
+template <int NW>
+__device__ __forceinline__ void front_bwd_team(const SolveArgs& a, int s, double* sm_team, int tid, int team) {
+    constexpr int FMAX = 32 * NW;
+    double* xs = sm_team;                              // [FMAX] gathered ancestor values
+    double* xb = sm_team + FMAX;                       // [2][8]
+    const FrontDesc d = a.desc[s];
+    const int f = d.f, w = d.w, r = f - w;
+    const int32_t* rows = a.rows + d.rows_off + w;
+    if (tid < r) xs[tid] = a.xp[rows[tid]];
+    double t = (tid < w) ? a.xp[d.col0 + tid] * fast_rcp(a.dvec[d.col0 + tid]) : 0.0;
+    team_sync<NW>(team);
+    const double* Lt = a.Lt + d.lp_off;                // row-major f x w
+    {   // t_j -= sum_{i >= w} L(i,j) x_i : no recurrence, batches of 8 rows
+        double acc = 0.0;
+        for (int i0 = 0; i0 < r; i0 += 8) {
+            double l[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { const int i = i0 + u; l[u] = (i < r && tid < w) ? Lt[(size_t)(w + i) * w + tid] : 0.0; }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { const int i = i0 + u; if (i < r) acc = fma(l[u], xs[i], acc); }
+        }
+        t -= acc;
+    }
+    // back-substitution with L11': x_k final -> t_j -= L(k,j) x_k for j < k
+    for (int k0 = w - 1; k0 >= 1; k0 -= 8) {
+        double l[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { const int k = k0 - u; l[u] = (k >= 1 && tid < k) ? Lt[(size_t)k * w + tid] : 0.0; }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int k = k0 - u;
+            if (k >= 1) {
+                double xk;
+                if (NW == 1) xk = __shfl_sync(0xffffffffu, t, k);
+                else {
+                    double* slot = xb + ((k & 1) * 8);
+                    if (tid == k) slot[0] = t;
+                    team_sync<NW>(team);
+                    xk = slot[0];
+                }
+                t = fma(-l[u], xk, t);
+            }
+        }
+    }
+    if (tid < w) a.xp[d.col0 + tid] = t;
+    team_sync<NW>(team);
+}
+
+template <int NW>
+__global__ void __launch_bounds__(TeamsPerCta<NW>::value * NW * 32) k_fwd_warp2(SolveArgs a, const ChildRec* childrec, WarpSched ws) {
+    __shared__ double sm[TeamsPerCta<NW>::value][32 * NW + 16];
+    constexpr int NTEAM = TeamsPerCta<NW>::value;
+    const int team = threadIdx.x / (32 * NW), tid = threadIdx.x % (32 * NW);
+    const int s0 = ws.cta_ptr[blockIdx.x], s1 = ws.cta_ptr[blockIdx.x + 1];
+    for (int st = s0; st < s1; ++st) {
+        const int off = ws.stage_off[st], cnt = ws.stage_cnt[st];
+        for (int q = team; q < cnt; q += NTEAM) front_fwd_team<NW>(a, childrec, ws.list[off + q], sm[team], tid, team);
+        if (s1 - s0 > 1) __syncthreads();
+    }
+}
+
+template <int NW>
+__global__ void __launch_bounds__(TeamsPerCta<NW>::value * NW * 32) k_bwd_warp2(SolveArgs a, WarpSched ws) {
+    __shared__ double sm[TeamsPerCta<NW>::value][32 * NW + 16];
+    constexpr int NTEAM = TeamsPerCta<NW>::value;
+    const int team = threadIdx.x / (32 * NW), tid = threadIdx.x % (32 * NW);
+    const int s0 = ws.cta_ptr[blockIdx.x], s1 = ws.cta_ptr[blockIdx.x + 1];
+    for (int st = s1 - 1; st >= s0; --st) {
+        const int off = ws.stage_off[st], cnt = ws.stage_cnt[st];
+        for (int q = team; q < cnt; q += NTEAM) front_bwd_team<NW>(a, ws.list[off + q], sm[team], tid, team);
+        if (s1 - s0 > 1) __syncthreads();
+    }
+}
+
+}  // namespace b2

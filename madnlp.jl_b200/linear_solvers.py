@@ -56,7 +56,7 @@ class B200SparseSolver:
 
     def __del__(self):
         h = getattr(self, "_h", None)
-        if h:
+        if h and lib is not None:
             lib.b2_destroy(h)
             self._h = None
 
@@ -127,7 +127,7 @@ class B200DenseSolver:
 
     def __del__(self):
         h = getattr(self, "_h", None)
-        if h:
+        if h and lib is not None:
             lib.b2d_destroy(h)
             self._h = None
 

@@ -62,7 +62,7 @@ class DistributedSparseSolver:
 
     def __del__(self):
         h = getattr(self, "_h", None)
-        if h:
+        if h and lib is not None:
             lib.b2_destroy(h)
             self._h = None
 

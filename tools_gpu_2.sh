@@ -5,5 +5,5 @@ timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1
 tail -15 gpurun_out/pytest_gpu.log
 timeout 900 python bench.py --steps 24 --warmup 4 > gpurun_out/bench1.json 2> gpurun_out/bench1.err; echo "bench rc=$?"
 cat gpurun_out/bench1.json; tail -5 gpurun_out/bench1.err
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 1 --cpu-sample-steps 1 > gpurun_out/ncu_bench.log 2>&1
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 1 --cpu-sample-steps 1 > gpurun_out/ncu_bench.log 2>&1
 echo "ncu rc=$?"; wc -l gpurun_out/launches.csv
