@@ -173,6 +173,8 @@ def run_b200(args, rank, world, local_rank):
     opt = pkg.capi.default_options()
     if os.environ.get("B2_FUSE_MAX"):
         opt.fuse_max_fronts = int(os.environ["B2_FUSE_MAX"])
+    if os.environ.get("B2_DEP"):
+        opt.dep_schedule = int(os.environ["B2_DEP"])
     if os.environ.get("B2_NEMIN"):
         opt.nemin = int(os.environ["B2_NEMIN"])
     kkt = K.create_kkt_system(K.SparseCondensedKKTSystem, cb, solver_cls, opt)

@@ -66,7 +66,10 @@ typedef struct b2_options {
                                 primal neighbours, so that a zero (2,2) block never yields a structurally zero pivot */
     int32_t fuse_max_fronts; /* bottom elimination subtrees with at most this many (warp-class) fronts run inside ONE
                                 CTA of a single launch (0 = plain level-by-level schedule)                      */
-    int32_t reserved[6];
+    int32_t dep_schedule;    /* bit 0 (factorisation), bit 1 (solves): when every front is team-class (order <= 64) run the sweep
+                                as ONE launch whose CTAs wait on their children's completion flags instead of on
+                                kernel boundaries.  Default 1: measured faster for the factorisation only.     */
+    int32_t reserved[5];
 } b2_options;
 
 int b2_options_default(b2_options* opt);

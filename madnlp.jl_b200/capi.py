@@ -44,7 +44,7 @@ class Options(C.Structure):
     _fields_ = [
         ("ordering", C.c_int32), ("nemin", C.c_int32), ("relax_zeros", C.c_double), ("pivot_eps", C.c_double),
         ("use_cuda_graph", C.c_int32), ("small_front_max", C.c_int32), ("n_parts", C.c_int32), ("part_rank", C.c_int32),
-        ("kkt_n_primal", C.c_int32), ("fuse_max_fronts", C.c_int32), ("reserved", C.c_int32 * 6),
+        ("kkt_n_primal", C.c_int32), ("fuse_max_fronts", C.c_int32), ("dep_schedule", C.c_int32), ("reserved", C.c_int32 * 5),
     ]
 
 
@@ -104,6 +104,7 @@ PROTOTYPES = {
     "b2_symbolic_query": (C.c_int, [_p, C.POINTER(SymbolicSizes)]),
     "b2_symbolic_export": (C.c_int, [_p] + [_p] * 13),
     "b2_symbolic_owner": (C.c_int, [_p, _p]),
+    "b2_symbolic_exchange": (C.c_int, [_p, _p, C.POINTER(_i64), C.POINTER(_i64)]),
     "b2_debug_get_factor": (C.c_int, [_p, _p, _p]),
     "b2_debug_profile_front": (C.c_int, [_p, _i32, _i32, _p]),
     "b2d_create": (C.c_int, [_i32, _i32, _p, C.POINTER(Options), _PP]),

@@ -571,7 +571,7 @@ void analyse(int32_t n, const int32_t* colptr, const int32_t* rowval, const Anal
                 if ((pass == 0) != boundary) continue;
                 int64_t r = (int64_t)below[s].size();
                 o[s] = off;
-                off += r * r;
+                off += (r * r + 1) & ~(int64_t)1;      // even number of doubles: 16-byte aligned blocks (cp.async.cg)
             }
             if (pass == 0) S.exch_cb = off;
         }

@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(SOLVE_WARPS * 32) k_bwd_warp(SolveArgs a, cons
 }
 
 // ---- forward, CTA per front (any size; panel streamed from HBM, y in shared memory)
-constexpr int SOLVE_CTA = 256;
+constexpr int SOLVE_CTA = 1024;   // one CTA streams the whole panel: many threads x unrolled independent loads = MLP
 __global__ void __launch_bounds__(SOLVE_CTA) k_fwd_cta(SolveArgs a, const int32_t* __restrict__ list) {
     extern __shared__ double y[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -119,7 +119,13 @@ __global__ void __launch_bounds__(SOLVE_CTA) k_fwd_cta(SolveArgs a, const int32_
         __syncthreads();
         for (int i = k0 + nb + tid; i < f; i += SOLVE_CTA) {
             double acc = y[i];
-            for (int k = k0; k < k0 + nb; ++k) acc = fma(-Lp[(size_t)k * f + i], y[k], acc);
+            const double* col = Lp + (size_t)k0 * f + i;
+            if (nb == 32) {
+#pragma unroll
+                for (int k = 0; k < 32; ++k) acc = fma(-col[(size_t)k * f], y[k0 + k], acc);
+            } else {
+                for (int k = 0; k < nb; ++k) acc = fma(-col[(size_t)k * f], y[k0 + k], acc);
+            }
             y[i] = acc;
         }
         __syncthreads();
@@ -147,7 +153,16 @@ __global__ void __launch_bounds__(SOLVE_CTA) k_bwd_cta(SolveArgs a, const int32_
         // x[k] -= sum_{i >= k0+nb} L(i,k) x[i]   (one warp per pivot column, coalesced over i)
         for (int k = k0 + warp; k < k0 + nb; k += NW) {
             double sacc = 0.0;
-            for (int i = k0 + nb + lane; i < f; i += 32) sacc = fma(Lp[(size_t)k * f + i], x[i], sacc);
+            const double* col = Lp + (size_t)k * f;
+            int i = k0 + nb + lane;
+            for (; i + 7 * 32 < f; i += 8 * 32) {
+                double v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = col[i + 32 * u];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) sacc = fma(v[u], x[i + 32 * u], sacc);
+            }
+            for (; i < f; i += 32) sacc = fma(col[i], x[i], sacc);
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
             if (lane == 0) x[k] -= sacc;

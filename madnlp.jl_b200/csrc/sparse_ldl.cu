@@ -11,6 +11,7 @@
 #include "front_kernels.cuh"
 #include "solve_kernels.cuh"
 #include "warp_kernels.cuh"
+#include "bigsolve_kernels.cuh"
 
 using namespace b2;
 
@@ -25,11 +26,15 @@ struct LevelSched {
     WarpLaunch W, W2;                               // fronts of order <= 32 / <= 64
     int offM = 0, nM = 0, maxfM = 0;                // shared-memory CTA class
     int offB = 0, nB = 0, maxfB = 0, maxwB = 0, maxchildB = 0, maxamapB = 0, maxrB = 0;   // HBM-resident class
-    int offC = 0, nC = 0, maxfC = 0;                // M and B fronts together, for the CTA solve kernels
+    int partialB = 0;                               // some front's pivot count is not a multiple of BIG_NB
+    int offC = 0, nC = 0, maxfC = 0, maxwC = 0;     // M and B fronts together, for the multi-CTA solve kernels
 };
 struct Phase {
     WarpLaunch fused;                               // bottom subtrees, one CTA each (n_cta == 0: none)
     std::vector<LevelSched> lev;
+    // single-launch dependency-driven schedule (used instead of fused + levels when every front is team-class)
+    int offAllC = 0, nAllC = 0, maxwAllC = 0;       // every M/B front of the phase (diagonal-block inversion)
+    int dep_ngroup = 0, dep_type_off = 0, dep_ptr_off = 0, dep_tasks_off = 0, dep_maxf1 = 0, dep_maxf2 = 0;
     cudaGraphExec_t g_factor = nullptr, g_fwd = nullptr, g_bwd = nullptr;
     int64_t n_factor_launches = 0, n_solve_launches = 0;
     int64_t n_fused_fronts = 0;
@@ -54,6 +59,9 @@ struct b2_solver {
     // numeric storage
     DevBuf<double> d_L, d_Lt, d_ws, d_dvec, d_xp, d_cbv;
     DevBuf<int32_t> d_counters;
+    DevBuf<double> d_Linv, d_side;
+    DevBuf<int64_t> d_linv_off;
+    DevBuf<int32_t> d_flags, d_parent;   // dependency flags [3][nsuper], supernode parents
     int32_t* h_counters = nullptr;   // pinned
     std::vector<int64_t> cbv_off;
     int64_t exch_cbv = 0;
@@ -91,6 +99,16 @@ SolveArgs solve_args(b2_solver* s) {
     return a;
 }
 
+BigSolveArgs big_solve_args(b2_solver* s) {
+    BigSolveArgs b;
+    b.s = solve_args(s);
+    b.Linv = s->d_Linv.p;
+    b.linv_off = s->d_linv_off.p;
+    b.side = s->d_side.p;
+    return b;
+}
+constexpr size_t BS_SMEM = (size_t)(BS * (BS + 1) + 2 * BS + 4 * BSF_ROWS) * sizeof(double);
+
 inline size_t smem_front(int f) { return (size_t)f * f * sizeof(double); }
 
 WarpSched warp_sched(b2_solver* s, const WarpLaunch& L) {
@@ -119,6 +137,14 @@ int64_t enqueue_factor(b2_solver* s, int ph, cudaStream_t st) {
         }
         ++nl;
     };
+    if (P.dep_ngroup && (s->opt.dep_schedule & 1)) {
+        DepSched ds;
+        ds.grp_type = sched + P.dep_type_off; ds.grp_ptr = sched + P.dep_ptr_off; ds.tasks = sched + P.dep_tasks_off; ds.ngroup = P.dep_ngroup;
+        cudaMemsetAsync(s->d_flags.p, 0, (size_t)s->S.nsuper * sizeof(int32_t), st);
+        const size_t sm = sizeof(double) * std::max<size_t>((size_t)FW_WARPS * TeamSmem<1>::doubles(P.dep_maxf1), (size_t)TeamSmem<2>::doubles(P.dep_maxf2));
+        k_factor_dep<<<P.dep_ngroup, 128, sm, st>>>(a, s->d_childrec.p, ds, P.dep_maxf1, P.dep_maxf2, s->d_flags.p, s->d_counters.p + 4);
+        return 2;
+    }
     if (P.fused.n_cta) warp_launch(P.fused);
     for (const LevelSched& lv : P.lev) {
         if (lv.W.n_cta) warp_launch(lv.W);
@@ -137,20 +163,36 @@ int64_t enqueue_factor(b2_solver* s, int ph, cudaStream_t st) {
                 k_big_extend_add<<<dim3(std::max(1, std::min(2 * nsm / lv.nB + 1, (lv.maxrB * 32 + 255) / 256)), lv.nB), 256, 0, st>>>(a, lb, c);
                 ++nl;
             }
-            const int nsteps = (lv.maxwB + BIG_NB - 1) / BIG_NB;
-            for (int step = 0; step < nsteps; ++step) {
-                const int kb = step * BIG_NB;
-                k_big_diag<<<lv.nB, 32, 0, st>>>(a, lb, step);
-                ++nl;
-                const int rem = lv.maxfB - kb - 1;      // rows below the (possibly partial) pivot block, upper bound
-                if (rem > 0) {
+            constexpr int OB = 128;                      // outer panel: 4 steps of BIG_NB columns
+            for (int ob = 0; ob < lv.maxwB; ob += OB) {
+                for (int kb = ob; kb < std::min(ob + OB, lv.maxwB); kb += BIG_NB) {
+                    const int step = kb / BIG_NB;
+                    k_big_diag<<<lv.nB, 32, 0, st>>>(a, lb, step);
+                    ++nl;
+                    const int rem = lv.maxfB - kb - 1;      // rows below the (possibly partial) pivot block, upper bound
+                    if (rem <= 0) continue;
                     k_big_panel<<<dim3((rem + BIG_ROWS - 1) / BIG_ROWS, lv.nB), BIG_ROWS, 0, st>>>(a, lb, step);
+                    ++nl;
+                    const int ncols = ob + OB - (kb + BIG_NB);      // rest of the outer panel
+                    if (ncols > 0 || lv.partialB) {                 // (a partial last block leaves columns [kb+nb, kb+32) to serve)
+                        const int nt = (rem + UT - 1) / UT;
+                        k_big_update<<<dim3(nt, (ncols + BIG_NB + UT - 1) / UT, lv.nB), 256, 0, st>>>(a, lb, kb, BIG_NB, BIG_NB, BIG_NB + ncols, 1);
+                        ++nl;
+                    }
+                }
+                const int rem = lv.maxfB - ob - 1;
+                if (rem > 0) {                              // everything behind the outer panel, all its pivots at once
                     const int nt = (rem + UT - 1) / UT;
-                    k_big_update<<<dim3(nt, nt, lv.nB), 256, 0, st>>>(a, lb, step);
-                    nl += 2;
+                    k_big_update<<<dim3(nt, nt, lv.nB), 256, 0, st>>>(a, lb, ob, OB, OB, 1 << 30, 0);
+                    ++nl;
                 }
             }
         }
+    }
+    if (P.nAllC) {
+        k_big_inv<<<dim3((P.maxwAllC + BS - 1) / BS, P.nAllC), BS, (size_t)BS * (BS + 1) * sizeof(double), st>>>(
+            s->d_desc.p, sched + P.offAllC, s->d_L.p, s->d_Linv.p, s->d_linv_off.p);
+        ++nl;
     }
     return nl;
 }
@@ -170,6 +212,15 @@ int64_t enqueue_solve(b2_solver* s, int ph, bool forward, cudaStream_t st) {
         }
         ++nl;
     };
+    if (P.dep_ngroup && (s->opt.dep_schedule & 2)) {
+        DepSched ds;
+        ds.grp_type = sched + P.dep_type_off; ds.grp_ptr = sched + P.dep_ptr_off; ds.tasks = sched + P.dep_tasks_off; ds.ngroup = P.dep_ngroup;
+        int* flags = s->d_flags.p + (size_t)(forward ? 1 : 2) * s->S.nsuper;
+        cudaMemsetAsync(flags, 0, (size_t)s->S.nsuper * sizeof(int32_t), st);
+        if (forward) k_fwd_dep<<<P.dep_ngroup, 128, 0, st>>>(a, s->d_childrec.p, ds, flags, s->d_counters.p + 4);
+        else k_bwd_dep<<<P.dep_ngroup, 128, 0, st>>>(a, ds, s->d_parent.p, flags, s->d_counters.p + 4);
+        return 2;
+    }
     if (forward && P.fused.n_cta) warp_launch(P.fused);
     const int nlev = (int)P.lev.size();
     for (int q = 0; q < nlev; ++q) {
@@ -177,10 +228,28 @@ int64_t enqueue_solve(b2_solver* s, int ph, bool forward, cudaStream_t st) {
         if (lv.W.n_cta) warp_launch(lv.W);
         if (lv.W2.n_cta) warp_launch(lv.W2);
         if (lv.nC) {
-            const size_t sm = (size_t)lv.maxfC * sizeof(double);
-            if (forward) k_fwd_cta<<<lv.nC, SOLVE_CTA, sm, st>>>(a, sched + lv.offC);
-            else k_bwd_cta<<<lv.nC, SOLVE_CTA, sm, st>>>(a, sched + lv.offC);
-            ++nl;
+            const BigSolveArgs bs = big_solve_args(s);
+            const int32_t* lc = sched + lv.offC;
+            const int nblk = (lv.maxwC + BS - 1) / BS;
+            if (forward) {
+                k_bs_fwd_init<<<lv.nC, 1024, 0, st>>>(bs, lc);
+                ++nl;
+                for (int b = 0; b < nblk; ++b) {
+                    const int rows = std::max(1, lv.maxfC - b * BS - 1);
+                    k_bs_fwd<<<dim3((rows + BSF_ROWS - 1) / BSF_ROWS, lv.nC), 256, BS_SMEM, st>>>(bs, lc, b);
+                    ++nl;
+                }
+            } else {
+                k_bs_bwd_init<<<dim3((lv.maxwC + 255) / 256, lv.nC), 256, 0, st>>>(bs, lc);
+                ++nl;
+                for (int b = nblk - 1; b >= 0; --b) {
+                    const int cols = std::max(1, b * BS);
+                    k_bs_bwd<<<dim3((cols + BSB_COLS - 1) / BSB_COLS, lv.nC), 256, BS_SMEM, st>>>(bs, lc, b);
+                    ++nl;
+                }
+                k_bs_bwd_finish<<<dim3((lv.maxwC + 255) / 256, lv.nC), 256, 0, st>>>(bs, lc);
+                ++nl;
+            }
         }
     }
     if (!forward && P.fused.n_cta) warp_launch(P.fused);
@@ -191,8 +260,10 @@ int set_smem_attrs() {
     B2_CUDA(cudaFuncSetAttribute(k_front_smem<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     B2_CUDA(cudaFuncSetAttribute(k_factor_warp<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     B2_CUDA(cudaFuncSetAttribute(k_factor_warp<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    B2_CUDA(cudaFuncSetAttribute(k_fwd_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    B2_CUDA(cudaFuncSetAttribute(k_bwd_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    B2_CUDA(cudaFuncSetAttribute(k_factor_dep, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    B2_CUDA(cudaFuncSetAttribute(k_big_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    B2_CUDA(cudaFuncSetAttribute(k_bs_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    B2_CUDA(cudaFuncSetAttribute(k_bs_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     return B2_OK;
 }
 
@@ -249,9 +320,42 @@ void build_schedule(b2_solver* s) {
     };
     for (int ph = 0; ph < 2; ++ph) {
         Phase& P = s->phase[ph];
-        P.lev.clear(); P.fused = WarpLaunch(); P.n_fused_fronts = 0;
+        P.lev.clear(); P.fused = WarpLaunch(); P.n_fused_fronts = 0; P.dep_ngroup = 0;
         std::vector<char> mine(ns, 0);
         for (int sn = 0; sn < ns; ++sn) mine[sn] = (ph == 0) ? (S.owner[sn] == rank) : (S.owner[sn] == -1);
+        // ---- dependency-driven single launch: every front of the phase is team-class and the tree is not sharded
+        if (s->opt.dep_schedule && s->opt.n_parts <= 1 && wmax > 32) {
+            bool all_team = true;
+            int cntm = 0;
+            for (int sn = 0; sn < ns && all_team; ++sn) if (mine[sn]) { int w, f; fdim(sn, w, f); all_team = f <= wmax; ++cntm; }
+            if (all_team && cntm > 0) {
+                std::vector<int32_t> order;
+                for (int l = 0; l < S.nlevels; ++l)
+                    for (int q = S.level_ptr[l]; q < S.level_ptr[l + 1]; ++q) if (mine[S.level_sn[q]]) order.push_back(S.level_sn[q]);
+                std::vector<int32_t> gtype, gptr(1, 0), tasks;
+                size_t k = 0;
+                while (k < order.size()) {
+                    int w, f; fdim(order[k], w, f);
+                    if (f > 32) {
+                        gtype.push_back(2); tasks.push_back(order[k]); ++k;
+                        P.dep_maxf2 = std::max(P.dep_maxf2, f);
+                    } else {
+                        gtype.push_back(1);
+                        int c = 0;
+                        while (k < order.size() && c < FW_WARPS) {
+                            int w2, f2; fdim(order[k], w2, f2);
+                            if (f2 > 32) break;
+                            tasks.push_back(order[k]); P.dep_maxf1 = std::max(P.dep_maxf1, f2); ++k; ++c;
+                        }
+                    }
+                    gptr.push_back((int32_t)tasks.size());
+                }
+                P.dep_ngroup = (int)gtype.size();
+                P.dep_type_off = (int)sched.size(); sched.insert(sched.end(), gtype.begin(), gtype.end());
+                P.dep_ptr_off = (int)sched.size(); sched.insert(sched.end(), gptr.begin(), gptr.end());
+                P.dep_tasks_off = (int)sched.size(); sched.insert(sched.end(), tasks.begin(), tasks.end());
+            }
+        }
         // ---- bottom subtrees that can run inside one CTA: all fronts warp-class, at most fuse_max fronts
         std::vector<int32_t> cnt(ns, 0);
         std::vector<char> okw(ns, 0);
@@ -317,6 +421,8 @@ void build_schedule(b2_solver* s) {
             ulev[sn] = lv;
             nul = std::max(nul, lv + 1);
         }
+        std::vector<int32_t> allC;
+        P.maxwAllC = 0;
         std::vector<std::vector<int32_t>> by_level(nul);
         for (int sn = 0; sn < ns; ++sn) if (ulev[sn] >= 0) by_level[ulev[sn]].push_back(sn);
         for (int l = 0; l < nul; ++l) {
@@ -332,13 +438,14 @@ void build_schedule(b2_solver* s) {
                 else {
                     Bx.push_back(sn);
                     lv.maxfB = std::max(lv.maxfB, f); lv.maxwB = std::max(lv.maxwB, w);
+                    if (w % BIG_NB) lv.partialB = 1;
                     lv.maxchildB = std::max(lv.maxchildB, nch); lv.maxamapB = std::max(lv.maxamapB, nam);
                     for (int c = S.child_ptr[sn]; c < S.child_ptr[sn + 1]; ++c) {
                         int cw, cf; fdim(S.child_idx[c], cw, cf);
                         lv.maxrB = std::max(lv.maxrB, cf - cw);
                     }
                 }
-                if (f > wmax) lv.maxfC = std::max(lv.maxfC, f);
+                if (f > wmax) { lv.maxfC = std::max(lv.maxfC, f); lv.maxwC = std::max(lv.maxwC, w); allC.push_back(sn); P.maxwAllC = std::max(P.maxwAllC, w); }
             }
             auto level_launch = [&](const std::vector<int32_t>& X, int nw) {
                 std::vector<std::vector<std::vector<int32_t>>> ctas;
@@ -356,6 +463,7 @@ void build_schedule(b2_solver* s) {
             lv.offC = lv.offM; lv.nC = lv.nM + lv.nB;        // M and B lists are adjacent
             P.lev.push_back(lv);
         }
+        P.offAllC = (int)sched.size(); P.nAllC = (int)allC.size(); sched.insert(sched.end(), allC.begin(), allC.end());
     }
     if (sched.empty()) sched.push_back(0);
     B2_CUDA_THROW(s->d_sched.upload(sched.data(), sched.size()));
@@ -468,15 +576,31 @@ int create_common(int32_t n, int64_t nnz, const int32_t* colptr_h, const int32_t
         }
         B2_CUDA_THROW(s->d_L.alloc((size_t)S.lp_off[ns]));
         B2_CUDA_THROW(s->d_Lt.alloc((size_t)S.lp_off[ns]));
+        {
+            const int wmax_ = std::min(W_MAX, s->opt.small_front_max);
+            std::vector<int64_t> lo(ns, -1);
+            int64_t tot = 0;
+            for (int sn = 0; sn < ns; ++sn) {
+                const int w = S.sn_first[sn + 1] - S.sn_first[sn];
+                const int f = (int)(S.rows_ptr[sn + 1] - S.rows_ptr[sn]);
+                if (f > wmax_) { lo[sn] = tot; tot += (int64_t)((w + BS - 1) / BS) * BS * BS; }
+            }
+            B2_CUDA_THROW(s->d_linv_off.upload(lo.data(), lo.size()));
+            B2_CUDA_THROW(s->d_Linv.alloc((size_t)std::max<int64_t>(1, tot)));
+            B2_CUDA_THROW(s->d_side.alloc(tot > 0 ? (size_t)n : 1));
+        }
         B2_CUDA_THROW(s->d_ws.alloc((size_t)std::max<int64_t>(1, S.cb_off[ns])));
         B2_CUDA_THROW(s->d_dvec.alloc(n));
         B2_CUDA_THROW(s->d_xp.alloc(n));
         B2_CUDA_THROW(s->d_cbv.alloc((size_t)std::max<int64_t>(1, s->cbv_off[ns])));
-        B2_CUDA_THROW(s->d_counters.alloc(4));
-        B2_CUDA_THROW(cudaMemset(s->d_counters.p, 0, 4 * sizeof(int32_t)));
+        B2_CUDA_THROW(s->d_counters.alloc(8));
+        B2_CUDA_THROW(cudaMemset(s->d_counters.p, 0, 8 * sizeof(int32_t)));
+        B2_CUDA_THROW(s->d_flags.alloc((size_t)3 * ns + 1));
+        B2_CUDA_THROW(cudaMemset(s->d_flags.p, 0, s->d_flags.bytes()));
+        B2_CUDA_THROW(s->d_parent.upload(S.sn_parent.data(), S.sn_parent.size()));
         B2_CUDA_THROW(cudaMemset(s->d_ws.p, 0, s->d_ws.bytes()));
         B2_CUDA_THROW(cudaMemset(s->d_cbv.p, 0, s->d_cbv.bytes()));
-        B2_CUDA_THROW(cudaMallocHost((void**)&s->h_counters, 4 * sizeof(int32_t)));
+        B2_CUDA_THROW(cudaMallocHost((void**)&s->h_counters, 8 * sizeof(int32_t)));
         B2_CUDA_THROW(cudaStreamCreateWithFlags(&s->cap_stream, cudaStreamNonBlocking));
         build_schedule(s);
         if (set_smem_attrs() != B2_OK) throw std::runtime_error("attr");
@@ -536,6 +660,7 @@ int b2_options_default(b2_options* opt) {
     opt->use_cuda_graph = 1;
     opt->small_front_max = 160;
     opt->fuse_max_fronts = 16;
+    opt->dep_schedule = 1;
     opt->n_parts = 1;
     opt->part_rank = 0;
     return B2_OK;
@@ -570,7 +695,7 @@ int b2_factorize_local(b2_solver* s, void* stream) {
     if (!s || s->symbolic_only) { set_error("b2_factorize: solver has no device state"); return B2_ERR_INVALID; }
     if (!s->nzval_d) { set_error("b2_factorize: value pointer not set"); return B2_ERR_INVALID; }
     cudaStream_t st = as_stream(stream);
-    B2_CUDA(cudaMemsetAsync(s->d_counters.p, 0, 4 * sizeof(int32_t), st));
+    B2_CUDA(cudaMemsetAsync(s->d_counters.p, 0, 8 * sizeof(int32_t), st));
     if (s->opt.n_parts > 1 && s->S.exch_cb > 0) B2_CUDA(cudaMemsetAsync(s->d_ws.p, 0, (size_t)s->S.exch_cb * sizeof(double), st));
     return run_factor_phase(s, 0, st);
 }
@@ -593,8 +718,9 @@ int b2_factorize(b2_solver* s, void* stream) {
 int b2_inertia(b2_solver* s, int64_t* num_pos, int64_t* num_zero, int64_t* num_neg, void* stream) {
     if (!s || s->symbolic_only || !s->factorized) { set_error("b2_inertia: not factorized"); return B2_ERR_FACTORIZATION; }
     cudaStream_t st = as_stream(stream);
-    B2_CUDA(cudaMemcpyAsync(s->h_counters, s->d_counters.p, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    B2_CUDA(cudaMemcpyAsync(s->h_counters, s->d_counters.p, 8 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     B2_CUDA(cudaStreamSynchronize(st));
+    if (s->h_counters[4]) { set_error("b2: dependency wait timed out inside the single-launch schedule"); return B2_ERR_FACTORIZATION; }
     // single-part: everything is in the "local" phase.  Multi-part: this is only this rank's view; the host layer
     // all-reduces b2_inertia_parts() instead.
     const int64_t neg = (int64_t)s->h_counters[0] + s->h_counters[2], zero = (int64_t)s->h_counters[1] + s->h_counters[3];
@@ -774,6 +900,14 @@ int b2_debug_get_factor(b2_solver* s, double* lval_h, double* dvec_h) {
     return B2_OK;
 }
 
+int b2_symbolic_exchange(b2_solver* s, int64_t* cbv_off, int64_t* exch_cb, int64_t* exch_cbv) {
+    if (!s) return B2_ERR_INVALID;
+    if (cbv_off) std::memcpy(cbv_off, s->cbv_off.data(), s->cbv_off.size() * sizeof(int64_t));
+    if (exch_cb) *exch_cb = s->S.exch_cb;
+    if (exch_cbv) *exch_cbv = s->exch_cbv;
+    return B2_OK;
+}
+
 int b2_symbolic_owner(b2_solver* s, int32_t* owner) {
     if (!s || !owner) return B2_ERR_INVALID;
     std::memcpy(owner, s->S.owner.data(), s->S.owner.size() * sizeof(int32_t));
@@ -791,7 +925,8 @@ struct b2d_solver {
     int32_t N = 0, lda = 0;
     const double* A_d = nullptr;
     b2_options opt;
-    DevBuf<double> fact, dvec;
+    DevBuf<double> fact, dvec, linv, side;
+    DevBuf<int64_t> linv_off;
     DevBuf<FrontDesc> desc;
     DevBuf<int32_t> list, counters;
     int32_t* h_counters = nullptr;
@@ -819,17 +954,27 @@ void enqueue_dense_factor(b2d_solver* s, cudaStream_t st) {
     const int N = s->N;
     cudaMemsetAsync(s->counters.p, 0, 4 * sizeof(int32_t), st);
     k_copy_lower<<<dim3(std::max(1, std::min(8, (N + 255) / 256)), N), 256, 0, st>>>(N, s->lda, s->A_d, s->fact.p);
-    const int nsteps = (N + BIG_NB - 1) / BIG_NB;
-    for (int step = 0; step < nsteps; ++step) {
-        const int kb = step * BIG_NB;
-        k_big_diag<<<1, 32, 0, st>>>(a, s->list.p, step);
-        const int rem = N - kb - std::min(BIG_NB, N - kb);
-        if (rem > 0) {
+    constexpr int OB = 128;
+    for (int ob = 0; ob < N; ob += OB) {
+        for (int kb = ob; kb < std::min(ob + OB, N); kb += BIG_NB) {
+            const int step = kb / BIG_NB;
+            k_big_diag<<<1, 32, 0, st>>>(a, s->list.p, step);
+            const int rem = N - kb - 1;
+            if (rem <= 0) continue;
             k_big_panel<<<dim3((rem + BIG_ROWS - 1) / BIG_ROWS, 1), BIG_ROWS, 0, st>>>(a, s->list.p, step);
+            const int ncols = ob + OB - (kb + BIG_NB);
+            if (ncols > 0 || (N % BIG_NB)) {
+                const int nt = (rem + UT - 1) / UT;
+                k_big_update<<<dim3(nt, (ncols + BIG_NB + UT - 1) / UT, 1), 256, 0, st>>>(a, s->list.p, kb, BIG_NB, BIG_NB, BIG_NB + ncols, 1);
+            }
+        }
+        const int rem = N - ob - 1;
+        if (rem > 0) {
             const int nt = (rem + UT - 1) / UT;
-            k_big_update<<<dim3(nt, nt, 1), 256, 0, st>>>(a, s->list.p, step);
+            k_big_update<<<dim3(nt, nt, 1), 256, 0, st>>>(a, s->list.p, ob, OB, OB, 1 << 30, 0);
         }
     }
+    k_big_inv<<<dim3((N + BS - 1) / BS, 1), BS, (size_t)BS * (BS + 1) * sizeof(double), st>>>(s->desc.p, s->list.p, s->fact.p, s->linv.p, s->linv_off.p);
 }
 }  // namespace
 
@@ -850,7 +995,9 @@ int b2d_create(int32_t N, int32_t lda, const double* A_d, const b2_options* opt,
     std::memset(&d, 0, sizeof(d));
     d.col0 = 0; d.w = N; d.f = N;
     int32_t zero = 0;
-    if (s->fact.alloc((size_t)N * N) != cudaSuccess || s->dvec.alloc(N) != cudaSuccess || s->desc.upload(&d, 1) != cudaSuccess ||
+    int64_t zero64 = 0;
+    if (s->side.alloc(N) != cudaSuccess || s->linv.alloc((size_t)((N + BS - 1) / BS) * BS * BS) != cudaSuccess || s->linv_off.upload(&zero64, 1) != cudaSuccess ||
+        s->fact.alloc((size_t)N * N) != cudaSuccess || s->dvec.alloc(N) != cudaSuccess || s->desc.upload(&d, 1) != cudaSuccess ||
         s->list.upload(&zero, 1) != cudaSuccess || s->counters.alloc(4) != cudaSuccess ||
         cudaMallocHost((void**)&s->h_counters, 4 * sizeof(int32_t)) != cudaSuccess ||
         cudaStreamCreateWithFlags(&s->cap_stream, cudaStreamNonBlocking) != cudaSuccess ||
@@ -904,13 +1051,24 @@ int b2d_solve(b2d_solver* s, double* x_d, int32_t nrhs, void* stream) {
     if (!s || !x_d || nrhs < 1) { set_error("b2d_solve: invalid argument"); return B2_ERR_INVALID; }
     if (!s->factorized) { set_error("b2d_solve: not factorized"); return B2_ERR_SOLVE; }
     cudaStream_t st = as_stream(stream);
+    const int N = s->N;
+    const int nblk = (N + BS - 1) / BS;
     for (int c = 0; c < nrhs; ++c) {
-        SolveArgs a;
-        a.desc = s->desc.p; a.rows = nullptr; a.child_idx = nullptr; a.rel = nullptr; a.cbv_off = nullptr;
-        a.L = s->fact.p; a.dvec = s->dvec.p; a.xp = x_d + (size_t)c * s->N; a.cbv = nullptr;
-        const size_t sm = (size_t)s->N * sizeof(double);
-        k_fwd_cta<<<1, SOLVE_CTA, sm, st>>>(a, s->list.p);
-        k_bwd_cta<<<1, SOLVE_CTA, sm, st>>>(a, s->list.p);
+        BigSolveArgs bs;
+        SolveArgs& a = bs.s;
+        a.desc = s->desc.p; a.rows = nullptr; a.child_idx = nullptr; a.rel = nullptr; a.cbv_off = s->linv_off.p;   // single zero offset
+        a.L = s->fact.p; a.Lt = nullptr; a.dvec = s->dvec.p; a.xp = x_d + (size_t)c * N; a.cbv = nullptr;
+        bs.Linv = s->linv.p; bs.linv_off = s->linv_off.p; bs.side = s->side.p;
+        for (int b = 0; b < nblk; ++b) {
+            const int rows = std::max(1, N - b * BS - 1);
+            k_bs_fwd<<<dim3((rows + BSF_ROWS - 1) / BSF_ROWS, 1), 256, BS_SMEM, st>>>(bs, s->list.p, b);
+        }
+        k_bs_bwd_init<<<dim3((N + 255) / 256, 1), 256, 0, st>>>(bs, s->list.p);
+        for (int b = nblk - 1; b >= 0; --b) {
+            const int cols = std::max(1, b * BS);
+            k_bs_bwd<<<dim3((cols + BSB_COLS - 1) / BSB_COLS, 1), 256, BS_SMEM, st>>>(bs, s->list.p, b);
+        }
+        k_bs_bwd_finish<<<dim3((N + 255) / 256, 1), 256, 0, st>>>(bs, s->list.p);
     }
     B2_CUDA(cudaGetLastError());
     return B2_OK;

@@ -63,9 +63,10 @@ constexpr int MAXC = 8;                                // children staged per ro
 template <int NW>
 struct TeamSmem {
     static constexpr int FMAX = 32 * NW;
-    static constexpr int STAGE = (NW == 1) ? 1024 : 8192;   // doubles; one child always fits (rc^2 <= (FMAX-1)^2)
+    static constexpr int STAGE = (NW == 1) ? 1024 : 4096;   // doubles; one child always fits (rc^2 <= (FMAX-1)^2)
+    static __host__ __device__ int fsize(int maxf) { return (maxf * maxf + 1) & ~1; }   // keeps `stage` 16-byte aligned
     static __host__ __device__ int doubles(int maxf) {
-        return maxf * maxf + 4 * FMAX + (MAXC * FMAX) / 2 + MAXC * 4 + STAGE;
+        return fsize(maxf) + 4 * FMAX + (MAXC * FMAX) / 2 + MAXC * 4 + STAGE;
     }
 };
 
@@ -77,14 +78,33 @@ __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
 }
+__device__ __forceinline__ void cp_async16_cg(void* smem_dst, const void* gsrc) {      // L2-only: data written by other CTAs
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+// dependency flags of the single-launch ("dependency-driven") schedule
+__device__ __forceinline__ void flag_wait(const int* flag, int* err) {
+    int v = 0;
+    unsigned it = 0;
+    do {
+        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        if (v) break;
+        __nanosleep(32);
+    } while (++it < (1u << 24));
+    if (!v) atomicExch(err, 1);          // bounded spin: never hang the device, report instead
+}
+__device__ __forceinline__ void flag_set(int* flag) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(flag), "r"(1) : "memory");
+}
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-template <int NW>
+template <int NW, bool DEP = false>
 __device__ __forceinline__ void front_factor_team(const FactorArgs& a, const ChildRec* childrec, int s, double* sm_team,
-                                                  int tid, int team, int maxf, int& nneg, int& npert, long long* prof = nullptr) {
+                                                  int tid, int team, int maxf, int& nneg, int& npert, long long* prof = nullptr,
+                                                  int* done = nullptr, int* err = nullptr) {
     constexpr int FMAX = 32 * NW, TEAM = 32 * NW, STAGE = TeamSmem<NW>::STAGE;
     double* F = sm_team;
-    double* colbuf = F + maxf * maxf;                  // [2][2*FMAX]
+    double* colbuf = F + TeamSmem<NW>::fsize(maxf);    // [2][2*FMAX]
     int* relst = (int*)(colbuf + 4 * FMAX);            // [MAXC][FMAX]
     ChildRec* recs = (ChildRec*)(relst + MAXC * FMAX); // [MAXC]
     double* stage = (double*)(recs + MAXC);            // [STAGE]
@@ -119,17 +139,26 @@ __device__ __forceinline__ void front_factor_team(const FactorArgs& a, const Chi
     //      every block of a round is landed in shared memory by cp.async in ONE memory round trip.
     for (int c0 = 0; c0 < d.nchild;) {
         const int nrec = min(MAXC, d.nchild - c0);
-        if (tid < nrec) recs[tid] = childrec[d.child_off + c0 + tid];
+        if (tid < nrec) {
+            recs[tid] = childrec[d.child_off + c0 + tid];
+            if (DEP) flag_wait(done + recs[tid].sn, err);      // child fronts finished (its update block is in L2)
+        }
         team_sync<NW>(team);
         int nc = 0, tot = 0;
-        while (nc < nrec) { const int rc = recs[nc].rc; if (nc > 0 && tot + rc * rc > STAGE) break; tot += rc * rc; ++nc; }
+        while (nc < nrec) {
+            const int sz = (recs[nc].rc * recs[nc].rc + 1) & ~1;
+            if (nc > 0 && tot + sz > STAGE) break;
+            tot += sz; ++nc;
+        }
         int off = 0;
         for (int c = 0; c < nc; ++c) {
             const int rc = recs[c].rc;
-            const double* CB = a.ws + recs[c].cb_off;
-            for (int e = tid; e < rc * rc; e += TEAM) cp_async8(stage + off + e, CB + e);
+            const double* CB = a.ws + recs[c].cb_off;          // 16-byte aligned, padded to an even count
+            const int sz = (rc * rc + 1) & ~1;
+            if (DEP) { for (int e = 2 * tid; e < sz; e += 2 * TEAM) cp_async16_cg(stage + off + e, CB + e); }
+            else { for (int e = tid; e < rc * rc; e += TEAM) cp_async8(stage + off + e, CB + e); }
             if (tid < rc) cp_async4(relst + c * FMAX + tid, a.rel + recs[c].rel_off + tid);
-            off += rc * rc;
+            off += sz;
         }
         cp_async_wait_all();
         team_sync<NW>(team);
@@ -151,7 +180,7 @@ __device__ __forceinline__ void front_factor_team(const FactorArgs& a, const Chi
                 }
             }
             team_sync<NW>(team);
-            off += rc * rc;
+            off += (rc * rc + 1) & ~1;
         }
         c0 += nc;
     }
@@ -200,14 +229,16 @@ __device__ __forceinline__ void front_factor_team(const FactorArgs& a, const Chi
 #pragma unroll
         for (int j = 0; j < FMAX; ++j) if (j <= ir) CBo[(size_t)j * r + ir] = av[j];
     }
+    if (DEP) __threadfence();
     team_sync<NW>(team);
+    if (DEP && tid == 0) flag_set(done + s);
     B2_STAMP(7);
 }
 
 // debug: re-factor ONE front with clock64() stamps at the phase boundaries (children's update blocks must be valid)
 template <int NW>
 __global__ void k_factor_team_profile(FactorArgs a, const ChildRec* childrec, int sn, int maxf, long long* prof, int reps) {
-    extern __shared__ double sm[];
+    extern __shared__ __align__(16) double sm[];
     int nneg = 0, npert = 0;
     for (int r = 0; r < reps; ++r) front_factor_team<NW>(a, childrec, sn, sm, threadIdx.x, 0, maxf, nneg, npert, prof + 8 * r);
 }
@@ -217,7 +248,7 @@ template <int NW> struct TeamsPerCta { static constexpr int value = (NW == 1) ? 
 
 template <int NW>
 __global__ void __launch_bounds__(TeamsPerCta<NW>::value * NW * 32) k_factor_warp(FactorArgs a, const ChildRec* childrec, WarpSched ws, int maxf) {
-    extern __shared__ double sm[];
+    extern __shared__ __align__(16) double sm[];
     constexpr int NTEAM = TeamsPerCta<NW>::value;
     const int team = threadIdx.x / (32 * NW), tid = threadIdx.x % (32 * NW);
     double* smt = sm + (size_t)team * TeamSmem<NW>::doubles(maxf);
@@ -239,8 +270,9 @@ __global__ void __launch_bounds__(TeamsPerCta<NW>::value * NW * 32) k_factor_war
 //           shared-memory broadcast of y_k (double-buffered) -- L(i,k) streams from the column-major panel, prefetched
 //           8 pivots ahead, independent of the recurrence.
 // Backward: thread = pivot column j; t_j in a register; L(i,j) streams from the ROW-major panel copy `Lt`.
-template <int NW>
-__device__ __forceinline__ void front_fwd_team(const SolveArgs& a, const ChildRec* childrec, int s, double* sm_team, int tid, int team) {
+template <int NW, bool DEP = false>
+__device__ __forceinline__ void front_fwd_team(const SolveArgs& a, const ChildRec* childrec, int s, double* sm_team, int tid, int team,
+                                               int* done = nullptr, int* err = nullptr) {
     constexpr int FMAX = 32 * NW;
     double* ys = sm_team;                              // [FMAX] assembly of the front's rhs
     double* yb = sm_team + FMAX;                       // [2][8] broadcast slots
@@ -248,9 +280,13 @@ __device__ __forceinline__ void front_fwd_team(const SolveArgs& a, const ChildRe
     const int f = d.f, w = d.w;
     ys[tid] = (tid < w) ? a.xp[d.col0 + tid] : 0.0;
     team_sync<NW>(team);
+    if (DEP) {      // wait for all children first (thread c polls child c), then pull their contribution vectors from L2
+        for (int c = tid; c < d.nchild; c += 32 * NW) flag_wait(done + childrec[d.child_off + c].sn, err);
+        team_sync<NW>(team);
+    }
     for (int c = 0; c < d.nchild; ++c) {
         const ChildRec rec = childrec[d.child_off + c];
-        if (tid < rec.rc) ys[a.rel[rec.rel_off + tid]] += a.cbv[rec.cbv_off + tid];
+        if (tid < rec.rc) ys[a.rel[rec.rel_off + tid]] += DEP ? __ldcg(a.cbv + rec.cbv_off + tid) : a.cbv[rec.cbv_off + tid];
         team_sync<NW>(team);
     }
     double y = ys[tid];
@@ -276,18 +312,25 @@ __device__ __forceinline__ void front_fwd_team(const SolveArgs& a, const ChildRe
         }
     }
     if (tid < f) { if (tid < w) a.xp[d.col0 + tid] = y; else a.cbv[a.cbv_off[s] + tid - w] = y; }
+    if (DEP) __threadfence();
     team_sync<NW>(team);
+    if (DEP && tid == 0) flag_set(done + s);
 }
 
-template <int NW>
-__device__ __forceinline__ void front_bwd_team(const SolveArgs& a, int s, double* sm_team, int tid, int team) {
+template <int NW, bool DEP = false>
+__device__ __forceinline__ void front_bwd_team(const SolveArgs& a, int s, double* sm_team, int tid, int team,
+                                               int* done = nullptr, int* err = nullptr, const int32_t* parent = nullptr) {
     constexpr int FMAX = 32 * NW;
     double* xs = sm_team;                              // [FMAX] gathered ancestor values
     double* xb = sm_team + FMAX;                       // [2][8]
     const FrontDesc d = a.desc[s];
     const int f = d.f, w = d.w, r = f - w;
     const int32_t* rows = a.rows + d.rows_off + w;
-    if (tid < r) xs[tid] = a.xp[rows[tid]];
+    if (DEP) {      // all ancestors are final once the parent is
+        if (tid == 0) { const int p = parent[s]; if (p >= 0) flag_wait(done + p, err); }
+        team_sync<NW>(team);
+    }
+    if (tid < r) xs[tid] = DEP ? __ldcg(a.xp + rows[tid]) : a.xp[rows[tid]];
     double t = (tid < w) ? a.xp[d.col0 + tid] * fast_rcp(a.dvec[d.col0 + tid]) : 0.0;
     team_sync<NW>(team);
     const double* Lt = a.Lt + d.lp_off;                // row-major f x w
@@ -324,7 +367,9 @@ __device__ __forceinline__ void front_bwd_team(const SolveArgs& a, int s, double
         }
     }
     if (tid < w) a.xp[d.col0 + tid] = t;
+    if (DEP) __threadfence();
     team_sync<NW>(team);
+    if (DEP && tid == 0) flag_set(done + s);
 }
 
 template <int NW>
@@ -350,6 +395,62 @@ __global__ void __launch_bounds__(TeamsPerCta<NW>::value * NW * 32) k_bwd_warp2(
         const int off = ws.stage_off[st], cnt = ws.stage_cnt[st];
         for (int q = team; q < cnt; q += NTEAM) front_bwd_team<NW>(a, ws.list[off + q], sm[team], tid, team);
         if (s1 - s0 > 1) __syncthreads();
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------------ single-launch schedule
+// The whole (team-class) elimination tree in ONE launch per sweep: CTAs are issued in topological order, a front waits on
+// its children's completion flags (acquire loads on global memory, bounded spin) instead of on a kernel boundary.  A CTA
+// of 128 threads runs a GROUP of tasks: four one-warp teams (fronts of order <= 32) or one two-warp team (order <= 64).
+struct DepSched {
+    const int32_t* grp_type;   // 1 or 2 (warps per team)
+    const int32_t* grp_ptr;    // [ngroup+1] into tasks
+    const int32_t* tasks;      // supernode ids in topological (level, id) order
+    int ngroup;
+};
+
+__global__ void __launch_bounds__(128) k_factor_dep(FactorArgs a, const ChildRec* childrec, DepSched ds, int maxf1, int maxf2,
+                                                    int* done, int* err) {
+    extern __shared__ __align__(16) double sm[];
+    const int g = blockIdx.x;
+    const int type = ds.grp_type[g], t0 = ds.grp_ptr[g], n = ds.grp_ptr[g + 1] - t0;
+    int nneg = 0, npert = 0;
+    if (type == 1) {
+        const int team = threadIdx.x >> 5, tid = threadIdx.x & 31;
+        if (team < n) front_factor_team<1, true>(a, childrec, ds.tasks[t0 + team], sm + (size_t)team * TeamSmem<1>::doubles(maxf1),
+                                                 tid, team, maxf1, nneg, npert, nullptr, done, err);
+        if (tid == 0) { if (nneg) atomicAdd(a.counters + 0, nneg); if (npert) atomicAdd(a.counters + 1, npert); }
+    } else {
+        const int team = threadIdx.x >> 6, tid = threadIdx.x & 63;
+        if (team < n) front_factor_team<2, true>(a, childrec, ds.tasks[t0 + team], sm, tid, team, maxf2, nneg, npert, nullptr, done, err);
+        if (tid == 0 && team < n) { if (nneg) atomicAdd(a.counters + 0, nneg); if (npert) atomicAdd(a.counters + 1, npert); }
+    }
+}
+
+__global__ void __launch_bounds__(128) k_fwd_dep(SolveArgs a, const ChildRec* childrec, DepSched ds, int* done, int* err) {
+    __shared__ double sm[4][32 + 16 + 64];
+    const int g = blockIdx.x;
+    const int type = ds.grp_type[g], t0 = ds.grp_ptr[g], n = ds.grp_ptr[g + 1] - t0;
+    if (type == 1) {
+        const int team = threadIdx.x >> 5, tid = threadIdx.x & 31;
+        if (team < n) front_fwd_team<1, true>(a, childrec, ds.tasks[t0 + team], sm[team], tid, team, done, err);
+    } else {
+        const int team = threadIdx.x >> 6, tid = threadIdx.x & 63;
+        if (team < n) front_fwd_team<2, true>(a, childrec, ds.tasks[t0 + team], sm[0], tid, team, done, err);
+    }
+}
+
+__global__ void __launch_bounds__(128) k_bwd_dep(SolveArgs a, DepSched ds, const int32_t* parent, int* done, int* err) {
+    __shared__ double sm[4][32 + 16 + 64];
+    const int g = ds.ngroup - 1 - blockIdx.x;            // reverse topological order
+    const int type = ds.grp_type[g], t0 = ds.grp_ptr[g], n = ds.grp_ptr[g + 1] - t0;
+    if (type == 1) {
+        const int team = threadIdx.x >> 5, tid = threadIdx.x & 31;
+        if (team < n) front_bwd_team<1, true>(a, ds.tasks[t0 + team], sm[team], tid, team, done, err, parent);
+    } else {
+        const int team = threadIdx.x >> 6, tid = threadIdx.x & 63;
+        if (team < n) front_bwd_team<2, true>(a, ds.tasks[t0 + team], sm[0], tid, team, done, err, parent);
     }
 }
 

@@ -37,6 +37,10 @@ class Symbolic:
                                           p(self.rel), p(self.amap_ptr), p(self.amap_src), p(self.amap_dst)))
         self.owner = a(ns, np.int32)
         capi.check(lib.b2_symbolic_owner(self.h, p(self.owner)))
+        self.cbv_off = a(ns + 1, np.int64)
+        ecb, ecv = C.c_int64(), C.c_int64()
+        capi.check(lib.b2_symbolic_exchange(self.h, p(self.cbv_off), C.byref(ecb), C.byref(ecv)))
+        self.exch_cb, self.exch_cbv = ecb.value, ecv.value
         st = capi.Stats()
         capi.check(lib.b2_get_stats(self.h, C.byref(st)))
         self.stats = st.as_dict()
@@ -128,3 +132,92 @@ class Symbolic:
         out = np.zeros(self.n)
         out[self.perm] = x
         return out
+
+
+class PhasedReplay:
+    """Replays the multi-GPU protocol of parallel.py on flat workspaces laid out exactly like the device buffers
+    (update blocks at cb_off, contribution vectors at cbv_off, exchange regions first), one rank's view."""
+
+    def __init__(self, S: Symbolic, rank: int):
+        self.S, self.rank = S, rank
+        self.ws = np.zeros(max(1, int(S.cb_off[S.ns])))
+        self.cbv = np.zeros(max(1, int(S.cbv_off[S.ns])))
+        self.L = np.zeros(S.lval_size)
+        self.d = np.zeros(S.n)
+        self.neg = [0, 0]
+        self.order = np.lexsort((np.arange(S.ns), S.sn_level))
+        self.ch = S.children()
+
+    def _mine(self, s, phase):
+        return (self.S.owner[s] == self.rank) if phase == 0 else (self.S.owner[s] == -1)
+
+    def factor_phase(self, nzval, phase, eps=1e-13):
+        S = self.S
+        if phase == 0:
+            self.ws[:S.exch_cb] = 0.0
+        for s in self.order:
+            if not self._mine(s, phase):
+                continue
+            w = S.sn_first[s + 1] - S.sn_first[s]
+            f = int(S.rows_ptr[s + 1] - S.rows_ptr[s]); r = f - w
+            F = np.zeros((f, f))
+            a0, a1 = S.amap_ptr[s], S.amap_ptr[s + 1]
+            dst = S.amap_dst[a0:a1] - S.lp_off[s]
+            F[dst % f, dst // f] = nzval[S.amap_src[a0:a1]]
+            for c in self.ch[s]:
+                rc = int(S.rel_ptr[c + 1] - S.rel_ptr[c])
+                rl = S.rel[S.rel_ptr[c]:S.rel_ptr[c + 1]]
+                CB = np.tril(self.ws[S.cb_off[c]:S.cb_off[c] + rc * rc].reshape(rc, rc).T)
+                F[np.ix_(rl, rl)] += CB + np.tril(CB, -1).T
+            F = np.tril(F)
+            for k in range(w):
+                dk = F[k, k]
+                if not (abs(dk) >= eps):
+                    dk = -eps if dk < 0 else eps
+                elif dk < 0:
+                    self.neg[phase] += 1
+                F[k, k] = dk
+                u = F[k + 1:, k].copy()
+                F[k + 1:, k] = u / dk
+                F[k + 1:, k + 1:] -= np.tril(np.outer(F[k + 1:, k], u))
+            self.L[S.lp_off[s]:S.lp_off[s] + f * w] = F[:, :w].T.ravel()
+            self.d[S.sn_first[s]:S.sn_first[s + 1]] = np.diag(F)[:w]
+            self.ws[S.cb_off[s]:S.cb_off[s] + r * r] = np.tril(F[w:, w:]).T.ravel()      # column-major, lower part
+
+    def fwd_phase(self, x, phase):
+        S = self.S
+        if phase == 0:
+            self.cbv[:S.exch_cbv] = 0.0
+        for s in self.order:
+            if not self._mine(s, phase):
+                continue
+            w = S.sn_first[s + 1] - S.sn_first[s]
+            f = int(S.rows_ptr[s + 1] - S.rows_ptr[s])
+            P = self.L[S.lp_off[s]:S.lp_off[s] + f * w].reshape(w, f).T
+            y = np.zeros(f)
+            y[:w] = x[S.sn_first[s]:S.sn_first[s + 1]]
+            for c in self.ch[s]:
+                rc = int(S.rel_ptr[c + 1] - S.rel_ptr[c])
+                rl = S.rel[S.rel_ptr[c]:S.rel_ptr[c + 1]]
+                y[rl] += self.cbv[S.cbv_off[c]:S.cbv_off[c] + rc]
+            for k in range(w):
+                y[k + 1:] -= P[k + 1:, k] * y[k]
+            x[S.sn_first[s]:S.sn_first[s + 1]] = y[:w]
+            self.cbv[S.cbv_off[s]:S.cbv_off[s] + f - w] = y[w:]
+
+    def bwd_phase(self, x, phase):
+        S = self.S
+        for s in self.order[::-1]:
+            if not self._mine(s, phase):
+                continue
+            w = S.sn_first[s + 1] - S.sn_first[s]
+            f = int(S.rows_ptr[s + 1] - S.rows_ptr[s])
+            P = self.L[S.lp_off[s]:S.lp_off[s] + f * w].reshape(w, f).T
+            rows = S.rows[S.rows_ptr[s]:S.rows_ptr[s + 1]]
+            c0 = S.sn_first[s]
+            xx = np.zeros(f)
+            xx[:w] = x[c0:c0 + w] / self.d[c0:c0 + w]
+            xx[w:] = x[rows[w:]]
+            for k in range(w - 1, -1, -1):
+                xx[k] -= P[k + 1:, k] @ xx[k + 1:]
+            x[c0:c0 + w] = xx[:w]

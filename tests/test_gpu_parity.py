@@ -259,8 +259,8 @@ def test_big_front_path_3d_grid():
     _need_gpu()
     import scipy.sparse.linalg as spla
     from madnlp_jl_b200.linear_solvers import B200SparseSolver, DeviceCSC
-    for delta, res_tol, sol_tol in ((1e-2, 1e-13, 1e-9), (1e-8, 1e-9, None)):
-        N, n_tot, m, I, J, V = W.augmented_grid_kkt(14, 14, 14, delta=delta)
+    for nx, delta, res_tol, sol_tol in ((14, 1e-2, 1e-13, 1e-9), (14, 1e-8, 1e-9, None), (22, 1e-2, 1e-13, 1e-9)):
+        N, n_tot, m, I, J, V = W.augmented_grid_kkt(nx, nx, nx, delta=delta)
         cp, rv, mp = o.coo_to_csc(I, J, N, N)
         nz = np.zeros(len(rv)); o.transfer(nz, V, mp)
         csc = DeviceCSC(N, N, cp, rv, _dev(nz))
