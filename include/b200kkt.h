@@ -140,12 +140,15 @@ int b2_symbolic_query(b2_solver* s, b2_symbolic_sizes* sz);
 int b2_symbolic_export(b2_solver* s, int32_t* perm, int32_t* sn_first, int32_t* sn_parent, int32_t* sn_level,
                        int64_t* rows_ptr, int32_t* rows, int64_t* lp_off, int64_t* cb_off,
                        int64_t* rel_ptr, int32_t* rel, int64_t* amap_ptr, int64_t* amap_src, int64_t* amap_dst);
-int b2_symbolic_owner(b2_solver* s, int32_t* owner);
+int b2_symbolic_owner(b2_solver* s, int32_t* owner);   /* n_supernodes entries: rank, or -1 for the shared top tree */
+/* layout of the multi-GPU exchange: contribution-vector offsets (n_supernodes+1) and the sizes (in doubles) of the
+ * leading regions of the update-block / contribution-vector workspaces that are all-reduced */
+int b2_symbolic_exchange(b2_solver* s, int64_t* cbv_off, int64_t* exch_cb, int64_t* exch_cbv);
 /* test/debug: copy the numeric factor (lval_size doubles, panel layout of b2_symbolic_export) and D (n doubles, permuted
  * order) to the host; synchronises the device. */
 int b2_debug_get_factor(b2_solver* s, double* lval_h, double* dvec_h);
 /* test/debug: re-factor one warp-class front `reps` times with clock64() stamps at its 8 phase boundaries */
-int b2_debug_profile_front(b2_solver* s, int32_t sn, int32_t reps, int64_t* stamps_h);   /* n_supernodes entries: rank, or -1 for the shared top tree */
+int b2_debug_profile_front(b2_solver* s, int32_t sn, int32_t reps, int64_t* stamps_h);
 
 /* ------------------------------------------------------------------ dense LDL^T */
 typedef struct b2d_solver b2d_solver;
