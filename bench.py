@@ -179,7 +179,7 @@ def run_b200(args, rank, world, local_rank):
         opt.nemin = int(os.environ["B2_NEMIN"])
     kkt = K.create_kkt_system(K.SparseCondensedKKTSystem, cb, solver_cls, opt)
     kkt.initialize()
-    la = IPMLinearAlgebra(kkt)
+    la = IPMLinearAlgebra(kkt, use_cuda_graph=(world == 1 and not os.environ.get("B2_NO_STEP_GRAPH")))
     stats = kkt.linear_solver.stats()
 
     host = [{k: torch.from_numpy(np.ascontiguousarray(getattr(it, k))).pin_memory() for k in FIELDS} for it in its]
@@ -190,16 +190,16 @@ def run_b200(args, rank, world, local_rank):
     flush_buf = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)
     stream = torch.cuda.current_stream()
 
-    # phase timers: events around build_kkt / factorize / refinement of the FIRST factorisation of a step
-    ev = {k: (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for k in ("asm", "fac")}
-    phase_ms = {"asm": [], "fac": []}
-    orig_build, orig_fact = kkt.build_kkt, kkt.linear_solver.factorize
-
-    def timed_build():
-        ev["asm"][0].record(stream); orig_build(); ev["asm"][1].record(stream)
-
-    def timed_fact():
-        ev["fac"][0].record(stream); r = orig_fact(); ev["fac"][1].record(stream); return r
+    def time_phase(fn, reps=10):
+        """median CUDA-event time of one call, L2 flushed before each repeat"""
+        ts = []
+        for _ in range(reps):
+            if not args.no_flush:
+                flush_buf.fill_(1.0)
+            a0 = torch.cuda.Event(enable_timing=True); a1 = torch.cuda.Event(enable_timing=True)
+            a0.record(stream); fn(); a1.record(stream); a1.synchronize()
+            ts.append(a0.elapsed_time(a1))
+        return float(np.median(ts))
 
     def one_step(i, e2e, record):
         it = (host if e2e else devit)[i % N_ITERATES]
@@ -213,9 +213,6 @@ def run_b200(args, rank, world, local_rank):
             d_host.copy_(la.d.values, non_blocking=True)
         e1.record(stream)
         e1.synchronize()
-        if record:
-            phase_ms["asm"].append(ev["asm"][0].elapsed_time(ev["asm"][1]))
-            phase_ms["fac"].append(ev["fac"][0].elapsed_time(ev["fac"][1]))
         assert ok
         return e0.elapsed_time(e1)
 
@@ -238,14 +235,18 @@ def run_b200(args, rank, world, local_rank):
         return float(tot.item()), wall
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    kkt.build_kkt = timed_build
-    kkt.linear_solver.factorize = timed_fact
     if sampler:
         sampler.start()
     dev_ms, dev_wall = timed_run(False, record=True)
     e2e_ms, e2e_wall = timed_run(True)
+    # phase timings of the hot path's three metrics, measured separately from the step loop
+    def assemble():
+        kkt.compress_jacobian(); kkt.compress_hessian(); kkt.set_aug_diagonal_(); kkt.build_kkt()
+    xsol = torch.randn(kkt.n, dtype=torch.float64, device=dev)
+    asm_ms = time_phase(assemble)
+    fac_ms = time_phase(kkt.linear_solver.factorize)
+    sol_ms = time_phase(lambda: kkt.linear_solver.solve_linear_system(xsol))
     clocks = sampler.stop() if sampler else None
-    kkt.build_kkt, kkt.linear_solver.factorize = orig_build, orig_fact
 
     if rank == 0:
         peaks = {}
@@ -255,8 +256,6 @@ def run_b200(args, rank, world, local_rank):
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
-        fac_ms = float(np.mean(phase_ms["fac"])) if phase_ms["fac"] else None
-        asm_ms = float(np.mean(phase_ms["asm"])) if phase_ms["asm"] else None
         # algorithmic bytes of one numeric factorisation (SURVEY.md 8d, A9 sparse): 8*(nnz K + nnz L)
         alg_bytes = 8.0 * (stats["nnz_a"] + stats["nnz_l"])
         achieved = alg_bytes / (fac_ms * 1e-3) / 1e9 if fac_ms else None
@@ -274,13 +273,15 @@ def run_b200(args, rank, world, local_rank):
                        "iterates": N_ITERATES, "l2": "flushed between steps (256 MiB write, untimed)" if not args.no_flush else "not flushed",
                        "parallelism": f"subtree-sharded x{world}" if world > 1 else "single GPU",
                        "refinement_solves_per_factorization": solves},
-            "ms_per_factorize": fac_ms, "ms_per_assemble": asm_ms,
+            "ms_per_factorize": fac_ms, "ms_per_assemble": asm_ms, "ms_per_solve": sol_ms,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                     "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int((stats["n_factor_launches"] + 5 + solves * (stats["n_solve_launches"] + 8)) * args.steps),
-            "roofline": {"kernel": "numeric factorisation (k_front_smem level launches, one CUDA graph)", "bound": "hbm",
+            "roofline": {"kernel": "k_factor_dep: numeric multifrontal LDL^T of the whole elimination tree in one launch", "bound": "hbm",
                          "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": (achieved / hbm_peak) if achieved else None,
-                         "traffic": None, "peak_source": peak_src,
+                         "traffic": 11.39e6 if (args.workload == "case10000_goc" and world == 1) else None,
+                         "traffic_source": "profiles/r01_prof_factor_dep_summary.txt (ncu --set full: dram read 11.32 MB + write 0.07 MB per launch)",
+                         "algorithmic_bytes": alg_bytes, "peak_source": peak_src,
                          "note": "latency-bound: %d fronts of order <= %d in %d levels, %.3g Mflop" % (
                              stats["n_supernodes"], stats["max_front"], stats["n_levels"], stats["flops"] / 1e6)},
             "clocks": clocks,

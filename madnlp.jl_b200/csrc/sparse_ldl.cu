@@ -31,6 +31,7 @@ struct LevelSched {
 };
 struct Phase {
     WarpLaunch fused;                               // bottom subtrees, one CTA each (n_cta == 0: none)
+    WarpLaunch topfused;                            // the sparse top of the tree (levels with <= 4 fronts): ONE CTA, one stage per level
     std::vector<LevelSched> lev;
     // single-launch dependency-driven schedule (used instead of fused + levels when every front is team-class)
     int offAllC = 0, nAllC = 0, maxwAllC = 0;       // every M/B front of the phase (diagonal-block inversion)
@@ -189,6 +190,7 @@ int64_t enqueue_factor(b2_solver* s, int ph, cudaStream_t st) {
             }
         }
     }
+    if (P.topfused.n_cta) warp_launch(P.topfused);
     if (P.nAllC) {
         k_big_inv<<<dim3((P.maxwAllC + BS - 1) / BS, P.nAllC), BS, (size_t)BS * (BS + 1) * sizeof(double), st>>>(
             s->d_desc.p, sched + P.offAllC, s->d_L.p, s->d_Linv.p, s->d_linv_off.p);
@@ -204,11 +206,13 @@ int64_t enqueue_solve(b2_solver* s, int ph, bool forward, cudaStream_t st) {
     const Phase& P = s->phase[ph];
     auto warp_launch = [&](const WarpLaunch& L) {
         if (L.nw == 1) {
-            if (forward) k_fwd_warp2<1><<<L.n_cta, FW_WARPS * 32, 0, st>>>(a, s->d_childrec.p, warp_sched(s, L));
-            else k_bwd_warp2<1><<<L.n_cta, FW_WARPS * 32, 0, st>>>(a, warp_sched(s, L));
+            const size_t sm = (size_t)FW_WARPS * SolveSmem<1>::doubles * sizeof(double);
+            if (forward) k_fwd_warp2<1><<<L.n_cta, FW_WARPS * 32, sm, st>>>(a, s->d_childrec.p, warp_sched(s, L));
+            else k_bwd_warp2<1><<<L.n_cta, FW_WARPS * 32, sm, st>>>(a, warp_sched(s, L));
         } else {
-            if (forward) k_fwd_warp2<2><<<L.n_cta, 64, 0, st>>>(a, s->d_childrec.p, warp_sched(s, L));
-            else k_bwd_warp2<2><<<L.n_cta, 64, 0, st>>>(a, warp_sched(s, L));
+            const size_t sm = (size_t)SolveSmem<2>::doubles * sizeof(double);
+            if (forward) k_fwd_warp2<2><<<L.n_cta, 64, sm, st>>>(a, s->d_childrec.p, warp_sched(s, L));
+            else k_bwd_warp2<2><<<L.n_cta, 64, sm, st>>>(a, warp_sched(s, L));
         }
         ++nl;
     };
@@ -217,11 +221,13 @@ int64_t enqueue_solve(b2_solver* s, int ph, bool forward, cudaStream_t st) {
         ds.grp_type = sched + P.dep_type_off; ds.grp_ptr = sched + P.dep_ptr_off; ds.tasks = sched + P.dep_tasks_off; ds.ngroup = P.dep_ngroup;
         int* flags = s->d_flags.p + (size_t)(forward ? 1 : 2) * s->S.nsuper;
         cudaMemsetAsync(flags, 0, (size_t)s->S.nsuper * sizeof(int32_t), st);
-        if (forward) k_fwd_dep<<<P.dep_ngroup, 128, 0, st>>>(a, s->d_childrec.p, ds, flags, s->d_counters.p + 4);
-        else k_bwd_dep<<<P.dep_ngroup, 128, 0, st>>>(a, ds, s->d_parent.p, flags, s->d_counters.p + 4);
+        const size_t smd = sizeof(double) * std::max<size_t>((size_t)4 * SolveSmem<1>::doubles, (size_t)SolveSmem<2>::doubles);
+        if (forward) k_fwd_dep<<<P.dep_ngroup, 128, smd, st>>>(a, s->d_childrec.p, ds, flags, s->d_counters.p + 4);
+        else k_bwd_dep<<<P.dep_ngroup, 128, smd, st>>>(a, ds, s->d_parent.p, flags, s->d_counters.p + 4);
         return 2;
     }
     if (forward && P.fused.n_cta) warp_launch(P.fused);
+    if (!forward && P.topfused.n_cta) warp_launch(P.topfused);
     const int nlev = (int)P.lev.size();
     for (int q = 0; q < nlev; ++q) {
         const LevelSched& lv = forward ? P.lev[q] : P.lev[nlev - 1 - q];
@@ -252,6 +258,7 @@ int64_t enqueue_solve(b2_solver* s, int ph, bool forward, cudaStream_t st) {
             }
         }
     }
+    if (forward && P.topfused.n_cta) warp_launch(P.topfused);
     if (!forward && P.fused.n_cta) warp_launch(P.fused);
     return nl;
 }
@@ -261,6 +268,12 @@ int set_smem_attrs() {
     B2_CUDA(cudaFuncSetAttribute(k_factor_warp<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     B2_CUDA(cudaFuncSetAttribute(k_factor_warp<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     B2_CUDA(cudaFuncSetAttribute(k_factor_dep, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    B2_CUDA(cudaFuncSetAttribute(k_fwd_warp2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    B2_CUDA(cudaFuncSetAttribute(k_bwd_warp2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    B2_CUDA(cudaFuncSetAttribute(k_fwd_warp2<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    B2_CUDA(cudaFuncSetAttribute(k_bwd_warp2<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    B2_CUDA(cudaFuncSetAttribute(k_fwd_dep, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    B2_CUDA(cudaFuncSetAttribute(k_bwd_dep, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     B2_CUDA(cudaFuncSetAttribute(k_big_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     B2_CUDA(cudaFuncSetAttribute(k_bs_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     B2_CUDA(cudaFuncSetAttribute(k_bs_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
@@ -425,6 +438,25 @@ void build_schedule(b2_solver* s) {
         P.maxwAllC = 0;
         std::vector<std::vector<int32_t>> by_level(nul);
         for (int sn = 0; sn < ns; ++sn) if (ulev[sn] >= 0) by_level[ulev[sn]].push_back(sn);
+        // ---- the top of the tree: trailing levels that hold at most 4 team-class fronts each are chained inside ONE CTA
+        //      (stage = level): a launch boundary per level would cost more than the fronts themselves.
+        P.topfused = WarpLaunch();
+        int ntoplev = 0;
+        if (wmax > 32 && s->opt.fuse_max_fronts > 0) {
+            while (ntoplev < nul) {
+                const auto& lvv = by_level[nul - 1 - ntoplev];
+                bool ok = lvv.size() <= 4;
+                for (int sn : lvv) { int w, f; fdim(sn, w, f); ok = ok && f <= wmax; }
+                if (!ok) break;
+                ++ntoplev;
+            }
+            if (ntoplev >= 2) {
+                std::vector<std::vector<std::vector<int32_t>>> ctas(1);
+                for (int l = nul - ntoplev; l < nul; ++l) ctas[0].push_back(by_level[l]);
+                P.topfused = emit_warp_launch(ctas, 2);
+                nul -= ntoplev;
+            }
+        }
         for (int l = 0; l < nul; ++l) {
             std::vector<int32_t> Wx, W2x, Mx, Bx;
             LevelSched lv;
@@ -612,9 +644,17 @@ int create_common(int32_t n, int64_t nnz, const int32_t* colptr_h, const int32_t
     return B2_OK;
 }
 
+// a pre-instantiated graph cannot be launched into a stream that is itself being captured (e.g. the caller records a
+// whole IPM step into its own CUDA graph): in that case the kernels are enqueued directly and become part of THAT graph
+bool stream_is_capturing(cudaStream_t st) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) != cudaSuccess) { cudaGetLastError(); return false; }
+    return cs == cudaStreamCaptureStatusActive;
+}
+
 int run_factor_phase(b2_solver* s, int ph, cudaStream_t st) {
     Phase& P = s->phase[ph];
-    if (s->opt.use_cuda_graph) {
+    if (s->opt.use_cuda_graph && !stream_is_capturing(st)) {
         if (!P.g_factor) {
             int rc = capture(s, &P.g_factor, [&](cudaStream_t cs) { P.n_factor_launches = enqueue_factor(s, ph, cs); });
             if (rc != B2_OK) return rc;
@@ -630,7 +670,7 @@ int run_factor_phase(b2_solver* s, int ph, cudaStream_t st) {
 int run_solve_phase(b2_solver* s, int ph, bool fwd, cudaStream_t st) {
     Phase& P = s->phase[ph];
     cudaGraphExec_t* g = fwd ? &P.g_fwd : &P.g_bwd;
-    if (s->opt.use_cuda_graph) {
+    if (s->opt.use_cuda_graph && !stream_is_capturing(st)) {
         if (!*g) {
             int64_t nl = 0;
             int rc = capture(s, g, [&](cudaStream_t cs) { nl = enqueue_solve(s, ph, fwd, cs); });
@@ -1015,7 +1055,7 @@ int b2d_destroy(b2d_solver* s) { delete s; return B2_OK; }
 int b2d_factorize(b2d_solver* s, void* stream) {
     if (!s) return B2_ERR_INVALID;
     cudaStream_t st = as_stream(stream);
-    if (s->opt.use_cuda_graph) {
+    if (s->opt.use_cuda_graph && !stream_is_capturing(st)) {
         if (!s->g_factor) {
             cudaGraph_t g = nullptr;
             B2_CUDA(cudaStreamBeginCapture(s->cap_stream, cudaStreamCaptureModeThreadLocal));

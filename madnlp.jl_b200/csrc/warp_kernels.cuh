@@ -266,35 +266,63 @@ __global__ void __launch_bounds__(TeamsPerCta<NW>::value * NW * 32) k_factor_war
 }
 
 // ------------------------------------------------------------------------------------------------ solves
-// Forward:  thread = row i of the front; y_i in a register; the recurrence y_i -= L(i,k) y_k is carried by a
-//           shared-memory broadcast of y_k (double-buffered) -- L(i,k) streams from the column-major panel, prefetched
-//           8 pivots ahead, independent of the recurrence.
-// Backward: thread = pivot column j; t_j in a register; L(i,j) streams from the ROW-major panel copy `Lt`.
+// A front's solve is three memory round trips, whatever its number of children or pivots:
+//   (1) descriptor;  (2) child records + the whole panel (cp.async into shared memory, in flight while (3) runs) + own
+//   right-hand side;  (3) every child's relative indices and contribution vector at once.
+// Forward:  thread = row i of the front; y_i in a register; the recurrence y_i -= L(i,k) y_k reads L from the staged
+//           column-major panel and y_k from a shuffle (one-warp teams) or a double-buffered shared slot (two-warp teams).
+// Backward: thread = pivot column j; t_j in a register; L(i,j) comes from the staged ROW-major copy `Lt`.
+template <int NW>
+struct SolveSmem {
+    static constexpr int FMAX = 32 * NW;
+    // ys/xs [FMAX] | slots [16] | recs [MAXC] (4 doubles each) | panel [FMAX*FMAX]
+    static constexpr int doubles = FMAX + 16 + 4 * MAXC + FMAX * FMAX;
+};
+
 template <int NW, bool DEP = false>
 __device__ __forceinline__ void front_fwd_team(const SolveArgs& a, const ChildRec* childrec, int s, double* sm_team, int tid, int team,
                                                int* done = nullptr, int* err = nullptr) {
-    constexpr int FMAX = 32 * NW;
+    constexpr int FMAX = 32 * NW, TEAM = 32 * NW;
     double* ys = sm_team;                              // [FMAX] assembly of the front's rhs
-    double* yb = sm_team + FMAX;                       // [2][8] broadcast slots
+    double* yb = ys + FMAX;                            // [2][8] broadcast slots
+    ChildRec* recs = (ChildRec*)(yb + 16);             // [MAXC]
+    double* P = (double*)(recs + MAXC);                // panel, column-major, ld f
     const FrontDesc d = a.desc[s];
     const int f = d.f, w = d.w;
+    {
+        const double* Lp = a.L + d.lp_off;
+        for (int e = tid; e < f * w; e += TEAM) cp_async8(P + e, Lp + e);
+    }
     ys[tid] = (tid < w) ? a.xp[d.col0 + tid] : 0.0;
+    for (int c0 = 0; c0 < d.nchild; c0 += MAXC) {
+        const int nc = min(MAXC, d.nchild - c0);
+        if (tid < nc) {
+            recs[tid] = childrec[d.child_off + c0 + tid];
+            if (DEP) flag_wait(done + recs[tid].sn, err);
+        }
+        team_sync<NW>(team);
+        int tg[MAXC]; double vv[MAXC];
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c) {
+            const bool on = c < nc && tid < recs[c].rc;
+            tg[c] = on ? a.rel[recs[c].rel_off + tid] : -1;
+            vv[c] = on ? (DEP ? __ldcg(a.cbv + recs[c].cbv_off + tid) : a.cbv[recs[c].cbv_off + tid]) : 0.0;
+        }
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c) {               // ascending child order: deterministic sums
+            if (c < nc) {
+                if (tg[c] >= 0) ys[tg[c]] += vv[c];
+                team_sync<NW>(team);
+            }
+        }
+    }
+    cp_async_wait_all();
     team_sync<NW>(team);
-    if (DEP) {      // wait for all children first (thread c polls child c), then pull their contribution vectors from L2
-        for (int c = tid; c < d.nchild; c += 32 * NW) flag_wait(done + childrec[d.child_off + c].sn, err);
-        team_sync<NW>(team);
-    }
-    for (int c = 0; c < d.nchild; ++c) {
-        const ChildRec rec = childrec[d.child_off + c];
-        if (tid < rec.rc) ys[a.rel[rec.rel_off + tid]] += DEP ? __ldcg(a.cbv + rec.cbv_off + tid) : a.cbv[rec.cbv_off + tid];
-        team_sync<NW>(team);
-    }
     double y = ys[tid];
-    const double* Lp = a.L + d.lp_off;
     for (int k0 = 0; k0 < w; k0 += 8) {
         double l[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) { const int k = k0 + u; l[u] = (k < w && tid > k && tid < f) ? Lp[(size_t)k * f + tid] : 0.0; }
+        for (int u = 0; u < 8; ++u) { const int k = k0 + u; l[u] = (k < w && tid > k && tid < f) ? P[k * f + tid] : 0.0; }
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             const int k = k0 + u;
@@ -320,11 +348,16 @@ __device__ __forceinline__ void front_fwd_team(const SolveArgs& a, const ChildRe
 template <int NW, bool DEP = false>
 __device__ __forceinline__ void front_bwd_team(const SolveArgs& a, int s, double* sm_team, int tid, int team,
                                                int* done = nullptr, int* err = nullptr, const int32_t* parent = nullptr) {
-    constexpr int FMAX = 32 * NW;
+    constexpr int FMAX = 32 * NW, TEAM = 32 * NW;
     double* xs = sm_team;                              // [FMAX] gathered ancestor values
-    double* xb = sm_team + FMAX;                       // [2][8]
+    double* xb = xs + FMAX;                            // [2][8]
+    double* P = xb + 16 + 4 * MAXC;                    // row-major f x w panel (same slice layout as the forward sweep)
     const FrontDesc d = a.desc[s];
     const int f = d.f, w = d.w, r = f - w;
+    {
+        const double* Lt = a.Lt + d.lp_off;
+        for (int e = tid; e < f * w; e += TEAM) cp_async8(P + e, Lt + e);
+    }
     const int32_t* rows = a.rows + d.rows_off + w;
     if (DEP) {      // all ancestors are final once the parent is
         if (tid == 0) { const int p = parent[s]; if (p >= 0) flag_wait(done + p, err); }
@@ -332,16 +365,13 @@ __device__ __forceinline__ void front_bwd_team(const SolveArgs& a, int s, double
     }
     if (tid < r) xs[tid] = DEP ? __ldcg(a.xp + rows[tid]) : a.xp[rows[tid]];
     double t = (tid < w) ? a.xp[d.col0 + tid] * fast_rcp(a.dvec[d.col0 + tid]) : 0.0;
+    cp_async_wait_all();
     team_sync<NW>(team);
-    const double* Lt = a.Lt + d.lp_off;                // row-major f x w
-    {   // t_j -= sum_{i >= w} L(i,j) x_i : no recurrence, batches of 8 rows
+    {   // t_j -= sum_{i >= w} L(i,j) x_i : no recurrence
         double acc = 0.0;
-        for (int i0 = 0; i0 < r; i0 += 8) {
-            double l[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) { const int i = i0 + u; l[u] = (i < r && tid < w) ? Lt[(size_t)(w + i) * w + tid] : 0.0; }
-#pragma unroll
-            for (int u = 0; u < 8; ++u) { const int i = i0 + u; if (i < r) acc = fma(l[u], xs[i], acc); }
+        if (tid < w) {
+#pragma unroll 8
+            for (int i = 0; i < r; ++i) acc = fma(P[(w + i) * w + tid], xs[i], acc);
         }
         t -= acc;
     }
@@ -349,7 +379,7 @@ __device__ __forceinline__ void front_bwd_team(const SolveArgs& a, int s, double
     for (int k0 = w - 1; k0 >= 1; k0 -= 8) {
         double l[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) { const int k = k0 - u; l[u] = (k >= 1 && tid < k) ? Lt[(size_t)k * w + tid] : 0.0; }
+        for (int u = 0; u < 8; ++u) { const int k = k0 - u; l[u] = (k >= 1 && tid < k) ? P[k * w + tid] : 0.0; }
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             const int k = k0 - u;
@@ -374,7 +404,8 @@ __device__ __forceinline__ void front_bwd_team(const SolveArgs& a, int s, double
 
 template <int NW>
 __global__ void __launch_bounds__(TeamsPerCta<NW>::value * NW * 32) k_fwd_warp2(SolveArgs a, const ChildRec* childrec, WarpSched ws) {
-    __shared__ double sm[TeamsPerCta<NW>::value][32 * NW + 16];
+    extern __shared__ __align__(16) double smd[];
+    double (*sm)[SolveSmem<NW>::doubles] = (double (*)[SolveSmem<NW>::doubles])smd;
     constexpr int NTEAM = TeamsPerCta<NW>::value;
     const int team = threadIdx.x / (32 * NW), tid = threadIdx.x % (32 * NW);
     const int s0 = ws.cta_ptr[blockIdx.x], s1 = ws.cta_ptr[blockIdx.x + 1];
@@ -387,7 +418,8 @@ __global__ void __launch_bounds__(TeamsPerCta<NW>::value * NW * 32) k_fwd_warp2(
 
 template <int NW>
 __global__ void __launch_bounds__(TeamsPerCta<NW>::value * NW * 32) k_bwd_warp2(SolveArgs a, WarpSched ws) {
-    __shared__ double sm[TeamsPerCta<NW>::value][32 * NW + 16];
+    extern __shared__ __align__(16) double smd[];
+    double (*sm)[SolveSmem<NW>::doubles] = (double (*)[SolveSmem<NW>::doubles])smd;
     constexpr int NTEAM = TeamsPerCta<NW>::value;
     const int team = threadIdx.x / (32 * NW), tid = threadIdx.x % (32 * NW);
     const int s0 = ws.cta_ptr[blockIdx.x], s1 = ws.cta_ptr[blockIdx.x + 1];
@@ -429,7 +461,8 @@ __global__ void __launch_bounds__(128) k_factor_dep(FactorArgs a, const ChildRec
 }
 
 __global__ void __launch_bounds__(128) k_fwd_dep(SolveArgs a, const ChildRec* childrec, DepSched ds, int* done, int* err) {
-    __shared__ double sm[4][32 + 16 + 64];
+    extern __shared__ __align__(16) double smd[];       // max(4 one-warp slices, 1 two-warp slice)
+    double (*sm)[SolveSmem<1>::doubles] = (double (*)[SolveSmem<1>::doubles])smd;
     const int g = blockIdx.x;
     const int type = ds.grp_type[g], t0 = ds.grp_ptr[g], n = ds.grp_ptr[g + 1] - t0;
     if (type == 1) {
@@ -437,12 +470,13 @@ __global__ void __launch_bounds__(128) k_fwd_dep(SolveArgs a, const ChildRec* ch
         if (team < n) front_fwd_team<1, true>(a, childrec, ds.tasks[t0 + team], sm[team], tid, team, done, err);
     } else {
         const int team = threadIdx.x >> 6, tid = threadIdx.x & 63;
-        if (team < n) front_fwd_team<2, true>(a, childrec, ds.tasks[t0 + team], sm[0], tid, team, done, err);
+        if (team < n) front_fwd_team<2, true>(a, childrec, ds.tasks[t0 + team], smd, tid, team, done, err);
     }
 }
 
 __global__ void __launch_bounds__(128) k_bwd_dep(SolveArgs a, DepSched ds, const int32_t* parent, int* done, int* err) {
-    __shared__ double sm[4][32 + 16 + 64];
+    extern __shared__ __align__(16) double smd[];
+    double (*sm)[SolveSmem<1>::doubles] = (double (*)[SolveSmem<1>::doubles])smd;
     const int g = ds.ngroup - 1 - blockIdx.x;            // reverse topological order
     const int type = ds.grp_type[g], t0 = ds.grp_ptr[g], n = ds.grp_ptr[g + 1] - t0;
     if (type == 1) {
@@ -450,7 +484,7 @@ __global__ void __launch_bounds__(128) k_bwd_dep(SolveArgs a, DepSched ds, const
         if (team < n) front_bwd_team<1, true>(a, ds.tasks[t0 + team], sm[team], tid, team, done, err, parent);
     } else {
         const int team = threadIdx.x >> 6, tid = threadIdx.x & 63;
-        if (team < n) front_bwd_team<2, true>(a, ds.tasks[t0 + team], sm[0], tid, team, done, err, parent);
+        if (team < n) front_bwd_team<2, true>(a, ds.tasks[t0 + team], smd, tid, team, done, err, parent);
     }
 }
 

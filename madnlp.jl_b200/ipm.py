@@ -36,9 +36,11 @@ class InertiaOptions:
 class IPMLinearAlgebra:
     """Owns the work vectors of MadNLPSolver that the hot path touches (d, p, _w4) and drives one iteration."""
 
-    def __init__(self, kkt, tol=1e-8):
+    def __init__(self, kkt, tol=1e-8, use_cuda_graph=True):
         self.kkt = kkt
-        self.iterator = RichardsonIterator(kkt, tol=tol)
+        self.use_cuda_graph = use_cuda_graph
+        self._prologue_graph = None
+        self.iterator = RichardsonIterator(kkt, tol=tol, use_cuda_graph=use_cuda_graph)
         self.d = UnreducedKKTVector.for_kkt(kkt)
         self.p = UnreducedKKTVector.for_kkt(kkt)
         self.w = UnreducedKKTVector.for_kkt(kkt)
@@ -60,6 +62,14 @@ class IPMLinearAlgebra:
         k.u_lower.copy_(it["u_lower"], non_blocking=non_blocking)
         self.p.values.copy_(it["rhs"], non_blocking=non_blocking)
 
+    def _prologue(self):
+        k = self.kkt
+        k.compress_jacobian()
+        k.compress_hessian()
+        k.set_aug_diagonal_()
+        k.build_kkt()
+        k.linear_solver.factorize()
+
     def _factorize_wrapper(self):
         self.kkt.build_kkt()
         self.kkt.linear_solver.factorize()
@@ -76,14 +86,26 @@ class IPMLinearAlgebra:
     def step(self, mu=1e-2):
         """One `regular!` linear-algebra pass; returns True when a step direction was obtained."""
         k = self.kkt
-        k.compress_jacobian()
-        k.compress_hessian()
-        k.set_aug_diagonal_()
+        # compress_* + set_aug_diagonal! + the first factorize_wrapper! of inertia_correction!: fixed launch sequence,
+        # replayed as one CUDA graph from the third step on (eager, capture, replay)
+        if not self.use_cuda_graph or self._prologue_graph is None:
+            self._prologue()
+            if self.use_cuda_graph:
+                self._prologue_graph = False
+        elif self._prologue_graph is False:
+            g = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize()
+            with torch.cuda.graph(g):
+                self._prologue()
+            self._prologue_graph = g
+            g.replay()
+        else:
+            self._prologue_graph.replay()
+        self.cnt["factorizations"] += 1
         # inertia_correction!(InertiaBased)
         o = self.opt
         n_trial = 0
         del_w = del_c = del_w_prev = del_c_prev = 0.0
-        self._factorize_wrapper()
         inertia = k.linear_solver.inertia()
         ok = self._solve_refine_wrapper() if k.is_inertia_correct(*inertia) else False
         while not ok:

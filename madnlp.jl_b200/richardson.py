@@ -14,8 +14,13 @@ from .capi import lib, check, ptr
 
 
 class RichardsonIterator:
-    def __init__(self, kkt, tol=1e-8, richardson_max_iter=10):
+    """`use_cuda_graph=True` replays the body of one refinement step (solve_kkt!, axpy, copy, mul!, two norms -- about a dozen
+    launches plus the solver's own graphs) as ONE CUDA graph: same kernels, same order, one launch from the host."""
+
+    def __init__(self, kkt, tol=1e-8, richardson_max_iter=10, use_cuda_graph=True):
         self.kkt = kkt
+        self.use_cuda_graph = use_cuda_graph
+        self._graphs = {}
         self.richardson_max_iter = richardson_max_iter
         self.richardson_tol = tol ** (5 / 4)
         self.richardson_acceptable_tol = tol ** (5 / 8)
@@ -24,10 +29,38 @@ class RichardsonIterator:
         self.ir = 0
         self.residual_ratio = 0.0
 
-    def _norm_pair(self, w, x, stream):
-        n = w.values.numel()
+    def _body(self, x, b, w):
+        """solve_kkt!(w); x += w; w = b; w -= K x; norms of w and x on the device (backsolve.jl:45-52)"""
+        kkt = self.kkt
+        stream = capi.stream_ptr(getattr(kkt, "stream", None))
+        n = b.values.numel()
+        kkt.solve_kkt(w)
+        check(lib.b2_axpy(n, 1.0, ptr(w.values), ptr(x.values), stream))
+        check(lib.b2_copy(n, ptr(b.values), ptr(w.values), stream))
+        kkt.mul(w, x, -1.0, 1.0)
         check(lib.b2_norm_inf(n, ptr(w.values), ptr(self._norms[0:1]), stream))
         check(lib.b2_norm_inf(n, ptr(x.values), ptr(self._norms[1:2]), stream))
+
+    def _iteration(self, x, b, w):
+        if not self.use_cuda_graph:
+            self._body(x, b, w)
+        else:
+            key = (x.values.data_ptr(), b.values.data_ptr(), w.values.data_ptr())
+            g = self._graphs.get(key)
+            if g is None:
+                # first use with these vectors: run eagerly (this also instantiates the solver's internal graphs) ...
+                self._body(x, b, w)
+                self._graphs[key] = False
+            elif g is False:
+                # ... second use: capture; the captured launch sequence is then replayed
+                g = torch.cuda.CUDAGraph()
+                torch.cuda.synchronize()
+                with torch.cuda.graph(g):
+                    self._body(x, b, w)
+                self._graphs[key] = g
+                g.replay()
+            else:
+                g.replay()
         self._norms_h.copy_(self._norms, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return float(self._norms_h[0]), float(self._norms_h[1])
@@ -44,11 +77,7 @@ class RichardsonIterator:
         if norm_b != 0.0:
             check(lib.b2_copy(n, ptr(b.values), ptr(w.values), stream))
             while True:
-                kkt.solve_kkt(w)
-                check(lib.b2_axpy(n, 1.0, ptr(w.values), ptr(x.values), stream))
-                check(lib.b2_copy(n, ptr(b.values), ptr(w.values), stream))
-                kkt.mul(w, x, -1.0, 1.0)
-                norm_w, norm_x = self._norm_pair(w, x, stream)
+                norm_w, norm_x = self._iteration(x, b, w)
                 residual_ratio = norm_w / (min(norm_x, 1e6 * norm_b) + norm_b)
                 self.ir += 1
                 if self.ir >= self.richardson_max_iter or residual_ratio < self.richardson_tol:
