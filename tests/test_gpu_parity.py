@@ -338,3 +338,25 @@ def test_ipm_replay_regularises_like_the_reference():
         assert la.step(mu=it.mu)
         assert (la.cnt["regularized"] > before) == expect_reg
         assert kg.is_inertia_correct(*la.last_inertia)
+
+
+def test_golden_fixture_on_device():
+    """The committed HS15 fixture (tests/golden/hs15_kkt.json): factor + solve the stored condensed and augmented
+    matrices through the C ABI and reproduce the stored solve_kkt vector / inertia."""
+    _need_gpu()
+    import json, os
+    from madnlp_jl_b200.linear_solvers import B200SparseSolver, DeviceCSC
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "hs15_kkt.json")))
+    for key, n, npr in (("hs15_sparse", 6, 4), ("hs15_condensed", 2, 0)):
+        e = g[key]
+        csc = DeviceCSC(n, n, np.array(e["colptr"], dtype=np.int32), np.array(e["rowval"], dtype=np.int32), _dev(np.array(e["nzval"])))
+        M = B200SparseSolver(csc, B200SparseSolver.default_options(kkt_n_primal=npr))
+        M.factorize()
+        assert list(M.inertia()) == e["inertia"]
+    k = g["kat_2x2"]
+    cp, rv, mp = o.coo_to_csc(np.array(k["row"]), np.array(k["col"]), 2, 2)
+    nz = np.zeros(len(rv)); o.transfer(nz, np.array(k["val"]), mp)
+    M = B200SparseSolver(DeviceCSC(2, 2, cp, rv, _dev(nz)))
+    M.factorize()
+    x = M.solve_linear_system(_dev(np.array(k["b"]))).cpu().numpy()
+    assert np.abs(x - np.array(k["x"])).max() < 1e-14 and list(M.inertia()) == k["inertia"]

@@ -93,3 +93,22 @@ def test_condensed_matches_full_system():
         assert ok and ratio < 1e-8
         sols.append(x.full().copy())
     assert np.abs(sols[0] - sols[1]).max() / np.abs(sols[0]).max() < 1e-6
+
+
+def test_committed_golden_fixture_matches_oracle():
+    """tests/golden/hs15_kkt.json (written by tests/golden/make_golden.py) pins the oracle across refactors and is what
+    the GPU tests compare against on the box (no reference tree there)."""
+    import json, os
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "hs15_kkt.json")))
+    assert g["kat_2x2"]["x"] == [0.8542713567839195, 1.4572864321608041]
+    cb = o.HS15Model.callback()
+    kkt = o.SparseKKTSystem(cb, o.DenseLDLInertiaSolver)
+    x, y, inertia = o.test_kkt_system(kkt, o.HS15Model)
+    assert np.abs(x.full() - np.array(g["hs15_sparse"]["solve_kkt_of_ones"])).max() < 1e-14
+    assert list(inertia) == g["hs15_sparse"]["inertia"] == [4, 0, 2]
+    assert (kkt.aug_colptr == np.array(g["hs15_sparse"]["colptr"])).all()
+    assert np.abs(kkt.aug_nz - np.array(g["hs15_sparse"]["nzval"])).max() == 0.0
+    kc = o.SparseCondensedKKTSystem(cb)
+    xc, yc, ic = o.test_kkt_system(kc, o.HS15Model)
+    assert np.abs(xc.full() - np.array(g["hs15_condensed"]["solve_kkt_of_ones"])).max() < 1e-14
+    assert np.abs(kc.aug_nz - np.array(g["hs15_condensed"]["nzval"])).max() == 0.0

@@ -4,7 +4,7 @@ ms/assemble, ms/factorize, ms/solve with CUDA events (median of 20 after 3 warm-
 achieved GFLOP/s / GB/s against the measured peaks, next to (a) the reference's GPU library path where torch exposes
 the same library routine (cuBLAS GEMM, cuSOLVER sytrf/potrf) and (b) the CPU oracle.  Prints one JSON line per config."""
 import json, os, sys, time
-ROOT = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (ROOT, os.path.join(ROOT, "oracle")):
     sys.path.insert(0, p)
 import numpy as np, torch

@@ -1,6 +1,6 @@
 """GPU debug: compare the device factor front by front with the numpy replay (tests/mf_emulator.py)."""
 import sys, os, ctypes as C
-ROOT=os.path.dirname(os.path.abspath(__file__))
+ROOT=os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (ROOT, ROOT+"/oracle", ROOT+"/tests"): sys.path.insert(0,p)
 import numpy as np, torch
 import madnlp_oracle as o, madnlp_jl_b200 as pkg

@@ -1,6 +1,6 @@
 """GPU debug: clock64() phase breakdown of the warp factor kernel on the largest top-level fronts of the OPF-10k case."""
 import sys, os, ctypes as C
-ROOT=os.path.dirname(os.path.abspath(__file__))
+ROOT=os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (ROOT, ROOT+"/oracle", ROOT+"/tests"): sys.path.insert(0,p)
 import numpy as np, torch
 import madnlp_jl_b200 as pkg
