@@ -203,6 +203,14 @@ int b2d_condensed_assemble(int32_t n, int32_t m, int32_t ns, int32_t n_eq,
                            const double* pr_diag_d, const double* du_diag_d,
                            double* diag_buffer_d, double* aug_d, void* stream);
 
+/* dense mat-vecs on column-major device matrices for the DenseCondensedKKTSystem wrappers (jtprod!/mul!/solve_kkt!,
+ * src/IPM/factorization.jl:190-229,326-344; the reference calls cuBLAS gemv/symv, lib/MadNLPGPU/.../cuda.jl:54-84):
+ *   gemv_n: y = alpha*A*x + beta*y (A rows x cols, ld = lda)   gemv_t: y = alpha*A'*x + beta*y
+ *   symv_lower: y = alpha*sym(A)*x + beta*y reading only the lower triangle (the reference's _symv!('L', ...)) */
+int b2d_gemv_n(int32_t rows, int32_t cols, int32_t lda, const double* A_d, const double* x_d, double* y_d, double alpha, double beta, void* stream);
+int b2d_gemv_t(int32_t rows, int32_t cols, int32_t lda, const double* A_d, const double* x_d, double* y_d, double alpha, double beta, void* stream);
+int b2d_symv_lower(int32_t n, int32_t lda, const double* A_d, const double* x_d, double* y_d, double alpha, double beta, void* stream);
+
 /* ------------------------------------------------------------------ IPM vector kernels */
 /* Index sets ind_lb / ind_ub over the primal vector (x,s) (src/Callbacks/nlpmodels.jl:369-406), uploaded once
  * together with their inverse maps so that every kernel below is a single race-free pass over n_tot. */

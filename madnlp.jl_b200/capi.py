@@ -112,6 +112,9 @@ PROTOTYPES = {
     "b2d_factorize": (C.c_int, [_p, _p]),
     "b2d_inertia": (C.c_int, [_p, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64), _p]),
     "b2d_solve": (C.c_int, [_p, _p, _i32, _p]),
+    "b2d_gemv_n": (C.c_int, [_i32, _i32, _i32, _p, _p, _p, _f64, _f64, _p]),
+    "b2d_gemv_t": (C.c_int, [_i32, _i32, _i32, _p, _p, _p, _f64, _f64, _p]),
+    "b2d_symv_lower": (C.c_int, [_i32, _i32, _p, _p, _p, _f64, _f64, _p]),
     "b2_coo_to_csc": (C.c_int, [_i32, _i32, _i64, _p, _p, _p, _p, _p, C.POINTER(_i64)]),
     "b2_transfer_plan_create": (C.c_int, [_i64, _i64, _p, _PP]),
     "b2_transfer_plan_destroy": (C.c_int, [_p]),

@@ -434,3 +434,97 @@ extern "C" int b2_fill(int64_t n, double v, double* x_d, void* stream) {
     B2_CUDA(cudaGetLastError());
     return B2_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// dense mat-vecs (column-major): HBM-bound streams of A; one warp per 32 rows (gemv_n) / per column (gemv_t)
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double scl2(double beta, double w) { return beta == 0.0 ? 0.0 : beta * w; }
+
+// y_i = alpha * sum_j A(i,j) x_j + beta y_i : thread = row (coalesced along a column), 256 rows per CTA, columns split
+// over gridDim.y chunks and combined with a second pass when gridDim.y > 1 is avoided: each CTA owns its rows fully.
+__global__ void __launch_bounds__(256) k_gemv_n(int rows, int cols, int lda, const double* __restrict__ A, const double* __restrict__ x,
+                                                double* __restrict__ y, double alpha, double beta) {
+    __shared__ double xs[256];
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    double acc = 0.0;
+    for (int j0 = 0; j0 < cols; j0 += 256) {
+        __syncthreads();
+        if (j0 + threadIdx.x < cols) xs[threadIdx.x] = x[j0 + threadIdx.x];
+        __syncthreads();
+        const int nj = min(256, cols - j0);
+        if (i < rows) {
+            const double* col = A + (size_t)j0 * lda + i;
+            int j = 0;
+            for (; j + 8 <= nj; j += 8) {
+                double v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = col[(size_t)(j + u) * lda];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) acc = fma(v[u], xs[j + u], acc);
+            }
+            for (; j < nj; ++j) acc = fma(col[(size_t)j * lda], xs[j], acc);
+        }
+    }
+    if (i < rows) y[i] = alpha * acc + scl2(beta, y[i]);
+}
+// y_j = alpha * sum_i A(i,j) x_i + beta y_j : one warp per column, lanes stride the rows
+__global__ void __launch_bounds__(256) k_gemv_t(int rows, int cols, int lda, const double* __restrict__ A, const double* __restrict__ x,
+                                                double* __restrict__ y, double alpha, double beta) {
+    const int lane = threadIdx.x & 31;
+    const int j = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (j >= cols) return;
+    const double* col = A + (size_t)j * lda;
+    double acc = 0.0;
+    int i = lane;
+    for (; i + 7 * 32 < rows; i += 8 * 32) {
+        double v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = col[i + 32 * u];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc = fma(v[u], x[i + 32 * u], acc);
+    }
+    for (; i < rows; i += 32) acc = fma(col[i], x[i], acc);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) y[j] = alpha * acc + scl2(beta, y[j]);
+}
+// symmetric product from the lower triangle: y_j = alpha*( sum_{i>=j} A(i,j) x_i + sum_{i<j} A(j,i) x_i ) + beta*y_j.
+// One warp per column j: the column part streams coalesced; the row part (A(j,i), i<j) is a strided read of row j.
+__global__ void __launch_bounds__(256) k_symv_lower(int n, int lda, const double* __restrict__ A, const double* __restrict__ x,
+                                                    double* __restrict__ y, double alpha, double beta) {
+    const int lane = threadIdx.x & 31;
+    const int j = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (j >= n) return;
+    const double* col = A + (size_t)j * lda;
+    double acc = 0.0;
+    for (int i = j + lane; i < n; i += 32) acc = fma(col[i], x[i], acc);
+    for (int i = lane; i < j; i += 32) acc = fma(A[(size_t)i * lda + j], x[i], acc);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) y[j] = alpha * acc + scl2(beta, y[j]);
+}
+
+extern "C" int b2d_gemv_n(int32_t rows, int32_t cols, int32_t lda, const double* A_d, const double* x_d, double* y_d, double alpha,
+                          double beta, void* stream) {
+    if (rows < 0 || cols < 0 || lda < rows || (rows && (!y_d || (cols && (!A_d || !x_d))))) { set_error("b2d_gemv_n: invalid argument"); return B2_ERR_INVALID; }
+    if (rows == 0) return B2_OK;
+    k_gemv_n<<<(rows + 255) / 256, 256, 0, as_stream(stream)>>>(rows, cols, lda, A_d, x_d, y_d, alpha, beta);
+    B2_CUDA(cudaGetLastError());
+    return B2_OK;
+}
+extern "C" int b2d_gemv_t(int32_t rows, int32_t cols, int32_t lda, const double* A_d, const double* x_d, double* y_d, double alpha,
+                          double beta, void* stream) {
+    if (rows < 0 || cols < 0 || lda < rows || (cols && (!y_d || (rows && (!A_d || !x_d))))) { set_error("b2d_gemv_t: invalid argument"); return B2_ERR_INVALID; }
+    if (cols == 0) return B2_OK;
+    k_gemv_t<<<(cols + 7) / 8, 256, 0, as_stream(stream)>>>(rows, cols, lda, A_d, x_d, y_d, alpha, beta);
+    B2_CUDA(cudaGetLastError());
+    return B2_OK;
+}
+extern "C" int b2d_symv_lower(int32_t n, int32_t lda, const double* A_d, const double* x_d, double* y_d, double alpha, double beta,
+                              void* stream) {
+    if (n < 0 || lda < n || (n && (!A_d || !x_d || !y_d))) { set_error("b2d_symv_lower: invalid argument"); return B2_ERR_INVALID; }
+    if (n == 0) return B2_OK;
+    k_symv_lower<<<(n + 7) / 8, 256, 0, as_stream(stream)>>>(n, lda, A_d, x_d, y_d, alpha, beta);
+    B2_CUDA(cudaGetLastError());
+    return B2_OK;
+}

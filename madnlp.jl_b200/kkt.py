@@ -440,10 +440,14 @@ class DenseCondensedKKTSystem(_KKTBase):
         """Dense/condensed.jl:189-191."""
         return num_zero == 0 and num_neg == self.n_eq
 
+    def _gemv(self, trans, x, y, alpha, beta):
+        """y = alpha*op(jac)*x + beta*y with jac the m x n column-major device matrix (own kernels, no cuBLAS)"""
+        fn = lib.b2d_gemv_t if trans else lib.b2d_gemv_n
+        check(fn(self.m, self.n, self.m, ptr(self.jac), ptr(x), ptr(y), float(alpha), float(beta), _sp(self.stream)))
+
     def solve_kkt(self, w: UnreducedKKTVector):
-        """src/IPM/factorization.jl:190-229.  The two dense mat-vecs with `jac` go through torch (cuBLAS gemv):
-        library calls on the wrapper, not on the factor/solve kernels."""
-        n, ns, n_eq = self.n, self.ns, self.n_eq
+        """src/IPM/factorization.jl:190-229."""
+        n, ns = self.n, self.ns
         full = w.values
         wx = full[:n]; ws = full[n:n + ns]
         dual = w.dual()
@@ -452,14 +456,13 @@ class DenseCondensedKKTSystem(_KKTBase):
         self.buffer.zero_()
         wz = dual[self._ind_ineq_d]
         self.buffer[self._ind_ineq_d] = self.diag_buffer * (wz + ws / Ss)
-        J = self.jac.t()                                   # m x n view of the column-major memory
         x = self.pd_buffer
-        x[:n] = J.t() @ self.buffer
-        x[:n] += wx
+        x[:n] = wx
+        self._gemv(True, self.buffer, x, 1.0, 1.0)            # xx = jac' * buffer + wx
         x[n:] = dual[self._ind_eq_d]
         self.linear_solver.solve_linear_system(x)
         wx.copy_(x[:n])
-        dual.copy_(J @ wx)
+        self._gemv(False, wx, dual, 1.0, 0.0)                  # dual(w) = jac * wx
         dual[self._ind_eq_d] = x[n:]
         dual[self._ind_ineq_d] = dual[self._ind_ineq_d] * self.diag_buffer
         dual -= self.buffer
@@ -474,15 +477,14 @@ class DenseCondensedKKTSystem(_KKTBase):
         wx, ws = wp[:n], wp[n:]
         xx, xs = xp[:n], xp[n:]
         wy, xy = w.dual(), x.dual()
-        Hl = torch.tril(self.hess.t())                     # lower triangle of H (as _symv!('L', ...) reads it)
-        Hs = Hl + torch.tril(Hl, -1).t()
-        J = self.jac.t()
-        bw = (lambda t: beta * t) if beta != 0.0 else (lambda t: torch.zeros_like(t))
-        wx.copy_(alpha * (Hs @ xx) + bw(wx))
+        check(lib.b2d_symv_lower(n, n, ptr(self.hess), ptr(xx), ptr(wx), float(alpha), float(beta), _sp(self.stream)))   # _symv!('L', ...)
         if self.m > 0:
-            wx += alpha * (J.t() @ xy)
-            wy.copy_(alpha * (J @ xx) + bw(wy))
-        ws.copy_(bw(ws) - alpha * xy[self._ind_ineq_d])
+            self._gemv(True, xy, wx, alpha, 1.0)
+            self._gemv(False, xx, wy, alpha, beta)
+        if beta == 0.0:
+            ws.copy_(-alpha * xy[self._ind_ineq_d])
+        else:
+            ws.copy_(beta * ws - alpha * xy[self._ind_ineq_d])
         wy[self._ind_ineq_d] -= alpha * xs
         self._kktmul(w, x, alpha, beta)
         return w

@@ -360,3 +360,37 @@ def test_golden_fixture_on_device():
     M.factorize()
     x = M.solve_linear_system(_dev(np.array(k["b"]))).cpu().numpy()
     assert np.abs(x - np.array(k["x"])).max() < 1e-14 and list(M.inertia()) == k["inertia"]
+
+
+@pytest.mark.parametrize("rows,cols", [(1, 1), (130, 320), (515, 77), (2048, 4096)])
+def test_dense_matvec_kernels(rows, cols):
+    """b2d_gemv_n / b2d_gemv_t / b2d_symv_lower (the mat-vecs of AbstractDenseKKTSystem mul!/solve_kkt!) vs numpy fp64;
+    tolerance: 1e-13 relative to |A||x| (different summation order only)."""
+    _need_gpu()
+    from madnlp_jl_b200.capi import lib, check
+    rng = np.random.default_rng(rows * 7 + cols)
+    A = rng.standard_normal((rows, cols))
+    x = rng.standard_normal(cols); xt = rng.standard_normal(rows)
+    y0 = rng.standard_normal(rows); yt0 = rng.standard_normal(cols)
+    Ad = _dev(A.T.copy())                                  # column-major storage, lda = rows
+    st = torch.cuda.current_stream().cuda_stream
+    for alpha, beta in ((1.0, 0.0), (-0.5, 2.0)):
+        y = _dev(y0.copy()); yt = _dev(yt0.copy())
+        if beta == 0.0:
+            y.fill_(float("nan")); yt.fill_(float("nan"))  # beta == 0 must not read y (BLAS convention)
+        check(lib.b2d_gemv_n(rows, cols, rows, Ad.data_ptr(), _dev(x).data_ptr(), y.data_ptr(), alpha, beta, st))
+        check(lib.b2d_gemv_t(rows, cols, rows, Ad.data_ptr(), _dev(xt).data_ptr(), yt.data_ptr(), alpha, beta, st))
+        ref = alpha * (A @ x) + (beta * y0 if beta else 0.0)
+        reft = alpha * (A.T @ xt) + (beta * yt0 if beta else 0.0)
+        scale = np.abs(A) @ np.abs(x) + np.abs(y0) + 1.0
+        scalet = np.abs(A.T) @ np.abs(xt) + np.abs(yt0) + 1.0
+        assert (np.abs(y.cpu().numpy() - ref) / scale).max() < 1e-13
+        assert (np.abs(yt.cpu().numpy() - reft) / scalet).max() < 1e-13
+    n = min(rows, cols)
+    S = rng.standard_normal((n, n)); S = S + S.T
+    low = np.tril(S) + np.triu(np.full((n, n), np.nan), 1)  # the upper triangle must never be read
+    xs = rng.standard_normal(n); ys0 = rng.standard_normal(n)
+    ys = _dev(ys0.copy())
+    check(lib.b2d_symv_lower(n, n, _dev(low.T.copy()).data_ptr(), _dev(xs).data_ptr(), ys.data_ptr(), 0.75, -1.0, st))
+    ref = 0.75 * (S @ xs) - ys0
+    assert (np.abs(ys.cpu().numpy() - ref) / (np.abs(S) @ np.abs(xs) + np.abs(ys0) + 1.0)).max() < 1e-13
