@@ -374,12 +374,13 @@ def test_dense_matvec_kernels(rows, cols):
     y0 = rng.standard_normal(rows); yt0 = rng.standard_normal(cols)
     Ad = _dev(A.T.copy())                                  # column-major storage, lda = rows
     st = torch.cuda.current_stream().cuda_stream
+    xd, xtd = _dev(x), _dev(xt)                            # (named: a temporary would be freed before the launch)
     for alpha, beta in ((1.0, 0.0), (-0.5, 2.0)):
         y = _dev(y0.copy()); yt = _dev(yt0.copy())
         if beta == 0.0:
             y.fill_(float("nan")); yt.fill_(float("nan"))  # beta == 0 must not read y (BLAS convention)
-        check(lib.b2d_gemv_n(rows, cols, rows, Ad.data_ptr(), _dev(x).data_ptr(), y.data_ptr(), alpha, beta, st))
-        check(lib.b2d_gemv_t(rows, cols, rows, Ad.data_ptr(), _dev(xt).data_ptr(), yt.data_ptr(), alpha, beta, st))
+        check(lib.b2d_gemv_n(rows, cols, rows, Ad.data_ptr(), xd.data_ptr(), y.data_ptr(), alpha, beta, st))
+        check(lib.b2d_gemv_t(rows, cols, rows, Ad.data_ptr(), xtd.data_ptr(), yt.data_ptr(), alpha, beta, st))
         ref = alpha * (A @ x) + (beta * y0 if beta else 0.0)
         reft = alpha * (A.T @ xt) + (beta * yt0 if beta else 0.0)
         scale = np.abs(A) @ np.abs(x) + np.abs(y0) + 1.0
@@ -390,7 +391,7 @@ def test_dense_matvec_kernels(rows, cols):
     S = rng.standard_normal((n, n)); S = S + S.T
     low = np.tril(S) + np.triu(np.full((n, n), np.nan), 1)  # the upper triangle must never be read
     xs = rng.standard_normal(n); ys0 = rng.standard_normal(n)
-    ys = _dev(ys0.copy())
-    check(lib.b2d_symv_lower(n, n, _dev(low.T.copy()).data_ptr(), _dev(xs).data_ptr(), ys.data_ptr(), 0.75, -1.0, st))
+    ys = _dev(ys0.copy()); lowd = _dev(low.T.copy()); xsd = _dev(xs)
+    check(lib.b2d_symv_lower(n, n, lowd.data_ptr(), xsd.data_ptr(), ys.data_ptr(), 0.75, -1.0, st))
     ref = 0.75 * (S @ xs) - ys0
     assert (np.abs(ys.cpu().numpy() - ref) / (np.abs(S) @ np.abs(xs) + np.abs(ys0) + 1.0)).max() < 1e-13
