@@ -1,0 +1,271 @@
+// Blocked right-looking LDL^T of the HBM-resident fronts (order > small_front_max) and of the dense solver, 128 pivot
+// columns per outer step, three launches per step:
+//
+//   k_big_diag128   one CTA per front: the 128 x 128 diagonal block is factorised entirely in shared memory
+//                   (4 sub-blocks of 32: register LDL^T by one warp, sub-panel substitution, in-block trailing update),
+//                   written back (unit-lower L11, D), and its unit-lower INVERSE is formed in place and stored to the
+//                   Linv buffer -- the same blocks the multi-CTA triangular solves use (bigsolve_kernels.cuh).
+//   k_big_trsm      rows below the block:  L21 = A21 * L11^{-T} * D^{-1}  as a DMMA GEMM against Linv (64 rows per CTA,
+//                   operands streamed by cp.async), in place.
+//   k_big_update_pipe (front_kernels.cuh)  trailing update with all 128 pivots at once.
+//
+// so a front of order N costs 3*N/128 dependent launches instead of 13*N/128, and the diagonal-block inversion is no
+// longer a separate pass.  Pivoting is static (front_kernels.cuh): |d| < eps is replaced by sign(d)*eps and counted.
+#pragma once
+#include "front_kernels.cuh"
+
+namespace b2 {
+
+constexpr int DB = 128;                   // outer block (== BS of the solve kernels)
+
+// Shared-memory / warp-shuffle issue is the scarce resource of a single SM here (measured on B200,
+// tools/microbench/fp64_pipes.cu: one LDS.64 or SHFL.64 per ~4.6-9 clk per scheduler vs one DFMA per ~2 clk), so the
+// block lives in REGISTERS: 256 threads as a 16 x 16 grid, thread (ty, tx) owns the 8 x 8 entries (ty + 16a, tx + 16b)
+// -- cyclic, so the shrinking trailing matrix stays balanced.  The matrix is kept fully symmetric, which makes the pivot
+// column also the pivot row: per pivot the 16 owner threads publish it (one barrier), and every thread then needs just
+// 8 + 8 values (conflict-free: lanes read consecutive or identical addresses) for up to 64 FMAs.  Entries of already-eliminated rows/columns in a
+// thread's boundary sub-block keep receiving (meaningless) updates; they are never read again.
+struct Diag128Smem {
+    double Lc[DB * DB];                   // Lc[k*DB + i] = l(i,k) for i > k, 0 for i <= k
+    double ubuf[2][DB];                   // pivot column (unscaled), double-buffered
+    double xbuf[2][DB];                   // row k of the inverse
+    double dd[DB];
+};
+
+__global__ void __launch_bounds__(256, 1) k_big_diag128(FactorArgs a, const int32_t* __restrict__ list, int kb,
+                                                        double* __restrict__ Linv, const int64_t* __restrict__ linv_off) {
+    const int s = list[blockIdx.x];
+    const FrontDesc d = a.desc[s];
+    if (kb >= d.w) return;
+    extern __shared__ __align__(16) unsigned char dsm_raw[];
+    Diag128Smem& sm = *reinterpret_cast<Diag128Smem*>(dsm_raw);
+    const int f = d.f, nb = min(DB, d.w - kb);
+    const int tid = threadIdx.x, ty = tid & 15, tx = tid >> 4;
+    double* Lp = a.L + d.lp_off;
+#ifdef B2_DIAG_PROF
+    long long tprof[8]; int np = 0;
+#define DPROF() do { __syncthreads(); tprof[np++] = clock64(); } while (0)
+#else
+#define DPROF() do {} while (0)
+#endif
+    DPROF();
+    // ---- stage the lower triangle (coalesced: i fastest), then pick the symmetric 8 x 8 register block out of it
+    double* stage = sm.Lc;                                         // stage[j*DB + i], i >= j
+    for (int e = tid; e < DB * DB; e += 256) {                     // all 64 copies of a thread in flight at once
+        const int i = e & (DB - 1), j = e >> 7;
+        if (j <= i) cp_async8_zfill(stage + j * DB + i, Lp + (size_t)(kb + j) * f + kb + min(i, nb - 1), i < nb);
+    }
+    cp_async_commit_group();
+    cp_async_wait_group_n<0>();
+    __syncthreads();
+    if (nb < DB) {                                                 // identity padding
+        if (tid < DB && tid >= nb) stage[tid * DB + tid] = 1.0;
+        __syncthreads();
+    }
+    double A[8][8];
+#pragma unroll
+    for (int ia = 0; ia < 8; ++ia)
+#pragma unroll
+        for (int ib = 0; ib < 8; ++ib) {
+            const int i = ty + 16 * ia, j = tx + 16 * ib;
+            A[ia][ib] = stage[min(i, j) * DB + max(i, j)];
+        }
+    __syncthreads();
+    int nneg = 0, npert = 0;
+    DPROF();
+    // ---- phase F: unblocked right-looking LDL^T, one barrier per pivot
+#pragma unroll
+    for (int kq = 0; kq < 8; ++kq) {
+        for (int kk = 0; kk < 16; ++kk) {
+            const int k = 16 * kq + kk;
+            if (k >= nb) break;
+            double* ub = sm.ubuf[k & 1];
+            if (tx == kk) {                                        // owners of column k: rows ty + 16a
+#pragma unroll
+                for (int ia = 0; ia < 8; ++ia) ub[ty + 16 * ia] = A[ia][kq];
+            }
+            __syncthreads();
+            double dk = ub[k];
+            if (!(fabs(dk) >= a.eps)) { dk = (dk < 0.0) ? -a.eps : a.eps; ++npert; }
+            else if (dk < 0.0) ++nneg;
+            const double rk = fast_rcp_d(dk);
+            double ur[8], uc[8];
+#pragma unroll
+            for (int ia = 0; ia < 8; ++ia) ur[ia] = (ia >= kq) ? ub[ty + 16 * ia] : 0.0;
+#pragma unroll
+            for (int ib = 0; ib < 8; ++ib) uc[ib] = (ib >= kq) ? ub[tx + 16 * ib] : 0.0;
+            if (tx == kk) {
+                double* lc = sm.Lc + k * DB + ty;
+#pragma unroll
+                for (int ia = 0; ia < 8; ++ia) lc[16 * ia] = (ty + 16 * ia > k) ? ur[ia] * rk : 0.0;
+                if (ty == kk) sm.dd[k] = dk;
+            }
+#pragma unroll
+            for (int ia = 0; ia < 8; ++ia) {
+                if (ia < kq) continue;
+                const double li = -ur[ia] * rk;
+#pragma unroll
+                for (int ib = 0; ib < 8; ++ib)
+                    if (ib >= kq) A[ia][ib] = fma(li, uc[ib], A[ia][ib]);
+            }
+        }
+    }
+    if (tid == 0) {
+        if (nneg) atomicAdd(a.counters + 0, nneg);
+        if (npert) atomicAdd(a.counters + 1, npert);
+    }
+    __syncthreads();
+    DPROF();
+    // ---- write back L11 (strict lower, unit diagonal implied) and D
+    for (int e = tid; e < DB * DB; e += 256) {
+        const int i = e & (DB - 1), j = e >> 7;
+        if (i < nb && j < i) Lp[(size_t)(kb + j) * f + kb + i] = sm.Lc[j * DB + i];
+    }
+    if (tid < nb) {
+        Lp[(size_t)(kb + tid) * f + kb + tid] = sm.dd[tid];
+        a.dvec[d.col0 + kb + tid] = sm.dd[tid];
+    }
+    DPROF();
+    // ---- phase I: X = L11^{-1} by the same elementary operations applied to the identity:
+    //      for k: X(i, :) -= l(i,k) * X(k, :), i > k  (row k is final by then and non-zero only in columns <= k)
+#pragma unroll
+    for (int ia = 0; ia < 8; ++ia)
+#pragma unroll
+        for (int ib = 0; ib < 8; ++ib) A[ia][ib] = (ty + 16 * ia == tx + 16 * ib) ? 1.0 : 0.0;
+#pragma unroll
+    for (int kq = 0; kq < 8; ++kq) {
+        for (int kk = 0; kk < 16; ++kk) {
+            const int k = 16 * kq + kk;
+            if (k + 1 >= nb) break;                                // the last column has nothing below it
+            double* xb = sm.xbuf[k & 1];
+            if (ty == kk) {                                        // owners of row k: columns tx + 16b
+#pragma unroll
+                for (int ib = 0; ib < 8; ++ib) xb[tx + 16 * ib] = A[kq][ib];
+            }
+            __syncthreads();
+            const double* lc = sm.Lc + k * DB + ty;
+#pragma unroll
+            for (int ia = 0; ia < 8; ++ia) {
+                if (ia < kq) continue;
+                const double li = -lc[16 * ia];
+#pragma unroll
+                for (int ib = 0; ib < 8; ++ib)
+                    if (ib <= kq) A[ia][ib] = fma(li, xb[tx + 16 * ib], A[ia][ib]);
+            }
+        }
+    }
+    DPROF();
+    // ---- store the inverse, column-major with ld DB, zero outside the nb x nb unit-lower block
+    double* out = Linv + linv_off[s] + (size_t)(kb / DB) * DB * DB;
+#pragma unroll
+    for (int ib = 0; ib < 8; ++ib)
+#pragma unroll
+        for (int ia = 0; ia < 8; ++ia) {
+            const int i = ty + 16 * ia, j = tx + 16 * ib;
+            double v = 0.0;
+            if (i < nb && j < nb) v = (i > j) ? A[ia][ib] : (i == j ? 1.0 : 0.0);
+            out[(size_t)j * DB + i] = v;
+        }
+#ifdef B2_DIAG_PROF
+    DPROF();
+    if (tid == 0 && blockIdx.x == 0 && (kb == 0 || kb == 1280))
+        printf("diag128 kb=%d nb=%d: load %lld  F %lld  writeback %lld  I %lld  store %lld  clk\n", kb, nb, tprof[1] - tprof[0], tprof[2] - tprof[1],
+               tprof[3] - tprof[2], tprof[4] - tprof[3], tprof[5] - tprof[4]);
+#endif
+#undef DPROF
+}
+
+// L21 = A21 * Linv^T * D^{-1} for the rows below the diagonal block, in place.  GEMM view (transposed so that the
+// 128-wide side is the pivot-column index):  Ut(c, i) = sum_{k <= c} Linv(c, k) * A21(i, k);  tile 128 (c) x 64 (rows i).
+constexpr int TR_ROWS = GU_N;            // 64 rows of the front per CTA
+__global__ void __launch_bounds__(256, 2) k_big_trsm(FactorArgs a, const int32_t* __restrict__ list, int kb,
+                                                     const double* __restrict__ Linv, const int64_t* __restrict__ linv_off) {
+    const int s = list[blockIdx.y];
+    const FrontDesc d = a.desc[s];
+    if (kb >= d.w) return;
+    const int f = d.f, nb = min(DB, d.w - kb);
+    const int r0 = kb + nb + blockIdx.x * TR_ROWS;
+    if (r0 >= f) return;
+    extern __shared__ __align__(16) double gu_sm[];
+    double* As = gu_sm;                                               // [stage][k][GU_LDA]  Linv(c, k)
+    double* Bs = gu_sm + GU_STAGES * GU_K * GU_LDA;                   // [stage][k][GU_LDB]  A21(i, k)
+    double* dinv = Bs + GU_STAGES * GU_K * GU_LDB;
+    double* Lp = a.L + d.lp_off;
+    const double* Li = Linv + linv_off[s] + (size_t)(kb / DB) * DB * DB;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, q = lane & 3;
+    const int wi = (warp & 3) * 32, wj = (warp >> 2) * 32;
+    if (tid < DB) dinv[tid] = (tid < nb) ? 1.0 / Lp[(size_t)(kb + tid) * f + kb + tid] : 0.0;
+    const int nchunk = (nb + GU_K - 1) / GU_K;
+    const int la_c = tid & (GU_M - 1), la_k = tid >> 7;
+    const int lb_i = tid & (GU_N - 1), lb_k = tid >> 6;
+    const bool b_ok = r0 + lb_i < f;
+    const double* b_src = Lp + (size_t)kb * f + (b_ok ? r0 + lb_i : 0);
+    auto issue = [&](int ch) {
+        const int st = ch % GU_STAGES;
+        double* Ad = As + (size_t)st * GU_K * GU_LDA + la_c;
+        double* Bd = Bs + (size_t)st * GU_K * GU_LDB + lb_i;
+#pragma unroll
+        for (int p = 0; p < GU_K / 2; ++p) {
+            const int k = ch * GU_K + la_k + 2 * p;                   // k < 128 always; the buffer is zero-padded
+            cp_async8_zfill(Ad + (la_k + 2 * p) * GU_LDA, Li + (size_t)k * DB + la_c, true);
+        }
+#pragma unroll
+        for (int p = 0; p < GU_K / 4; ++p) {
+            const int k = ch * GU_K + lb_k + 4 * p;
+            const bool ok = b_ok && k < nb;
+            cp_async8_zfill(Bd + (lb_k + 4 * p) * GU_LDB, b_src + (size_t)(ok ? k : 0) * f, ok);
+        }
+    };
+#pragma unroll
+    for (int sgi = 0; sgi < GU_STAGES - 1; ++sgi) {
+        if (sgi < nchunk) issue(sgi);
+        cp_async_commit_group();
+    }
+    double c[4][4][2];
+#pragma unroll
+    for (int x = 0; x < 4; ++x)
+#pragma unroll
+        for (int y = 0; y < 4; ++y) c[x][y][0] = c[x][y][1] = 0.0;
+    for (int ch = 0; ch < nchunk; ++ch) {
+        cp_async_wait_group_n<GU_STAGES - 2>();
+        __syncthreads();
+        if (ch + GU_STAGES - 1 < nchunk) issue(ch + GU_STAGES - 1);
+        cp_async_commit_group();
+        if (wi + 31 < ch * GU_K) continue;                            // Linv(c, k) = 0 for k > c: nothing for this warp
+        const double* Ab = As + (size_t)(ch % GU_STAGES) * GU_K * GU_LDA;
+        const double* Bb = Bs + (size_t)(ch % GU_STAGES) * GU_K * GU_LDB;
+#pragma unroll
+        for (int k0 = 0; k0 < GU_K; k0 += 4) {
+            double af[4], bf[4];
+#pragma unroll
+            for (int x = 0; x < 4; ++x) af[x] = Ab[(k0 + q) * GU_LDA + wi + 8 * x + g];
+#pragma unroll
+            for (int y = 0; y < 4; ++y) bf[y] = Bb[(k0 + q) * GU_LDB + wj + 8 * y + g];
+#pragma unroll
+            for (int x = 0; x < 4; ++x)
+#pragma unroll
+                for (int y = 0; y < 4; ++y)
+                    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                                 : "+d"(c[x][y][0]), "+d"(c[x][y][1])
+                                 : "d"(af[x]), "d"(bf[y]));
+        }
+    }
+    // epilogue: Ut -> shared memory as Cs[i][c], then coalesced stores of L21(i, c) = Ut(c, i) / d_c  (i fastest)
+    cp_async_wait_group_n<0>();
+    __syncthreads();
+    double* Cs = gu_sm;                                               // [TR_ROWS][GU_LDC]
+#pragma unroll
+    for (int x = 0; x < 4; ++x)
+#pragma unroll
+        for (int y = 0; y < 4; ++y)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) Cs[(wj + 8 * y + 2 * q + e) * GU_LDC + wi + 8 * x + g] = c[x][y][e];
+    __syncthreads();
+    const int i = tid & (TR_ROWS - 1);
+    if (r0 + i < f) {
+        for (int cc = tid >> 6; cc < nb; cc += 4) Lp[(size_t)(kb + cc) * f + r0 + i] = Cs[i * GU_LDC + cc] * dinv[cc];
+    }
+}
+
+}  // namespace b2

@@ -116,19 +116,30 @@ __global__ void __launch_bounds__(256) k_bs_fwd(BigSolveArgs b, const int32_t* _
 }
 
 // ---- backward init: t_j = y_j / d_j - sum_{i >= w} L(i,j) x(rows_i)  (y_j parked in `side` by the forward sweep);
-//      grid (ceil(w/256), nfronts)
+//      one warp per pivot column (lanes stride the rows: coalesced stream of the column), grid (ceil(w/8), nfronts)
 __global__ void __launch_bounds__(256) k_bs_bwd_init(BigSolveArgs b, const int32_t* __restrict__ list) {
     const SolveArgs& a = b.s;
     const int s = list[blockIdx.y];
     const FrontDesc d = a.desc[s];
-    const int j = blockIdx.x * 256 + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int j = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (j >= d.w) return;
     const int f = d.f;
-    const double* col = a.L + d.lp_off + (size_t)j * f;
-    const int32_t* rows = a.rows + d.rows_off;
+    const double* __restrict__ col = a.L + d.lp_off + (size_t)j * f;
+    const int32_t* __restrict__ rows = a.rows + d.rows_off;
     double acc = 0.0;
-    for (int i = d.w; i < f; ++i) acc = fma(col[i], a.xp[rows[i]], acc);
-    a.xp[d.col0 + j] = b.side[d.col0 + j] / a.dvec[d.col0 + j] - acc;
+    int i = d.w + lane;
+    for (; i + 96 < f; i += 128) {
+        double l[4], x[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { l[u] = col[i + 32 * u]; x[u] = a.xp[rows[i + 32 * u]]; }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) acc = fma(l[u], x[u], acc);
+    }
+    for (; i < f; i += 32) acc = fma(col[i], a.xp[rows[i]], acc);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) a.xp[d.col0 + j] = b.side[d.col0 + j] / a.dvec[d.col0 + j] - acc;
 }
 
 constexpr int BSB_COLS = 256;    // earlier pivot columns per CTA in the backward update

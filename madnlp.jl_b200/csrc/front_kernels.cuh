@@ -201,10 +201,26 @@ __global__ void k_big_extend_add(FactorArgs a, const int32_t* __restrict__ list,
     const int lane = threadIdx.x & 31;
     const int wglob = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int r = d.f - d.w;
     for (int j = wglob; j < rc; j += nwarps) {
         const int pj = rl[j];
-        const double* col = CB + (size_t)j * rc;
-        for (int i = j + lane; i < rc; i += 32) *front_ptr(a, d, rl[i], pj) += col[i];
+        const double* __restrict__ col = CB + (size_t)j * rc;
+        // destination column of the parent front (panel or update block), indexed by the parent-local row
+        double* dst = (pj < d.w) ? a.L + d.lp_off + (size_t)pj * d.f : a.ws + d.cb_off + (size_t)(pj - d.w) * r - d.w;
+        for (int i = j + lane; i < rc; i += 128) {          // 4 independent read-modify-writes in flight per lane
+            int ri[4]; double v[4], t[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int ii = i + 32 * u;
+                const bool ok = ii < rc;
+                ri[u] = ok ? rl[ii] : -1;
+                v[u] = ok ? col[ii] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) t[u] = (ri[u] >= 0) ? dst[ri[u]] : 0.0;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) if (ri[u] >= 0) dst[ri[u]] = t[u] + v[u];
+        }
     }
 }
 
@@ -373,6 +389,143 @@ __global__ void __launch_bounds__(256) k_big_update(FactorArgs a, const int32_t*
                 const int j = j0 + wj + 8 * y + 2 * q + e;
                 if (i < f && j < jhi && i >= j) *front_ptr(a, d, i, j) -= c[x][y][e];
             }
+}
+
+
+// ----------------------------------------------------------------------------------------------------------
+// Trailing update, pipelined variant (the WIDE updates carry > 95 % of the flops of a big front):
+//   C(i,j) -= sum_{k in [kb0, kb0+kcount)} L(i,k) d_k L(j,k),  i >= j, jlo <= j < jhi
+// 128 x 64 tiles, 8 warps as 4 x 2 (32 x 32 per warp = 4 x 4 m8n8k4 DMMA fragments).  Both operands are raw panel
+// columns of L streamed by cp.async through a GU_STAGES-deep ring of K = 16 slices (no register staging, loads stay in
+// flight under the tensor pipe); the -d_k scaling is applied to the A fragments in registers (4 DMUL per 16 DMMA), and
+// the epilogue adds the (negative) accumulators to C.
+// ----------------------------------------------------------------------------------------------------------
+constexpr int GU_M = 128, GU_N = 64, GU_K = 16, GU_STAGES = 4;
+constexpr int GU_LDA = GU_M + 4, GU_LDB = GU_N + 4, GU_LDC = GU_M + 2;
+constexpr size_t GU_SMEM = (size_t)(GU_STAGES * GU_K * (GU_LDA + GU_LDB) + 128) * sizeof(double);
+
+__device__ __forceinline__ void cp_async8_zfill(void* smem_dst, const void* gsrc, bool valid) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    const int sz = valid ? 8 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(sa), "l"(gsrc), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_group() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group_n() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__global__ void __launch_bounds__(256, 2) k_big_update_pipe(FactorArgs a, const int32_t* __restrict__ list, int kb0, int kmax, int jlo_rel,
+                                                            int jhi_rel, int clip_jlo) {
+    const FrontDesc d = a.desc[list[blockIdx.z]];
+    if (kb0 >= d.w) return;
+    const int f = d.f;
+    const int kcount = min(kmax, d.w - kb0);
+    const int jlo = kb0 + (clip_jlo ? min(jlo_rel, kcount) : jlo_rel);
+    const int jhi = min(f, kb0 + jhi_rel);
+    const int i0 = jlo + blockIdx.x * GU_M, j0 = jlo + blockIdx.y * GU_N;
+    if (j0 > i0 + GU_M - 1 || i0 >= f || j0 >= jhi) return;          // tile above the diagonal / outside the front
+    extern __shared__ __align__(16) double gu_sm[];
+    double* As = gu_sm;                                               // [stage][k][GU_LDA]
+    double* Bs = gu_sm + GU_STAGES * GU_K * GU_LDA;                   // [stage][k][GU_LDB]
+    double* dneg = Bs + GU_STAGES * GU_K * GU_LDB;                    // -d_k, k < kcount (<= 128)
+    const double* Lp = a.L + d.lp_off;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, q = lane & 3;
+    const int wi = (warp & 3) * 32, wj = (warp >> 2) * 32;
+    if (tid < 128) dneg[tid] = (tid < kcount) ? -Lp[(size_t)(kb0 + tid) * f + kb0 + tid] : 0.0;
+    const int nchunk = (kcount + GU_K - 1) / GU_K;
+    const int la_i = tid & (GU_M - 1), la_k = tid >> 7;               // A loader: 2 k-rows per pass, 8 passes
+    const int lb_j = tid & (GU_N - 1), lb_k = tid >> 6;               // B loader: 4 k-rows per pass, 4 passes
+    const bool a_ok = i0 + la_i < f, b_ok = j0 + lb_j < f;
+    const double* a_src = Lp + (size_t)kb0 * f + (a_ok ? i0 + la_i : 0);
+    const double* b_src = Lp + (size_t)kb0 * f + (b_ok ? j0 + lb_j : 0);
+    auto issue = [&](int ch) {
+        const int st = ch % GU_STAGES;
+        double* Ad = As + (size_t)st * GU_K * GU_LDA + la_i;
+        double* Bd = Bs + (size_t)st * GU_K * GU_LDB + lb_j;
+#pragma unroll
+        for (int p = 0; p < GU_K / 2; ++p) {
+            const int k = ch * GU_K + la_k + 2 * p;
+            const bool ok = a_ok && k < kcount;
+            cp_async8_zfill(Ad + (la_k + 2 * p) * GU_LDA, a_src + (size_t)(ok ? k : 0) * f, ok);
+        }
+#pragma unroll
+        for (int p = 0; p < GU_K / 4; ++p) {
+            const int k = ch * GU_K + lb_k + 4 * p;
+            const bool ok = b_ok && k < kcount;
+            cp_async8_zfill(Bd + (lb_k + 4 * p) * GU_LDB, b_src + (size_t)(ok ? k : 0) * f, ok);
+        }
+    };
+#pragma unroll
+    for (int sgi = 0; sgi < GU_STAGES - 1; ++sgi) {
+        if (sgi < nchunk) issue(sgi);
+        cp_async_commit_group();
+    }
+    double c[4][4][2];
+#pragma unroll
+    for (int x = 0; x < 4; ++x)
+#pragma unroll
+        for (int y = 0; y < 4; ++y) c[x][y][0] = c[x][y][1] = 0.0;
+    for (int ch = 0; ch < nchunk; ++ch) {
+        cp_async_wait_group_n<GU_STAGES - 2>();
+        __syncthreads();                                              // slice ch landed; slice ch-1 fully consumed
+        if (ch + GU_STAGES - 1 < nchunk) issue(ch + GU_STAGES - 1);
+        cp_async_commit_group();
+        const double* Ab = As + (size_t)(ch % GU_STAGES) * GU_K * GU_LDA;
+        const double* Bb = Bs + (size_t)(ch % GU_STAGES) * GU_K * GU_LDB;
+#pragma unroll
+        for (int k0 = 0; k0 < GU_K; k0 += 4) {
+            const double sc = dneg[ch * GU_K + k0 + q];
+            double af[4], bf[4];
+#pragma unroll
+            for (int x = 0; x < 4; ++x) af[x] = Ab[(k0 + q) * GU_LDA + wi + 8 * x + g] * sc;
+#pragma unroll
+            for (int y = 0; y < 4; ++y) bf[y] = Bb[(k0 + q) * GU_LDB + wj + 8 * y + g];
+#pragma unroll
+            for (int x = 0; x < 4; ++x)
+#pragma unroll
+                for (int y = 0; y < 4; ++y)
+                    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                                 : "+d"(c[x][y][0]), "+d"(c[x][y][1])
+                                 : "d"(af[x]), "d"(bf[y]));
+        }
+    }
+    // epilogue: accumulators -> shared memory (column-major tile), then a coalesced read-modify-write of C with all of
+    // a thread's loads in flight at once (the fragment layout would make it 32 dependent 8-byte round trips per thread)
+    cp_async_wait_group_n<0>();
+    __syncthreads();
+    double* Cs = gu_sm;                                               // [GU_N][GU_LDC]
+#pragma unroll
+    for (int x = 0; x < 4; ++x)
+#pragma unroll
+        for (int y = 0; y < 4; ++y)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) Cs[(wj + 8 * y + 2 * q + e) * GU_LDC + wi + 8 * x + g] = c[x][y][e];
+    __syncthreads();
+    const int r = f - d.w;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        double t[4][4];
+        double* colp[4];
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+            const int jj = warp * 8 + half * 4 + cc, j = j0 + jj;
+            colp[cc] = (j < d.w) ? a.L + d.lp_off + (size_t)j * f : a.ws + d.cb_off + (size_t)(j - d.w) * r - d.w;
+#pragma unroll
+            for (int rr = 0; rr < 4; ++rr) {
+                const int i = i0 + lane + 32 * rr;
+                t[cc][rr] = (j < jhi && i < f && i >= j) ? colp[cc][i] : 0.0;
+            }
+        }
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+            const int jj = warp * 8 + half * 4 + cc, j = j0 + jj;
+#pragma unroll
+            for (int rr = 0; rr < 4; ++rr) {
+                const int i = i0 + lane + 32 * rr;
+                if (j < jhi && i < f && i >= j) colp[cc][i] = t[cc][rr] + Cs[jj * GU_LDC + lane + 32 * rr];
+            }
+        }
+    }
 }
 
 }  // namespace b2

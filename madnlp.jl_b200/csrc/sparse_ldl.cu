@@ -9,6 +9,7 @@
 #include "analysis.hpp"
 #include "common.cuh"
 #include "front_kernels.cuh"
+#include "bigfactor_kernels.cuh"
 #include "solve_kernels.cuh"
 #include "warp_kernels.cuh"
 #include "bigsolve_kernels.cuh"
@@ -84,6 +85,64 @@ struct b2_solver {
 };
 
 namespace {
+
+// wide trailing update of every big front in `lb`: all `ob_cols` pivots of the outer panel at `ob` applied to the `rem`
+// rows/columns behind it (cp.async-pipelined DMMA kernel; B2_WIDE_PIPE=0 selects the unpipelined 64x64 kernel)
+bool wide_pipe_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("B2_WIDE_PIPE"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v != 0;
+}
+// 128-column outer steps (k_big_diag128 / k_big_trsm / k_big_update_pipe); B2_BIG_V2=0 selects the 32-column chain
+bool big_v2_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("B2_BIG_V2"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v != 0;
+}
+// one outer step of every big front in `lb`: diagonal block (factor + inverse), rows below, trailing update
+void launch_big_step(const FactorArgs& a, const int32_t* lb, int nfronts, int ob, int maxf, double* Linv, const int64_t* linv_off,
+                     cudaStream_t st, int64_t* nl) {
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(k_big_diag128, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Diag128Smem));
+        cudaFuncSetAttribute(k_big_trsm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GU_SMEM);
+        cudaFuncSetAttribute(k_big_update_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GU_SMEM);
+        attr = true;
+    }
+    k_big_diag128<<<nfronts, 256, sizeof(Diag128Smem), st>>>(a, lb, ob, Linv, linv_off);
+    if (nl) ++*nl;
+    const int rem = maxf - ob - 1;                  // rows below the first pivot of the block (upper bound over the fronts)
+    if (rem <= 0) return;
+    k_big_trsm<<<dim3((rem + TR_ROWS - 1) / TR_ROWS, nfronts), 256, GU_SMEM, st>>>(a, lb, ob, Linv, linv_off);
+    k_big_update_pipe<<<dim3((rem + GU_M - 1) / GU_M, (rem + GU_N - 1) / GU_N, nfronts), 256, GU_SMEM, st>>>(a, lb, ob, DB, DB, 1 << 30, 1);
+    if (nl) *nl += 2;
+}
+bool narrow_pipe_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("B2_NARROW_PIPE"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v != 0;
+}
+// narrow update after a 32-column step: the rest of the current outer panel only (columns [kb+nb, kb+32+ncols))
+void launch_narrow_update(const FactorArgs& a, const int32_t* lb, int nfronts, int kb, int ncols, int rem, cudaStream_t st) {
+    if (narrow_pipe_enabled()) {
+        static bool attr = false;
+        if (!attr) { cudaFuncSetAttribute(k_big_update_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GU_SMEM); attr = true; }
+        k_big_update_pipe<<<dim3((rem + GU_M - 1) / GU_M, (ncols + BIG_NB + GU_N - 1) / GU_N, nfronts), 256, GU_SMEM, st>>>(a, lb, kb, BIG_NB, BIG_NB, BIG_NB + ncols, 1);
+    } else {
+        const int nt = (rem + UT - 1) / UT;
+        k_big_update<<<dim3(nt, (ncols + BIG_NB + UT - 1) / UT, nfronts), 256, 0, st>>>(a, lb, kb, BIG_NB, BIG_NB, BIG_NB + ncols, 1);
+    }
+}
+void launch_wide_update(const FactorArgs& a, const int32_t* lb, int nfronts, int ob, int ob_cols, int rem, cudaStream_t st) {
+    if (wide_pipe_enabled()) {
+        static bool attr = false;
+        if (!attr) { cudaFuncSetAttribute(k_big_update_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GU_SMEM); attr = true; }
+        k_big_update_pipe<<<dim3((rem + GU_M - 1) / GU_M, (rem + GU_N - 1) / GU_N, nfronts), 256, GU_SMEM, st>>>(a, lb, ob, ob_cols, ob_cols, 1 << 30, 0);
+    } else {
+        const int nt = (rem + UT - 1) / UT;
+        k_big_update<<<dim3(nt, nt, nfronts), 256, 0, st>>>(a, lb, ob, ob_cols, ob_cols, 1 << 30, 0);
+    }
+}
 
 FactorArgs factor_args(b2_solver* s) {
     FactorArgs a;
@@ -165,6 +224,9 @@ int64_t enqueue_factor(b2_solver* s, int ph, cudaStream_t st) {
                 ++nl;
             }
             constexpr int OB = 128;                      // outer panel: 4 steps of BIG_NB columns
+            if (big_v2_enabled()) {
+                for (int ob = 0; ob < lv.maxwB; ob += DB) launch_big_step(a, lb, lv.nB, ob, lv.maxfB, s->d_Linv.p, s->d_linv_off.p, st, &nl);
+            } else
             for (int ob = 0; ob < lv.maxwB; ob += OB) {
                 for (int kb = ob; kb < std::min(ob + OB, lv.maxwB); kb += BIG_NB) {
                     const int step = kb / BIG_NB;
@@ -176,15 +238,13 @@ int64_t enqueue_factor(b2_solver* s, int ph, cudaStream_t st) {
                     ++nl;
                     const int ncols = ob + OB - (kb + BIG_NB);      // rest of the outer panel
                     if (ncols > 0 || lv.partialB) {                 // (a partial last block leaves columns [kb+nb, kb+32) to serve)
-                        const int nt = (rem + UT - 1) / UT;
-                        k_big_update<<<dim3(nt, (ncols + BIG_NB + UT - 1) / UT, lv.nB), 256, 0, st>>>(a, lb, kb, BIG_NB, BIG_NB, BIG_NB + ncols, 1);
+                        launch_narrow_update(a, lb, lv.nB, kb, ncols, rem, st);
                         ++nl;
                     }
                 }
-                const int rem = lv.maxfB - ob - 1;
+                const int rem = lv.maxfB - ob - OB;
                 if (rem > 0) {                              // everything behind the outer panel, all its pivots at once
-                    const int nt = (rem + UT - 1) / UT;
-                    k_big_update<<<dim3(nt, nt, lv.nB), 256, 0, st>>>(a, lb, ob, OB, OB, 1 << 30, 0);
+                    launch_wide_update(a, lb, lv.nB, ob, OB, rem, st);
                     ++nl;
                 }
             }
@@ -246,7 +306,7 @@ int64_t enqueue_solve(b2_solver* s, int ph, bool forward, cudaStream_t st) {
                     ++nl;
                 }
             } else {
-                k_bs_bwd_init<<<dim3((lv.maxwC + 255) / 256, lv.nC), 256, 0, st>>>(bs, lc);
+                k_bs_bwd_init<<<dim3((lv.maxwC + 7) / 8, lv.nC), 256, 0, st>>>(bs, lc);
                 ++nl;
                 for (int b = nblk - 1; b >= 0; --b) {
                     const int cols = std::max(1, b * BS);
@@ -477,7 +537,10 @@ void build_schedule(b2_solver* s) {
                         lv.maxrB = std::max(lv.maxrB, cf - cw);
                     }
                 }
-                if (f > wmax) { lv.maxfC = std::max(lv.maxfC, f); lv.maxwC = std::max(lv.maxwC, w); allC.push_back(sn); P.maxwAllC = std::max(P.maxwAllC, w); }
+                if (f > wmax) {
+                    lv.maxfC = std::max(lv.maxfC, f); lv.maxwC = std::max(lv.maxwC, w);
+                    if (f <= smax || !big_v2_enabled()) { allC.push_back(sn); P.maxwAllC = std::max(P.maxwAllC, w); }   // (B fronts invert in k_big_diag128)
+                }
             }
             auto level_launch = [&](const std::vector<int32_t>& X, int nw) {
                 std::vector<std::vector<std::vector<int32_t>>> ctas;
@@ -995,6 +1058,10 @@ void enqueue_dense_factor(b2d_solver* s, cudaStream_t st) {
     cudaMemsetAsync(s->counters.p, 0, 4 * sizeof(int32_t), st);
     k_copy_lower<<<dim3(std::max(1, std::min(8, (N + 255) / 256)), N), 256, 0, st>>>(N, s->lda, s->A_d, s->fact.p);
     constexpr int OB = 128;
+    if (big_v2_enabled()) {
+        for (int ob = 0; ob < N; ob += DB) launch_big_step(a, s->list.p, 1, ob, N, s->linv.p, s->linv_off.p, st, nullptr);
+        return;
+    }
     for (int ob = 0; ob < N; ob += OB) {
         for (int kb = ob; kb < std::min(ob + OB, N); kb += BIG_NB) {
             const int step = kb / BIG_NB;
@@ -1004,15 +1071,11 @@ void enqueue_dense_factor(b2d_solver* s, cudaStream_t st) {
             k_big_panel<<<dim3((rem + BIG_ROWS - 1) / BIG_ROWS, 1), BIG_ROWS, 0, st>>>(a, s->list.p, step);
             const int ncols = ob + OB - (kb + BIG_NB);
             if (ncols > 0 || (N % BIG_NB)) {
-                const int nt = (rem + UT - 1) / UT;
-                k_big_update<<<dim3(nt, (ncols + BIG_NB + UT - 1) / UT, 1), 256, 0, st>>>(a, s->list.p, kb, BIG_NB, BIG_NB, BIG_NB + ncols, 1);
+                launch_narrow_update(a, s->list.p, 1, kb, ncols, rem, st);
             }
         }
-        const int rem = N - ob - 1;
-        if (rem > 0) {
-            const int nt = (rem + UT - 1) / UT;
-            k_big_update<<<dim3(nt, nt, 1), 256, 0, st>>>(a, s->list.p, ob, OB, OB, 1 << 30, 0);
-        }
+        const int rem = N - ob - OB;
+        if (rem > 0) launch_wide_update(a, s->list.p, 1, ob, OB, rem, st);
     }
     k_big_inv<<<dim3((N + BS - 1) / BS, 1), BS, (size_t)BS * (BS + 1) * sizeof(double), st>>>(s->desc.p, s->list.p, s->fact.p, s->linv.p, s->linv_off.p);
 }
@@ -1103,7 +1166,7 @@ int b2d_solve(b2d_solver* s, double* x_d, int32_t nrhs, void* stream) {
             const int rows = std::max(1, N - b * BS - 1);
             k_bs_fwd<<<dim3((rows + BSF_ROWS - 1) / BSF_ROWS, 1), 256, BS_SMEM, st>>>(bs, s->list.p, b);
         }
-        k_bs_bwd_init<<<dim3((N + 255) / 256, 1), 256, 0, st>>>(bs, s->list.p);
+        k_bs_bwd_init<<<dim3((N + 7) / 8, 1), 256, 0, st>>>(bs, s->list.p);
         for (int b = nblk - 1; b >= 0; --b) {
             const int cols = std::max(1, b * BS);
             k_bs_bwd<<<dim3((cols + BSB_COLS - 1) / BSB_COLS, 1), 256, BS_SMEM, st>>>(bs, s->list.p, b);
