@@ -1,4 +1,4 @@
-"""N>1 path on CPU: two `gloo` ranks run the subtree-sharded factor/solve PROTOCOL of madnlp.jl_b200/parallel.py
+"""N>1 path on CPU: two and four `gloo` ranks run the subtree-sharded factor/solve PROTOCOL of madnlp.jl_b200/parallel.py
 (local phase -> all-reduce of the exchange region -> replicated top tree -> ...) with the kernels' arithmetic replayed in
 numpy over the symbolic structure and buffer layout exported by the C ABI.  What this pins without a GPU: every rank
 derives the same partition, the exchange regions line up across ranks, each exchanged block/vector has exactly one
@@ -72,18 +72,19 @@ def _worker(rank, world, port, q):
 
 
 @pytest.mark.timeout(300)
-def test_two_rank_protocol_with_gloo():
+@pytest.mark.parametrize("world", [2, 4])
+def test_sharded_protocol_with_gloo(world):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29500 + (os.getpid() % 2000)
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    port = 29500 + (os.getpid() % 2000) + world
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
     for p in procs:
         p.join(240)
     assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
-    results = sorted(q.get(timeout=5) for _ in range(2))
+    results = sorted(q.get(timeout=5) for _ in range(world))
     for rank, neg, neg_true, res in results:
         assert neg == neg_true and neg_true > 0
         assert res < 1e-10
