@@ -25,12 +25,34 @@ constexpr int DB = 128;                   // outer block (== BS of the solve ker
 // column also the pivot row: per pivot the 16 owner threads publish it (one barrier), and every thread then needs just
 // 8 + 8 values (conflict-free: lanes read consecutive or identical addresses) for up to 64 FMAs.  Entries of already-eliminated rows/columns in a
 // thread's boundary sub-block keep receiving (meaningless) updates; they are never read again.
+// Pivot-to-pivot synchronisation is an mbarrier per buffer instead of __syncthreads: the 16 threads that own the NEXT
+// pivot column update it first, publish it and arrive; everybody else arrives as soon as the current column has been
+// read, so the rest of the rank-1 update overlaps the owners' critical path (wait -> rcp -> column -> publish).
+constexpr int DB_LDS = DB + 1;            // padded stage (transposed reads of the symmetric fill are conflict-free)
 struct Diag128Smem {
-    double Lc[DB * DB];                   // Lc[k*DB + i] = l(i,k) for i > k, 0 for i <= k
+    double Lc[DB * DB_LDS];               // stage[j*DB_LDS + i] on entry; then Lc[k*DB + i] = l(i,k) for i > k, 0 for i <= k
     double ubuf[2][DB];                   // pivot column (unscaled), double-buffered
     double xbuf[2][DB];                   // row k of the inverse
     double dd[DB];
+    unsigned long long bar[4];            // [0..1] phase F, [2..3] phase I
 };
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, int parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "MBAR_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra MBAR_DONE;\n"
+        "bra MBAR_WAIT;\n"
+        "MBAR_DONE:\n"
+        "}\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+}
 
 __global__ void __launch_bounds__(256, 1) k_big_diag128(FactorArgs a, const int32_t* __restrict__ list, int kb,
                                                         double* __restrict__ Linv, const int64_t* __restrict__ linv_off) {
@@ -49,17 +71,18 @@ __global__ void __launch_bounds__(256, 1) k_big_diag128(FactorArgs a, const int3
 #define DPROF() do {} while (0)
 #endif
     DPROF();
+    if (tid < 4) mbar_init(&sm.bar[tid], 256);
     // ---- stage the lower triangle (coalesced: i fastest), then pick the symmetric 8 x 8 register block out of it
-    double* stage = sm.Lc;                                         // stage[j*DB + i], i >= j
+    double* stage = sm.Lc;                                         // stage[j*DB_LDS + i], i >= j
     for (int e = tid; e < DB * DB; e += 256) {                     // all 64 copies of a thread in flight at once
         const int i = e & (DB - 1), j = e >> 7;
-        if (j <= i) cp_async8_zfill(stage + j * DB + i, Lp + (size_t)(kb + j) * f + kb + min(i, nb - 1), i < nb);
+        if (j <= i) cp_async8_zfill(stage + j * DB_LDS + i, Lp + (size_t)(kb + j) * f + kb + min(i, nb - 1), i < nb);
     }
     cp_async_commit_group();
     cp_async_wait_group_n<0>();
     __syncthreads();
     if (nb < DB) {                                                 // identity padding
-        if (tid < DB && tid >= nb) stage[tid * DB + tid] = 1.0;
+        if (tid < DB && tid >= nb) stage[tid * DB_LDS + tid] = 1.0;
         __syncthreads();
     }
     double A[8][8];
@@ -68,46 +91,62 @@ __global__ void __launch_bounds__(256, 1) k_big_diag128(FactorArgs a, const int3
 #pragma unroll
         for (int ib = 0; ib < 8; ++ib) {
             const int i = ty + 16 * ia, j = tx + 16 * ib;
-            A[ia][ib] = stage[min(i, j) * DB + max(i, j)];
+            A[ia][ib] = stage[min(i, j) * DB_LDS + max(i, j)];
         }
     __syncthreads();
     int nneg = 0, npert = 0;
     DPROF();
-    // ---- phase F: unblocked right-looking LDL^T, one barrier per pivot
+    // ---- phase F: unblocked right-looking LDL^T
+    if (tx == 0) {
+#pragma unroll
+        for (int ia = 0; ia < 8; ++ia) sm.ubuf[0][ty + 16 * ia] = A[ia][0];
+    }
+    mbar_arrive(&sm.bar[0]);
 #pragma unroll
     for (int kq = 0; kq < 8; ++kq) {
         for (int kk = 0; kk < 16; ++kk) {
             const int k = 16 * kq + kk;
             if (k >= nb) break;
-            double* ub = sm.ubuf[k & 1];
-            if (tx == kk) {                                        // owners of column k: rows ty + 16a
-#pragma unroll
-                for (int ia = 0; ia < 8; ++ia) ub[ty + 16 * ia] = A[ia][kq];
-            }
-            __syncthreads();
+            const double* ub = sm.ubuf[k & 1];
+            mbar_wait(&sm.bar[k & 1], (k >> 1) & 1);
             double dk = ub[k];
-            if (!(fabs(dk) >= a.eps)) { dk = (dk < 0.0) ? -a.eps : a.eps; ++npert; }
-            else if (dk < 0.0) ++nneg;
-            const double rk = fast_rcp_d(dk);
             double ur[8], uc[8];
 #pragma unroll
             for (int ia = 0; ia < 8; ++ia) ur[ia] = (ia >= kq) ? ub[ty + 16 * ia] : 0.0;
 #pragma unroll
             for (int ib = 0; ib < 8; ++ib) uc[ib] = (ib >= kq) ? ub[tx + 16 * ib] : 0.0;
+            const bool have_next = k + 1 < nb;
+            const bool own_next = tx == ((kk + 1) & 15);
+            if (have_next && !own_next) mbar_arrive(&sm.bar[(k + 1) & 1]);     // (this column has been read)
+            if (!(fabs(dk) >= a.eps)) { dk = (dk < 0.0) ? -a.eps : a.eps; ++npert; }
+            else if (dk < 0.0) ++nneg;
+            const double rk = fast_rcp_d(dk);
+            double li[8];
+#pragma unroll
+            for (int ia = 0; ia < 8; ++ia) li[ia] = -ur[ia] * rk;
+            // the two candidate next-pivot columns first (b-index kq, or kq+1 when kk == 15)
+#pragma unroll
+            for (int ib = kq; ib < min(kq + 2, 8); ++ib)
+#pragma unroll
+                for (int ia = 0; ia < 8; ++ia)
+                    if (ia >= kq) A[ia][ib] = fma(li[ia], uc[ib], A[ia][ib]);
+            if (have_next && own_next) {
+                double* un = sm.ubuf[(k + 1) & 1];
+#pragma unroll
+                for (int ia = 0; ia < 8; ++ia) un[ty + 16 * ia] = (kk == 15) ? A[ia][min(kq + 1, 7)] : A[ia][kq];
+                mbar_arrive(&sm.bar[(k + 1) & 1]);
+            }
             if (tx == kk) {
                 double* lc = sm.Lc + k * DB + ty;
 #pragma unroll
-                for (int ia = 0; ia < 8; ++ia) lc[16 * ia] = (ty + 16 * ia > k) ? ur[ia] * rk : 0.0;
+                for (int ia = 0; ia < 8; ++ia) lc[16 * ia] = (ty + 16 * ia > k) ? -li[ia] : 0.0;
                 if (ty == kk) sm.dd[k] = dk;
             }
 #pragma unroll
-            for (int ia = 0; ia < 8; ++ia) {
-                if (ia < kq) continue;
-                const double li = -ur[ia] * rk;
+            for (int ib = kq + 2; ib < 8; ++ib)
 #pragma unroll
-                for (int ib = 0; ib < 8; ++ib)
-                    if (ib >= kq) A[ia][ib] = fma(li, uc[ib], A[ia][ib]);
-            }
+                for (int ia = 0; ia < 8; ++ia)
+                    if (ia >= kq) A[ia][ib] = fma(li[ia], uc[ib], A[ia][ib]);
         }
     }
     if (tid == 0) {
@@ -132,26 +171,44 @@ __global__ void __launch_bounds__(256, 1) k_big_diag128(FactorArgs a, const int3
     for (int ia = 0; ia < 8; ++ia)
 #pragma unroll
         for (int ib = 0; ib < 8; ++ib) A[ia][ib] = (ty + 16 * ia == tx + 16 * ib) ? 1.0 : 0.0;
+    if (ty == 0) {
+#pragma unroll
+        for (int ib = 0; ib < 8; ++ib) sm.xbuf[0][tx + 16 * ib] = A[0][ib];
+    }
+    mbar_arrive(&sm.bar[2]);
 #pragma unroll
     for (int kq = 0; kq < 8; ++kq) {
         for (int kk = 0; kk < 16; ++kk) {
             const int k = 16 * kq + kk;
             if (k + 1 >= nb) break;                                // the last column has nothing below it
-            double* xb = sm.xbuf[k & 1];
-            if (ty == kk) {                                        // owners of row k: columns tx + 16b
-#pragma unroll
-                for (int ib = 0; ib < 8; ++ib) xb[tx + 16 * ib] = A[kq][ib];
-            }
-            __syncthreads();
+            const double* xb = sm.xbuf[k & 1];
+            mbar_wait(&sm.bar[2 + (k & 1)], (k >> 1) & 1);
             const double* lc = sm.Lc + k * DB + ty;
+            double li[8], xr[8];
 #pragma unroll
-            for (int ia = 0; ia < 8; ++ia) {
-                if (ia < kq) continue;
-                const double li = -lc[16 * ia];
+            for (int ia = 0; ia < 8; ++ia) li[ia] = (ia >= kq) ? -lc[16 * ia] : 0.0;
+#pragma unroll
+            for (int ib = 0; ib < 8; ++ib) xr[ib] = (ib <= kq) ? xb[tx + 16 * ib] : 0.0;
+            const bool have_next = k + 2 < nb;
+            const bool own_next = ty == ((kk + 1) & 15);
+            if (have_next && !own_next) mbar_arrive(&sm.bar[2 + ((k + 1) & 1)]);
+            // the two candidate next rows first (a-index kq, or kq+1 when kk == 15)
+#pragma unroll
+            for (int ia = kq; ia < min(kq + 2, 8); ++ia)
 #pragma unroll
                 for (int ib = 0; ib < 8; ++ib)
-                    if (ib <= kq) A[ia][ib] = fma(li, xb[tx + 16 * ib], A[ia][ib]);
+                    if (ib <= kq) A[ia][ib] = fma(li[ia], xr[ib], A[ia][ib]);
+            if (have_next && own_next) {
+                double* xn = sm.xbuf[(k + 1) & 1];
+#pragma unroll
+                for (int ib = 0; ib < 8; ++ib) xn[tx + 16 * ib] = (kk == 15) ? A[min(kq + 1, 7)][ib] : A[kq][ib];
+                mbar_arrive(&sm.bar[2 + ((k + 1) & 1)]);
             }
+#pragma unroll
+            for (int ia = kq + 2; ia < 8; ++ia)
+#pragma unroll
+                for (int ib = 0; ib < 8; ++ib)
+                    if (ib <= kq) A[ia][ib] = fma(li[ia], xr[ib], A[ia][ib]);
         }
     }
     DPROF();

@@ -1,12 +1,14 @@
 // Multi-CTA triangular solves for HBM-resident fronts (order > 64) and the dense solver.
 //
-// The pivot columns of a front are cut into blocks of BS = 128.  After the factorisation, k_big_inv inverts every
-// 128 x 128 unit-lower diagonal block once (in shared memory).  A sweep is then one launch per block:
-//   forward  block b: every CTA forms y_b = Linv_b * rhs_b redundantly (128x128 GEMV out of shared memory), CTA 0 stores it,
-//                     and each CTA updates its own 64 rows below:  y_i -= sum_k L(i,k) y_b(k)      (coalesced stream of L)
-//   backward block b: every CTA forms x_b = Linv_b' * t_b, CTA 0 stores it, each CTA updates its 256 earlier pivot
-//                     columns:  t_j -= sum_i L(b_i, j) x_b(i)      (right-looking: no cross-CTA reduction, deterministic)
-// so a sweep over N = 4096 is 32 launches of ~60 CTAs instead of one CTA streaming 64 MB alone.
+// The pivot columns of a front are cut into blocks of BS = 128 whose unit-lower diagonal blocks are available INVERTED
+// (k_big_diag128 for the big fronts, k_big_inv for the shared-memory class).  A sweep is one launch per block:
+//   forward  block b: every CTA reads y_b (128 values) and updates its own 128 rows below:
+//                     y_i -= sum_k L(i,k) y_b(k)  (coalesced stream of the panel); the CTA that owns the rows of block
+//                     b+1 then forms y_{b+1} = Linv_{b+1} * rhs_{b+1} for the next launch.
+//   backward block b: every CTA reads x_b and updates one earlier block of 128 pivot columns:
+//                     t_j -= sum_i L(b_i, j) x_b(i)  (one warp per column: right-looking, deterministic, no cross-CTA
+//                     reduction); the CTA of block b-1 then forms x_{b-1} = Linv_{b-1}' * t_{b-1}.
+// so the 128 KB inverse block is read by ONE CTA per launch and the sweep is bounded by streaming L once.
 #pragma once
 #include "solve_kernels.cuh"
 
@@ -76,9 +78,71 @@ __global__ void __launch_bounds__(1024) k_bs_fwd_init(BigSolveArgs b, const int3
     }
 }
 
-constexpr int BSF_ROWS = 64;     // rows per CTA in the forward update (x 4 k-groups = 256 threads)
-__global__ void __launch_bounds__(256) k_bs_fwd(BigSolveArgs b, const int32_t* __restrict__ list, int blk) {
-    extern __shared__ double sm[];                 // Linv block [BS][BS+1] | rhs[BS] | y[BS] | part[4][64]
+// Every launch of a sweep is a link of a dependent chain, so what matters is its LATENCY: 1024 threads per CTA, every
+// thread issues all of its (<= 16) loads before the first use -- one memory round trip per phase.
+constexpr int BS_NT = 1024;
+constexpr int BS_KG = BS_NT / BS;         // 8 k-groups of 16 columns
+
+// ---- y = Linv_b * rhs (forward) or x = Linv_b' * t (backward) of one diagonal block; sm >= (1 + BS_KG) * BS doubles
+__device__ __forceinline__ void bs_block_apply(const double* __restrict__ Li, const double* rhs, int nb, bool transpose, double* out,
+                                               double* sm, int tid) {
+    __syncthreads();
+    if (tid < BS) sm[tid] = (tid < nb) ? rhs[tid] : 0.0;
+    __syncthreads();
+    if (!transpose) {
+        const int r = tid & (BS - 1), g = tid >> 7;               // BS_KG groups of 16 columns; Linv(r, c) = 0 for c > r
+        double v[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) { const int c = g * 16 + k; v[k] = (c <= r) ? Li[(size_t)c * BS + r] : 0.0; }
+        double acc = 0.0;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) acc = fma(v[k], sm[g * 16 + k], acc);
+        sm[BS + tid] = acc;
+        __syncthreads();
+        if (tid < nb) {
+            double tot = 0.0;
+#pragma unroll
+            for (int q = 0; q < BS_KG; ++q) tot += sm[BS + q * BS + tid];
+            out[tid] = tot;
+        }
+    } else {
+        const int warp = tid >> 5, lane = tid & 31;               // 32 warps x 4 columns; a column is contiguous over the rows
+        double v[4][4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int c = warp * 4 + q, r = lane + 32 * u;
+                v[q][u] = (r >= c) ? Li[(size_t)c * BS + r] : 0.0;
+            }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            double acc = 0.0;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) acc = fma(v[q][u], sm[lane + 32 * u], acc);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (lane == 0 && warp * 4 + q < nb) out[warp * 4 + q] = acc;
+        }
+    }
+}
+
+// ---- head of a sweep: block `blk` of every front (blk < 0: each front's own LAST block); one CTA per front
+__global__ void __launch_bounds__(BS_NT) k_bs_head(BigSolveArgs b, const int32_t* __restrict__ list, int blk, int transpose) {
+    __shared__ double sm[(1 + BS_KG) * BS];
+    const SolveArgs& a = b.s;
+    const int s = list[blockIdx.x];
+    const FrontDesc d = a.desc[s];
+    if (blk < 0) blk = (d.w - 1) / BS;
+    const int kb = blk * BS;
+    if (kb >= d.w) return;
+    const int nb = min(BS, d.w - kb);
+    bs_block_apply(b.Linv + b.linv_off[s] + (size_t)blk * BS * BS, a.xp + d.col0 + kb, nb, transpose != 0, b.side + d.col0 + kb, sm, threadIdx.x);
+}
+
+constexpr int BSF_ROWS = 128;    // rows per CTA in the forward update (x BS_KG k-groups = 1024 threads)
+__global__ void __launch_bounds__(BS_NT) k_bs_fwd(BigSolveArgs b, const int32_t* __restrict__ list, int blk) {
+    __shared__ double sm[(1 + BS_KG) * BS];                        // y_b | partial sums
     const SolveArgs& a = b.s;
     const int s = list[blockIdx.y];
     const FrontDesc d = a.desc[s];
@@ -86,33 +150,32 @@ __global__ void __launch_bounds__(256) k_bs_fwd(BigSolveArgs b, const int32_t* _
     if (kb >= d.w) return;
     const int nb = min(BS, d.w - kb), f = d.f, tid = threadIdx.x;
     const int row0 = kb + nb + blockIdx.x * BSF_ROWS;
-    if (row0 >= f && blockIdx.x > 0) return;
-    double* T = sm; double* rhs = T + BS * (BS + 1); double* yk = rhs + BS; double* part = yk + BS;
-    const double* Li = b.Linv + b.linv_off[s] + (size_t)blk * BS * BS;
-    for (int e = tid; e < BS * BS; e += 256) { const int c = e / BS, i = e - c * BS; T[i * (BS + 1) + c] = Li[e]; }
-    if (tid < BS) rhs[tid] = (tid < nb) ? a.xp[d.col0 + kb + tid] : 0.0;
-    __syncthreads();
-    if (tid < BS) {
-        double v = 0.0;
-        for (int c = 0; c <= tid; ++c) v = fma(T[tid * (BS + 1) + c], rhs[c], v);
-        yk[tid] = v;
-        if (blockIdx.x == 0 && tid < nb) b.side[d.col0 + kb + tid] = v;
-    }
-    __syncthreads();
-    const int ir = tid & (BSF_ROWS - 1), kg = tid / BSF_ROWS;       // 4 groups of 32 pivots
+    if (row0 >= f) return;
+    if (tid < BS) sm[tid] = (tid < nb) ? b.side[d.col0 + kb + tid] : 0.0;
+    const int ir = tid & (BSF_ROWS - 1), g = tid >> 7;
     const int i = row0 + ir;
-    double acc = 0.0;
-    if (i < f) {
-        const double* col = a.L + d.lp_off + (size_t)(kb + kg * 32) * f + i;
-#pragma unroll 8
-        for (int k = 0; k < 32; ++k) if (kg * 32 + k < nb) acc = fma(col[(size_t)k * f], yk[kg * 32 + k], acc);
+    double v[16];
+    {
+        const double* col = a.L + d.lp_off + (size_t)(kb + g * 16) * f + min(i, f - 1);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) v[k] = (i < f && g * 16 + k < nb) ? col[(size_t)k * f] : 0.0;
     }
-    part[kg * BSF_ROWS + ir] = acc;
     __syncthreads();
-    if (kg == 0 && i < f) {
-        const double tot = part[ir] + part[BSF_ROWS + ir] + part[2 * BSF_ROWS + ir] + part[3 * BSF_ROWS + ir];
+    double acc = 0.0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) acc = fma(v[k], sm[g * 16 + k], acc);
+    sm[BS + tid] = acc;
+    __syncthreads();
+    if (g == 0 && i < f) {
+        double tot = 0.0;
+#pragma unroll
+        for (int q = 0; q < BS_KG; ++q) tot += sm[BS + q * BS + ir];
         *yptr(a, d, a.cbv_off[s], i) -= tot;
     }
+    // the rows of this CTA are the pivots of the next block: its right-hand side is final now
+    if (blockIdx.x == 0 && kb + BS < d.w)
+        bs_block_apply(b.Linv + b.linv_off[s] + (size_t)(blk + 1) * BS * BS, a.xp + d.col0 + kb + BS, min(BS, d.w - kb - BS), false,
+                       b.side + d.col0 + kb + BS, sm, tid);
 }
 
 // ---- backward init: t_j = y_j / d_j - sum_{i >= w} L(i,j) x(rows_i)  (y_j parked in `side` by the forward sweep);
@@ -142,37 +205,39 @@ __global__ void __launch_bounds__(256) k_bs_bwd_init(BigSolveArgs b, const int32
     if (lane == 0) a.xp[d.col0 + j] = b.side[d.col0 + j] / a.dvec[d.col0 + j] - acc;
 }
 
-constexpr int BSB_COLS = 256;    // earlier pivot columns per CTA in the backward update
-__global__ void __launch_bounds__(256) k_bs_bwd(BigSolveArgs b, const int32_t* __restrict__ list, int blk) {
-    extern __shared__ double sm[];                 // Linv block [BS][BS+1] | t[BS] | x[BS]
+constexpr int BSB_COLS = BS;     // earlier pivot columns per CTA in the backward update: exactly one block
+__global__ void __launch_bounds__(BS_NT) k_bs_bwd(BigSolveArgs b, const int32_t* __restrict__ list, int blk) {
+    __shared__ double sm[(1 + BS_KG) * BS];                        // x_b
     const SolveArgs& a = b.s;
     const int s = list[blockIdx.y];
     const FrontDesc d = a.desc[s];
     const int kb = blk * BS;
     if (kb >= d.w) return;
     const int nb = min(BS, d.w - kb), f = d.f, tid = threadIdx.x;
-    const int col0 = blockIdx.x * BSB_COLS;
-    if (col0 >= kb && blockIdx.x > 0) return;
-    double* T = sm; double* tk = T + BS * (BS + 1); double* xk = tk + BS;
-    const double* Li = b.Linv + b.linv_off[s] + (size_t)blk * BS * BS;
-    for (int e = tid; e < BS * BS; e += 256) { const int c = e / BS, i = e - c * BS; T[i * (BS + 1) + c] = Li[e]; }
-    if (tid < BS) tk[tid] = (tid < nb) ? a.xp[d.col0 + kb + tid] : 0.0;
-    __syncthreads();
-    if (tid < BS) {                                // x = Linv' * t : x_t = sum_{c >= t} Linv(c,t) t_c
-        double v = 0.0;
-        for (int c = tid; c < nb; ++c) v = fma(T[c * (BS + 1) + tid], tk[c], v);
-        xk[tid] = v;
-        if (blockIdx.x == 0 && tid < nb) b.side[d.col0 + kb + tid] = v;
+    const int t = blockIdx.x;                                      // block of columns served by this CTA, t < blk
+    if (t >= blk) return;
+    if (tid < BS) sm[tid] = (tid < nb) ? b.side[d.col0 + kb + tid] : 0.0;
+    const int warp = tid >> 5, lane = tid & 31;                   // 32 warps x 4 columns: rows [kb, kb+nb) of a column are contiguous
+    double v[4][4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const double* col = a.L + d.lp_off + (size_t)(t * BS + warp * 4 + q) * f + kb;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[q][u] = (lane + 32 * u < nb) ? col[lane + 32 * u] : 0.0;
     }
     __syncthreads();
-    const int j = col0 + tid;
-    if (j < kb) {
-        const double* col = a.L + d.lp_off + (size_t)j * f + kb;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
         double acc = 0.0;
-#pragma unroll 8
-        for (int i = 0; i < BS; ++i) if (i < nb) acc = fma(col[i], xk[i], acc);
-        a.xp[d.col0 + j] -= acc;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) acc = fma(v[q][u], sm[lane + 32 * u], acc);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) a.xp[d.col0 + t * BS + warp * 4 + q] -= acc;
     }
+    // block blk-1 has received its last update: form x_{blk-1} for the next launch
+    if (t == blk - 1)
+        bs_block_apply(b.Linv + b.linv_off[s] + (size_t)t * BS * BS, a.xp + d.col0 + t * BS, BS, true, b.side + d.col0 + t * BS, sm, tid);
 }
 
 // ---- end of a front's backward sweep: solved pivots from `side` back into xp; grid (ceil(w/256), nfronts)

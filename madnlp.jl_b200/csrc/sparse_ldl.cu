@@ -167,7 +167,6 @@ BigSolveArgs big_solve_args(b2_solver* s) {
     b.side = s->d_side.p;
     return b;
 }
-constexpr size_t BS_SMEM = (size_t)(BS * (BS + 1) + 2 * BS + 4 * BSF_ROWS) * sizeof(double);
 
 inline size_t smem_front(int f) { return (size_t)f * f * sizeof(double); }
 
@@ -299,18 +298,19 @@ int64_t enqueue_solve(b2_solver* s, int ph, bool forward, cudaStream_t st) {
             const int nblk = (lv.maxwC + BS - 1) / BS;
             if (forward) {
                 k_bs_fwd_init<<<lv.nC, 1024, 0, st>>>(bs, lc);
-                ++nl;
+                k_bs_head<<<lv.nC, BS_NT, 0, st>>>(bs, lc, 0, 0);
+                nl += 2;
                 for (int b = 0; b < nblk; ++b) {
                     const int rows = std::max(1, lv.maxfC - b * BS - 1);
-                    k_bs_fwd<<<dim3((rows + BSF_ROWS - 1) / BSF_ROWS, lv.nC), 256, BS_SMEM, st>>>(bs, lc, b);
+                    k_bs_fwd<<<dim3((rows + BSF_ROWS - 1) / BSF_ROWS, lv.nC), BS_NT, 0, st>>>(bs, lc, b);
                     ++nl;
                 }
             } else {
                 k_bs_bwd_init<<<dim3((lv.maxwC + 7) / 8, lv.nC), 256, 0, st>>>(bs, lc);
-                ++nl;
-                for (int b = nblk - 1; b >= 0; --b) {
-                    const int cols = std::max(1, b * BS);
-                    k_bs_bwd<<<dim3((cols + BSB_COLS - 1) / BSB_COLS, lv.nC), 256, BS_SMEM, st>>>(bs, lc, b);
+                k_bs_head<<<lv.nC, BS_NT, 0, st>>>(bs, lc, -1, 1);
+                nl += 2;
+                for (int b = nblk - 1; b >= 1; --b) {
+                    k_bs_bwd<<<dim3(b, lv.nC), BS_NT, 0, st>>>(bs, lc, b);
                     ++nl;
                 }
                 k_bs_bwd_finish<<<dim3((lv.maxwC + 255) / 256, lv.nC), 256, 0, st>>>(bs, lc);
@@ -335,8 +335,6 @@ int set_smem_attrs() {
     B2_CUDA(cudaFuncSetAttribute(k_fwd_dep, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     B2_CUDA(cudaFuncSetAttribute(k_bwd_dep, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     B2_CUDA(cudaFuncSetAttribute(k_big_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    B2_CUDA(cudaFuncSetAttribute(k_bs_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    B2_CUDA(cudaFuncSetAttribute(k_bs_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     return B2_OK;
 }
 
@@ -1162,15 +1160,14 @@ int b2d_solve(b2d_solver* s, double* x_d, int32_t nrhs, void* stream) {
         a.desc = s->desc.p; a.rows = nullptr; a.child_idx = nullptr; a.rel = nullptr; a.cbv_off = s->linv_off.p;   // single zero offset
         a.L = s->fact.p; a.Lt = nullptr; a.dvec = s->dvec.p; a.xp = x_d + (size_t)c * N; a.cbv = nullptr;
         bs.Linv = s->linv.p; bs.linv_off = s->linv_off.p; bs.side = s->side.p;
+        k_bs_head<<<1, BS_NT, 0, st>>>(bs, s->list.p, 0, 0);
         for (int b = 0; b < nblk; ++b) {
             const int rows = std::max(1, N - b * BS - 1);
-            k_bs_fwd<<<dim3((rows + BSF_ROWS - 1) / BSF_ROWS, 1), 256, BS_SMEM, st>>>(bs, s->list.p, b);
+            k_bs_fwd<<<dim3((rows + BSF_ROWS - 1) / BSF_ROWS, 1), BS_NT, 0, st>>>(bs, s->list.p, b);
         }
         k_bs_bwd_init<<<dim3((N + 7) / 8, 1), 256, 0, st>>>(bs, s->list.p);
-        for (int b = nblk - 1; b >= 0; --b) {
-            const int cols = std::max(1, b * BS);
-            k_bs_bwd<<<dim3((cols + BSB_COLS - 1) / BSB_COLS, 1), 256, BS_SMEM, st>>>(bs, s->list.p, b);
-        }
+        k_bs_head<<<1, BS_NT, 0, st>>>(bs, s->list.p, -1, 1);
+        for (int b = nblk - 1; b >= 1; --b) k_bs_bwd<<<dim3(b, 1), BS_NT, 0, st>>>(bs, s->list.p, b);
         k_bs_bwd_finish<<<dim3((N + 255) / 256, 1), 256, 0, st>>>(bs, s->list.p);
     }
     B2_CUDA(cudaGetLastError());
