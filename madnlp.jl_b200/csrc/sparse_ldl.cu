@@ -263,15 +263,28 @@ int64_t enqueue_solve(b2_solver* s, int ph, bool forward, cudaStream_t st) {
     const int32_t* sched = s->d_sched.p;
     int64_t nl = 0;
     const Phase& P = s->phase[ph];
+    // level kernels are launched programmatically dependent on their predecessor (see warp_kernels.cuh: pdl_wait)
+    static const bool pdl = [] { const char* e = getenv("B2_PDL"); return !(e && e[0] == '0'); }();
+    cudaLaunchAttribute pattr[1];
+    pattr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    pattr[0].val.programmaticStreamSerializationAllowed = 1;
+    auto cfg_of = [&](int grid, int block, size_t sm) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = sm; cfg.stream = st;
+        cfg.attrs = pattr; cfg.numAttrs = pdl ? 1 : 0;
+        return cfg;
+    };
     auto warp_launch = [&](const WarpLaunch& L) {
+        const ChildRec* cr = s->d_childrec.p;
+        const WarpSched wsched = warp_sched(s, L);
         if (L.nw == 1) {
-            const size_t sm = (size_t)FW_WARPS * SolveSmem<1>::doubles * sizeof(double);
-            if (forward) k_fwd_warp2<1><<<L.n_cta, FW_WARPS * 32, sm, st>>>(a, s->d_childrec.p, warp_sched(s, L));
-            else k_bwd_warp2<1><<<L.n_cta, FW_WARPS * 32, sm, st>>>(a, warp_sched(s, L));
+            cudaLaunchConfig_t cfg = cfg_of(L.n_cta, FW_WARPS * 32, (size_t)FW_WARPS * SolveSmem<1>::doubles * sizeof(double));
+            if (forward) cudaLaunchKernelEx(&cfg, k_fwd_warp2<1>, a, cr, wsched);
+            else cudaLaunchKernelEx(&cfg, k_bwd_warp2<1>, a, wsched);
         } else {
-            const size_t sm = (size_t)SolveSmem<2>::doubles * sizeof(double);
-            if (forward) k_fwd_warp2<2><<<L.n_cta, 64, sm, st>>>(a, s->d_childrec.p, warp_sched(s, L));
-            else k_bwd_warp2<2><<<L.n_cta, 64, sm, st>>>(a, warp_sched(s, L));
+            cudaLaunchConfig_t cfg = cfg_of(L.n_cta, 64, (size_t)SolveSmem<2>::doubles * sizeof(double));
+            if (forward) cudaLaunchKernelEx(&cfg, k_fwd_warp2<2>, a, cr, wsched);
+            else cudaLaunchKernelEx(&cfg, k_bwd_warp2<2>, a, wsched);
         }
         ++nl;
     };

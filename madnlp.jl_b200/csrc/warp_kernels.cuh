@@ -266,6 +266,12 @@ __global__ void __launch_bounds__(TeamsPerCta<NW>::value * NW * 32) k_factor_war
 }
 
 // ------------------------------------------------------------------------------------------------ solves
+// Programmatic dependent launch: a level's kernel is launched while the previous level still runs.  Everything that is
+// CONSTANT during a solve (descriptors, index lists, the factor panels) is fetched before pdl_wait(); only the values the
+// previous levels produce (xp, cbv) are read after it.  Both calls are no-ops for a launch without the attribute.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // A front's solve is three memory round trips, whatever its number of children or pivots:
 //   (1) descriptor;  (2) child records + the whole panel (cp.async into shared memory, in flight while (3) runs) + own
 //   right-hand side;  (3) every child's relative indices and contribution vector at once.
@@ -293,8 +299,7 @@ __device__ __forceinline__ void front_fwd_team(const SolveArgs& a, const ChildRe
         const double* Lp = a.L + d.lp_off;
         for (int e = tid; e < f * w; e += TEAM) cp_async8(P + e, Lp + e);
     }
-    ys[tid] = (tid < w) ? a.xp[d.col0 + tid] : 0.0;
-    for (int c0 = 0; c0 < d.nchild; c0 += MAXC) {
+    for (int c0 = 0; c0 < max(d.nchild, 1); c0 += MAXC) {
         const int nc = min(MAXC, d.nchild - c0);
         if (tid < nc) {
             recs[tid] = childrec[d.child_off + c0 + tid];
@@ -303,11 +308,15 @@ __device__ __forceinline__ void front_fwd_team(const SolveArgs& a, const ChildRe
         team_sync<NW>(team);
         int tg[MAXC]; double vv[MAXC];
 #pragma unroll
-        for (int c = 0; c < MAXC; ++c) {
-            const bool on = c < nc && tid < recs[c].rc;
-            tg[c] = on ? a.rel[recs[c].rel_off + tid] : -1;
-            vv[c] = on ? (DEP ? __ldcg(a.cbv + recs[c].cbv_off + tid) : a.cbv[recs[c].cbv_off + tid]) : 0.0;
+        for (int c = 0; c < MAXC; ++c) tg[c] = (c < nc && tid < recs[c].rc) ? a.rel[recs[c].rel_off + tid] : -1;
+        if (c0 == 0) {                                  // (constant data is in flight; now the values of the levels below)
+            if (!DEP) pdl_wait();
+            ys[tid] = (tid < w) ? a.xp[d.col0 + tid] : 0.0;
         }
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c)
+            vv[c] = (tg[c] >= 0) ? (DEP ? __ldcg(a.cbv + recs[c].cbv_off + tid) : a.cbv[recs[c].cbv_off + tid]) : 0.0;
+        if (c0 == 0) team_sync<NW>(team);
 #pragma unroll
         for (int c = 0; c < MAXC; ++c) {               // ascending child order: deterministic sums
             if (c < nc) {
@@ -359,12 +368,14 @@ __device__ __forceinline__ void front_bwd_team(const SolveArgs& a, int s, double
         for (int e = tid; e < f * w; e += TEAM) cp_async8(P + e, Lt + e);
     }
     const int32_t* rows = a.rows + d.rows_off + w;
+    const int myrow = (tid < r) ? rows[tid] : 0;
+    const double dinv = (tid < w) ? fast_rcp(a.dvec[d.col0 + tid]) : 0.0;
     if (DEP) {      // all ancestors are final once the parent is
         if (tid == 0) { const int p = parent[s]; if (p >= 0) flag_wait(done + p, err); }
         team_sync<NW>(team);
-    }
-    if (tid < r) xs[tid] = DEP ? __ldcg(a.xp + rows[tid]) : a.xp[rows[tid]];
-    double t = (tid < w) ? a.xp[d.col0 + tid] * fast_rcp(a.dvec[d.col0 + tid]) : 0.0;
+    } else pdl_wait();
+    if (tid < r) xs[tid] = DEP ? __ldcg(a.xp + myrow) : a.xp[myrow];
+    double t = (tid < w) ? a.xp[d.col0 + tid] * dinv : 0.0;
     cp_async_wait_all();
     team_sync<NW>(team);
     {   // t_j -= sum_{i >= w} L(i,j) x_i : no recurrence
@@ -408,12 +419,14 @@ __global__ void __launch_bounds__(TeamsPerCta<NW>::value * NW * 32) k_fwd_warp2(
     double (*sm)[SolveSmem<NW>::doubles] = (double (*)[SolveSmem<NW>::doubles])smd;
     constexpr int NTEAM = TeamsPerCta<NW>::value;
     const int team = threadIdx.x / (32 * NW), tid = threadIdx.x % (32 * NW);
+    pdl_trigger();
     const int s0 = ws.cta_ptr[blockIdx.x], s1 = ws.cta_ptr[blockIdx.x + 1];
     for (int st = s0; st < s1; ++st) {
         const int off = ws.stage_off[st], cnt = ws.stage_cnt[st];
         for (int q = team; q < cnt; q += NTEAM) front_fwd_team<NW>(a, childrec, ws.list[off + q], sm[team], tid, team);
         if (s1 - s0 > 1) __syncthreads();
     }
+    pdl_wait();                                         // (idle teams too: this grid's completion must imply its predecessor's)
 }
 
 template <int NW>
@@ -422,12 +435,14 @@ __global__ void __launch_bounds__(TeamsPerCta<NW>::value * NW * 32) k_bwd_warp2(
     double (*sm)[SolveSmem<NW>::doubles] = (double (*)[SolveSmem<NW>::doubles])smd;
     constexpr int NTEAM = TeamsPerCta<NW>::value;
     const int team = threadIdx.x / (32 * NW), tid = threadIdx.x % (32 * NW);
+    pdl_trigger();
     const int s0 = ws.cta_ptr[blockIdx.x], s1 = ws.cta_ptr[blockIdx.x + 1];
     for (int st = s1 - 1; st >= s0; --st) {
         const int off = ws.stage_off[st], cnt = ws.stage_cnt[st];
         for (int q = team; q < cnt; q += NTEAM) front_bwd_team<NW>(a, ws.list[off + q], sm[team], tid, team);
         if (s1 - s0 > 1) __syncthreads();
     }
+    pdl_wait();
 }
 
 
