@@ -106,6 +106,11 @@ int b2_factorize(b2_solver* s, void* stream);
 /* (num_pos, num_zero, num_neg) in the reference's code order (src/IPM/solver.jl:626);
  * synchronises `stream`.  Perturbed pivots are reported as zeros (cf. mumps.jl:248-250). */
 int b2_inertia(b2_solver* s, int64_t* num_pos, int64_t* num_zero, int64_t* num_neg, void* stream);
+/* the same read split in two so that a caller can queue more work behind the factorisation before it blocks:
+ * b2_inertia_enqueue() queues the 32-byte D2H copy on `stream`; after the caller has synchronised that stream,
+ * b2_inertia_fetch() returns the counts without touching the device.  (b2_inertia == enqueue + synchronise + fetch.) */
+int b2_inertia_enqueue(b2_solver* s, void* stream);
+int b2_inertia_fetch(b2_solver* s, int64_t* num_pos, int64_t* num_zero, int64_t* num_neg);
 /* in-place x <- K^{-1} x, nrhs columns of length n (ld = n); asynchronous on `stream` */
 int b2_solve(b2_solver* s, double* x_d, int32_t nrhs, void* stream);
 /* raise robustness after a failed refinement (improve!, linearsolvers.jl / ma97.jl:103-111);
@@ -158,6 +163,8 @@ int b2d_create(int32_t N, int32_t lda, const double* A_d, const b2_options* opt,
 int b2d_destroy(b2d_solver* s);
 int b2d_factorize(b2d_solver* s, void* stream);
 int b2d_inertia(b2d_solver* s, int64_t* num_pos, int64_t* num_zero, int64_t* num_neg, void* stream);
+int b2d_inertia_enqueue(b2d_solver* s, void* stream);
+int b2d_inertia_fetch(b2d_solver* s, int64_t* num_pos, int64_t* num_zero, int64_t* num_neg);
 int b2d_solve(b2d_solver* s, double* x_d, int32_t nrhs, void* stream);
 
 /* ------------------------------------------------------------------ assembly: COO -> CSC */

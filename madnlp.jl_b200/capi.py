@@ -88,6 +88,8 @@ PROTOTYPES = {
     "b2_set_values_ptr": (C.c_int, [_p, _p]),
     "b2_factorize": (C.c_int, [_p, _p]),
     "b2_inertia": (C.c_int, [_p, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64), _p]),
+    "b2_inertia_enqueue": (C.c_int, [_p, _p]),
+    "b2_inertia_fetch": (C.c_int, [_p, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64)]),
     "b2_solve": (C.c_int, [_p, _p, _i32, _p]),
     "b2_improve": (C.c_int, [_p, C.POINTER(_i32)]),
     "b2_get_stats": (C.c_int, [_p, C.POINTER(Stats)]),
@@ -111,6 +113,8 @@ PROTOTYPES = {
     "b2d_destroy": (C.c_int, [_p]),
     "b2d_factorize": (C.c_int, [_p, _p]),
     "b2d_inertia": (C.c_int, [_p, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64), _p]),
+    "b2d_inertia_enqueue": (C.c_int, [_p, _p]),
+    "b2d_inertia_fetch": (C.c_int, [_p, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64)]),
     "b2d_solve": (C.c_int, [_p, _p, _i32, _p]),
     "b2d_gemv_n": (C.c_int, [_i32, _i32, _i32, _p, _p, _p, _f64, _f64, _p]),
     "b2d_gemv_t": (C.c_int, [_i32, _i32, _i32, _p, _p, _p, _f64, _f64, _p]),

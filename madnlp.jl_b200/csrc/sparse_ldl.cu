@@ -829,11 +829,14 @@ int b2_factorize(b2_solver* s, void* stream) {
     return B2_OK;
 }
 
-int b2_inertia(b2_solver* s, int64_t* num_pos, int64_t* num_zero, int64_t* num_neg, void* stream) {
+int b2_inertia_enqueue(b2_solver* s, void* stream) {
     if (!s || s->symbolic_only || !s->factorized) { set_error("b2_inertia: not factorized"); return B2_ERR_FACTORIZATION; }
-    cudaStream_t st = as_stream(stream);
-    B2_CUDA(cudaMemcpyAsync(s->h_counters, s->d_counters.p, 8 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    B2_CUDA(cudaStreamSynchronize(st));
+    B2_CUDA(cudaMemcpyAsync(s->h_counters, s->d_counters.p, 8 * sizeof(int32_t), cudaMemcpyDeviceToHost, as_stream(stream)));
+    return B2_OK;
+}
+
+int b2_inertia_fetch(b2_solver* s, int64_t* num_pos, int64_t* num_zero, int64_t* num_neg) {
+    if (!s || s->symbolic_only || !s->factorized) { set_error("b2_inertia: not factorized"); return B2_ERR_FACTORIZATION; }
     if (s->h_counters[4]) { set_error("b2: dependency wait timed out inside the single-launch schedule"); return B2_ERR_FACTORIZATION; }
     // single-part: everything is in the "local" phase.  Multi-part: this is only this rank's view; the host layer
     // all-reduces b2_inertia_parts() instead.
@@ -843,6 +846,13 @@ int b2_inertia(b2_solver* s, int64_t* num_pos, int64_t* num_zero, int64_t* num_n
     if (num_zero) *num_zero = zero;
     if (num_pos) *num_pos = (int64_t)s->S.n - neg - zero;
     return B2_OK;
+}
+
+int b2_inertia(b2_solver* s, int64_t* num_pos, int64_t* num_zero, int64_t* num_neg, void* stream) {
+    int rc = b2_inertia_enqueue(s, stream);
+    if (rc != B2_OK) return rc;
+    B2_CUDA(cudaStreamSynchronize(as_stream(stream)));
+    return b2_inertia_fetch(s, num_pos, num_zero, num_neg);
 }
 
 int b2_inertia_parts(b2_solver* s, int64_t* local_neg, int64_t* local_zero, int64_t* top_neg, int64_t* top_zero, void* stream) {
@@ -1149,16 +1159,26 @@ int b2d_factorize(b2d_solver* s, void* stream) {
     return B2_OK;
 }
 
-int b2d_inertia(b2d_solver* s, int64_t* num_pos, int64_t* num_zero, int64_t* num_neg, void* stream) {
+int b2d_inertia_enqueue(b2d_solver* s, void* stream) {
     if (!s || !s->factorized) { set_error("b2d_inertia: not factorized"); return B2_ERR_FACTORIZATION; }
-    cudaStream_t st = as_stream(stream);
-    B2_CUDA(cudaMemcpyAsync(s->h_counters, s->counters.p, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    B2_CUDA(cudaStreamSynchronize(st));
+    B2_CUDA(cudaMemcpyAsync(s->h_counters, s->counters.p, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, as_stream(stream)));
+    return B2_OK;
+}
+
+int b2d_inertia_fetch(b2d_solver* s, int64_t* num_pos, int64_t* num_zero, int64_t* num_neg) {
+    if (!s || !s->factorized) { set_error("b2d_inertia: not factorized"); return B2_ERR_FACTORIZATION; }
     const int64_t neg = s->h_counters[0], zero = s->h_counters[1];
     if (num_neg) *num_neg = neg;
     if (num_zero) *num_zero = zero;
     if (num_pos) *num_pos = (int64_t)s->N - neg - zero;
     return B2_OK;
+}
+
+int b2d_inertia(b2d_solver* s, int64_t* num_pos, int64_t* num_zero, int64_t* num_neg, void* stream) {
+    int rc = b2d_inertia_enqueue(s, stream);
+    if (rc != B2_OK) return rc;
+    B2_CUDA(cudaStreamSynchronize(as_stream(stream)));
+    return b2d_inertia_fetch(s, num_pos, num_zero, num_neg);
 }
 
 int b2d_solve(b2d_solver* s, double* x_d, int32_t nrhs, void* stream) {

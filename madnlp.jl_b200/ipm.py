@@ -36,9 +36,10 @@ class InertiaOptions:
 class IPMLinearAlgebra:
     """Owns the work vectors of MadNLPSolver that the hot path touches (d, p, _w4) and drives one iteration."""
 
-    def __init__(self, kkt, tol=1e-8, use_cuda_graph=True):
+    def __init__(self, kkt, tol=1e-8, use_cuda_graph=True, speculate=True):
         self.kkt = kkt
         self.use_cuda_graph = use_cuda_graph
+        self.speculate = speculate     # first refinement step queued before the inertia is known (see step())
         self._prologue_graph = None
         self.iterator = RichardsonIterator(kkt, tol=tol, use_cuda_graph=use_cuda_graph)
         self.d = UnreducedKKTVector.for_kkt(kkt)
@@ -106,8 +107,21 @@ class IPMLinearAlgebra:
         o = self.opt
         n_trial = 0
         del_w = del_c = del_w_prev = del_c_prev = 0.0
-        inertia = k.linear_solver.inertia()
-        ok = self._solve_refine_wrapper() if k.is_inertia_correct(*inertia) else False
+        ls = k.linear_solver
+        if self.speculate and hasattr(ls, "inertia_enqueue"):
+            # queue the inertia read AND the first refinement step behind the factorisation, block once for both
+            ls.inertia_enqueue()
+            self.iterator.start(self.d, self.p, self.w)
+            torch.cuda.current_stream().synchronize()
+            inertia = ls.inertia_fetch()
+            if k.is_inertia_correct(*inertia):
+                ok = self._solve_refine_wrapper()
+            else:
+                self.iterator.discard()
+                ok = False
+        else:
+            inertia = ls.inertia()
+            ok = self._solve_refine_wrapper() if k.is_inertia_correct(*inertia) else False
         while not ok:
             if n_trial == 0:
                 del_w = o.first_hessian_perturbation if self.del_w_last == 0.0 else max(

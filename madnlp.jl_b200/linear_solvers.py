@@ -92,6 +92,15 @@ class B200SparseSolver:
         check(lib.b2_inertia(self._h, C.byref(p), C.byref(z), C.byref(n), capi.stream_ptr(self.stream)))
         return (p.value, z.value, n.value)
 
+    def inertia_enqueue(self):
+        """queue the D2H copy of the pivot counts; `inertia_fetch` is valid once the stream has been synchronised"""
+        check(lib.b2_inertia_enqueue(self._h, capi.stream_ptr(self.stream)))
+
+    def inertia_fetch(self):
+        p, z, n = C.c_int64(), C.c_int64(), C.c_int64()
+        check(lib.b2_inertia_fetch(self._h, C.byref(p), C.byref(z), C.byref(n)))
+        return (p.value, z.value, n.value)
+
     def improve(self) -> bool:
         ch = C.c_int32(0)
         check(lib.b2_improve(self._h, C.byref(ch)))
@@ -160,6 +169,14 @@ class B200DenseSolver:
     def inertia(self):
         p, z, n = C.c_int64(), C.c_int64(), C.c_int64()
         check(lib.b2d_inertia(self._h, C.byref(p), C.byref(z), C.byref(n), capi.stream_ptr(self.stream)))
+        return (p.value, z.value, n.value)
+
+    def inertia_enqueue(self):
+        check(lib.b2d_inertia_enqueue(self._h, capi.stream_ptr(self.stream)))
+
+    def inertia_fetch(self):
+        p, z, n = C.c_int64(), C.c_int64(), C.c_int64()
+        check(lib.b2d_inertia_fetch(self._h, C.byref(p), C.byref(z), C.byref(n)))
         return (p.value, z.value, n.value)
 
     def improve(self) -> bool:

@@ -2,8 +2,8 @@
 
 Same loop, same stopping rule: residual_ratio = ||b - K x||_inf / (min(||x||_inf, 1e6 ||b||_inf) + ||b||_inf),
 stop when ratio < tol^(5/4) or after richardson_max_iter (=10) steps, accept when ratio < tol^(5/8)
-(backsolve.jl:25).  The two norms are reduced on the device and fetched with ONE 16-byte D2H copy per step
-(the reference syncs twice per step through `norm`).
+(backsolve.jl:25).  The norms are reduced on the device and fetched with ONE small D2H copy per step (the reference
+syncs twice per step through `norm`); ||b|| rides along with the first step's copy.
 """
 from __future__ import annotations
 
@@ -24,8 +24,9 @@ class RichardsonIterator:
         self.richardson_max_iter = richardson_max_iter
         self.richardson_tol = tol ** (5 / 4)
         self.richardson_acceptable_tol = tol ** (5 / 8)
-        self._norms = torch.zeros(2, dtype=torch.float64, device="cuda")
-        self._norms_h = torch.zeros(2, dtype=torch.float64).pin_memory()
+        self._norms = torch.zeros(3, dtype=torch.float64, device="cuda")        # ||w||, ||x||, ||b||
+        self._norms_h = torch.zeros(3, dtype=torch.float64).pin_memory()
+        self._started = False
         self.ir = 0
         self.residual_ratio = 0.0
 
@@ -41,7 +42,8 @@ class RichardsonIterator:
         check(lib.b2_norm_inf(n, ptr(w.values), ptr(self._norms[0:1]), stream))
         check(lib.b2_norm_inf(n, ptr(x.values), ptr(self._norms[1:2]), stream))
 
-    def _iteration(self, x, b, w):
+    def _launch_iteration(self, x, b, w):
+        """queue one refinement step and the D2H copy of its norms; no host synchronisation"""
         if not self.use_cuda_graph:
             self._body(x, b, w)
         else:
@@ -62,25 +64,41 @@ class RichardsonIterator:
             else:
                 g.replay()
         self._norms_h.copy_(self._norms, non_blocking=True)
+
+    def _fetch_norms(self):
         torch.cuda.current_stream().synchronize()
-        return float(self._norms_h[0]), float(self._norms_h[1])
+        return float(self._norms_h[0]), float(self._norms_h[1]), float(self._norms_h[2])
+
+    def start(self, x, b, w):
+        """Queue ||b||, x = 0, w = b and the FIRST refinement step without blocking.  A caller may issue this right behind
+        a factorisation, before it knows the inertia: the host then blocks once for both (IPMLinearAlgebra.step); if the
+        factorisation is rejected the queued step is simply discarded (solve_refine! always restarts from x = 0)."""
+        stream = capi.stream_ptr(getattr(self.kkt, "stream", None))
+        n = b.values.numel()
+        check(lib.b2_norm_inf(n, ptr(b.values), ptr(self._norms[2:3]), stream))
+        x.values.zero_()
+        check(lib.b2_copy(n, ptr(b.values), ptr(w.values), stream))
+        self._launch_iteration(x, b, w)
+        self._started = True
 
     def solve_refine(self, x, b, w) -> bool:
-        kkt = self.kkt
-        stream = capi.stream_ptr(getattr(kkt, "stream", None))
-        n = b.values.numel()
-        check(lib.b2_norm_inf(n, ptr(b.values), ptr(self._norms[0:1]), stream))
-        norm_b = float(self._norms[0].item())
-        residual_ratio = 0.0
-        x.values.zero_()
+        if not getattr(self, "_started", False):
+            self.start(x, b, w)
+        self._started = False
         self.ir = 0
-        if norm_b != 0.0:
-            check(lib.b2_copy(n, ptr(b.values), ptr(w.values), stream))
+        residual_ratio = 0.0
+        norm_w, norm_x, norm_b = self._fetch_norms()
+        if norm_b != 0.0:                    # (b == 0: the queued step solved for x = 0, as the reference returns)
             while True:
-                norm_w, norm_x = self._iteration(x, b, w)
                 residual_ratio = norm_w / (min(norm_x, 1e6 * norm_b) + norm_b)
                 self.ir += 1
                 if self.ir >= self.richardson_max_iter or residual_ratio < self.richardson_tol:
                     break
+                self._launch_iteration(x, b, w)
+                norm_w, norm_x, _ = self._fetch_norms()
         self.residual_ratio = residual_ratio
         return residual_ratio < self.richardson_acceptable_tol
+
+    def discard(self):
+        """drop a step queued by start() (its factorisation was rejected)"""
+        self._started = False
