@@ -269,12 +269,26 @@ int b2_condensed_kkt_mul(b2_bounds* b, b2_spmv_plan* hess, b2_spmv_plan* jt, int
                          const double* reg_d, const double* du_diag_d, const double* l_lower_d, const double* u_lower_d,
                          const double* l_diag_d, const double* u_diag_d, double alpha, double beta,
                          const double* x_d, double* w_d, void* stream);
+/* the same product that also accumulates ||w||_inf of its result into *norm_inf_d (device; the caller zeroes it -- 
+ * b2_richardson_update does); the residual norm of a Richardson step then costs no extra pass */
+int b2_condensed_kkt_mul_norm(b2_bounds* b, b2_spmv_plan* hess, b2_spmv_plan* jt, int64_t n, int64_t m,
+                         const double* hess_nz_d, const double* jt_nz_d,
+                         const double* reg_d, const double* du_diag_d, const double* l_lower_d, const double* u_lower_d,
+                         const double* l_diag_d, const double* u_diag_d, double alpha, double beta,
+                         const double* x_d, double* w_d, double* norm_inf_d, void* stream);
 
 /* infinity norm of a device vector into a device scalar (no host sync) */
+/* vector part of one Richardson step (src/LinearSolvers/backsolve.jl:45-48) in one pass: x += w ; w = b ;
+ * norms_d[0] = 0 (accumulator for b2_condensed_kkt_mul_norm) ; norms_d[1] = ||x||_inf */
+int b2_richardson_update(int64_t n, const double* b_d, double* w_d, double* x_d, double* norms_d, void* stream);
 int b2_norm_inf(int64_t n, const double* x_d, double* out_d, void* stream);
 /* y += a*x ; y = x ; x = v */
 int b2_axpy(int64_t n, double a, const double* x_d, double* y_d, void* stream);
 int b2_copy(int64_t n, const double* x_d, double* y_d, void* stream);
+/* count <= 16 independent copies dst[k][0:n[k]) = src[k][0:n[k]) in one launch (host arrays of device pointers): how the
+ * outputs of the model callbacks (eval_jac_wrapper!/eval_lag_hess_wrapper!, src/IPM/callbacks.jl) and the iterate's
+ * diagonals reach the KKT buffers when they are produced elsewhere on the device */
+int b2_copy_many(int32_t count, const double* const* src_d, double* const* dst_d, const int64_t* n, void* stream);
 int b2_fill(int64_t n, double v, double* x_d, void* stream);
 
 #ifdef __cplusplus

@@ -356,8 +356,14 @@ struct CondMulArgs {
     const int32_t *j_colptr, *j_rowval, *j_rowptr, *j_colidx, *j_valmap;
     const double *h_nz, *j_nz;
 };
-__global__ void k_cond_mul(CondMulArgs c, KktMulArgs a, const double* __restrict__ x, double* __restrict__ w) {
+__device__ __forceinline__ void norm_inf_commit(double mx, unsigned long long* out) {   // NaN-propagating max of non-negative doubles
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { const double t = __shfl_xor_sync(0xffffffffu, mx, o); if (t > mx || t != t) mx = t; }
+    if ((threadIdx.x & 31) == 0) atomicMax(out, (unsigned long long)__double_as_longlong(mx));
+}
+__global__ void k_cond_mul(CondMulArgs c, KktMulArgs a, const double* __restrict__ x, double* __restrict__ w, unsigned long long* norm_out) {
     const int64_t n = c.n, m = c.m;
+    double mx = 0.0;
     const double* xs = x + n;
     const double* xz = x + n + m;
     GRID_STRIDE(t, a.n_tot + a.m + a.nlb + a.nub) {
@@ -372,13 +378,17 @@ __global__ void k_cond_mul(CondMulArgs c, KktMulArgs a, const double* __restrict
             const int64_t j = t - n - m;
             wt = a.alpha * col_dot(c.j_colptr, c.j_rowval, c.j_nz, x, j) + scl(a.beta, wt) - a.alpha * xs[j];
         }
-        w[t] = kktmul_entry(a, t, wt, x);
+        const double wv = kktmul_entry(a, t, wt, x);
+        w[t] = wv;
+        const double av = fabs(wv);
+        if (av > mx || av != av) mx = av;
     }
+    if (norm_out) norm_inf_commit(mx, norm_out);
 }
-extern "C" int b2_condensed_kkt_mul(b2_bounds* b, b2_spmv_plan* hess, b2_spmv_plan* jt, int64_t n, int64_t m,
+extern "C" int b2_condensed_kkt_mul_norm(b2_bounds* b, b2_spmv_plan* hess, b2_spmv_plan* jt, int64_t n, int64_t m,
                                     const double* hess_nz_d, const double* jt_nz_d, const double* reg_d, const double* du_diag_d,
                                     const double* l_lower_d, const double* u_lower_d, const double* l_diag_d, const double* u_diag_d,
-                                    double alpha, double beta, const double* x_d, double* w_d, void* stream) {
+                                    double alpha, double beta, const double* x_d, double* w_d, double* norm_inf_d, void* stream) {
     if (!b || !hess || !jt || !x_d || !w_d || b->n_tot != n + m || hess->nrow != n || jt->nrow != n || jt->ncol != m) {
         set_error("b2_condensed_kkt_mul: invalid argument");
         return B2_ERR_INVALID;
@@ -390,9 +400,16 @@ extern "C" int b2_condensed_kkt_mul(b2_bounds* b, b2_spmv_plan* hess, b2_spmv_pl
     c.h_nz = hess_nz_d; c.j_nz = jt_nz_d;
     KktMulArgs a = make_kktmul(b, m, reg_d, du_diag_d, l_lower_d, u_lower_d, l_diag_d, u_diag_d, alpha, beta);
     const int64_t tot = a.n_tot + a.m + a.nlb + a.nub;
-    k_cond_mul<<<grid_for(tot), 256, 0, as_stream(stream)>>>(c, a, x_d, w_d);
+    k_cond_mul<<<grid_for(tot), 256, 0, as_stream(stream)>>>(c, a, x_d, w_d, (unsigned long long*)norm_inf_d);
     B2_CUDA(cudaGetLastError());
     return B2_OK;
+}
+extern "C" int b2_condensed_kkt_mul(b2_bounds* b, b2_spmv_plan* hess, b2_spmv_plan* jt, int64_t n, int64_t m,
+                                    const double* hess_nz_d, const double* jt_nz_d, const double* reg_d, const double* du_diag_d,
+                                    const double* l_lower_d, const double* u_lower_d, const double* l_diag_d, const double* u_diag_d,
+                                    double alpha, double beta, const double* x_d, double* w_d, void* stream) {
+    return b2_condensed_kkt_mul_norm(b, hess, jt, n, m, hess_nz_d, jt_nz_d, reg_d, du_diag_d, l_lower_d, u_lower_d, l_diag_d, u_diag_d, alpha,
+                                     beta, x_d, w_d, nullptr, stream);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -401,9 +418,28 @@ extern "C" int b2_condensed_kkt_mul(b2_bounds* b, b2_spmv_plan* hess, b2_spmv_pl
 __global__ void k_norm_inf(int64_t n, const double* __restrict__ x, unsigned long long* out) {
     double mx = 0.0;
     GRID_STRIDE(i, n) { const double v = fabs(x[i]); if (v > mx || v != v) mx = v; }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { const double t = __shfl_xor_sync(0xffffffffu, mx, o); if (t > mx || t != t) mx = t; }
-    if ((threadIdx.x & 31) == 0) atomicMax(out, (unsigned long long)__double_as_longlong(mx));   // non-negative doubles order as integers
+    norm_inf_commit(mx, out);                     // non-negative doubles order as integers
+}
+// the vector part of one Richardson step (src/LinearSolvers/backsolve.jl:45-48) in one pass: x += w ; w = b ; ||x||_inf
+__global__ void k_richardson_update(int64_t n, const double* __restrict__ b, double* __restrict__ w, double* __restrict__ x,
+                                    unsigned long long* norm_x) {
+    double mx = 0.0;
+    GRID_STRIDE(i, n) {
+        const double xi = x[i] + w[i];
+        x[i] = xi;
+        w[i] = b[i];
+        const double v = fabs(xi);
+        if (v > mx || v != v) mx = v;
+    }
+    norm_inf_commit(mx, norm_x);
+}
+extern "C" int b2_richardson_update(int64_t n, const double* b_d, double* w_d, double* x_d, double* norms_d, void* stream) {
+    if (n < 0 || !norms_d || (n && (!b_d || !w_d || !x_d))) { set_error("b2_richardson_update: invalid argument"); return B2_ERR_INVALID; }
+    cudaStream_t st = as_stream(stream);
+    B2_CUDA(cudaMemsetAsync(norms_d, 0, 2 * sizeof(double), st));
+    if (n) k_richardson_update<<<grid_for(n), 256, 0, st>>>(n, b_d, w_d, x_d, (unsigned long long*)(norms_d + 1));
+    B2_CUDA(cudaGetLastError());
+    return B2_OK;
 }
 extern "C" int b2_norm_inf(int64_t n, const double* x_d, double* out_d, void* stream) {
     if (n < 0 || !out_d || (n && !x_d)) { set_error("b2_norm_inf: invalid argument"); return B2_ERR_INVALID; }
@@ -425,6 +461,31 @@ extern "C" int b2_axpy(int64_t n, double a, const double* x_d, double* y_d, void
 extern "C" int b2_copy(int64_t n, const double* x_d, double* y_d, void* stream) {
     if (n < 0 || (n && (!x_d || !y_d))) return B2_ERR_INVALID;
     if (n) k_copy<<<grid_for(n), 256, 0, as_stream(stream)>>>(n, x_d, y_d);
+    B2_CUDA(cudaGetLastError());
+    return B2_OK;
+}
+// up to 16 independent vector copies in ONE launch (the model callbacks' outputs arriving in the KKT buffers)
+struct CopyManyArgs { const double* src[16]; double* dst[16]; int64_t n[16]; };
+__global__ void k_copy_many(CopyManyArgs c) {
+    const double* __restrict__ x = c.src[blockIdx.y];
+    double* __restrict__ y = c.dst[blockIdx.y];
+    const int64_t n = c.n[blockIdx.y];
+    GRID_STRIDE(i, n) y[i] = x[i];
+}
+extern "C" int b2_copy_many(int32_t count, const double* const* src_d, double* const* dst_d, const int64_t* n, void* stream) {
+    if (count < 0 || count > 16 || (count && (!src_d || !dst_d || !n))) { set_error("b2_copy_many: invalid argument (at most 16 segments)"); return B2_ERR_INVALID; }
+    if (count == 0) return B2_OK;
+    CopyManyArgs c;
+    int64_t nmax = 0;
+    for (int k = 0; k < 16; ++k) {
+        const bool on = k < count;
+        if (on && (n[k] < 0 || (n[k] && (!src_d[k] || !dst_d[k])))) { set_error("b2_copy_many: invalid segment"); return B2_ERR_INVALID; }
+        c.src[k] = on ? src_d[k] : nullptr; c.dst[k] = on ? dst_d[k] : nullptr; c.n[k] = on ? n[k] : 0;
+        if (on) nmax = std::max(nmax, n[k]);
+    }
+    if (nmax == 0) return B2_OK;
+    const int gx = (int)std::max<int64_t>(1, std::min<int64_t>((nmax + 255) / 256, 2 * sm_count()));
+    k_copy_many<<<dim3(gx, count), 256, 0, as_stream(stream)>>>(c);
     B2_CUDA(cudaGetLastError());
     return B2_OK;
 }

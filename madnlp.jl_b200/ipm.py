@@ -53,15 +53,22 @@ class IPMLinearAlgebra:
         """Copy one iterate's callback outputs / diagonal inputs into the KKT buffers (H2D when `it` holds pinned
         host tensors, D2D when it holds device tensors)."""
         k = self.kkt
-        k.get_jacobian().copy_(it["jac"], non_blocking=non_blocking)
-        k.get_hessian().copy_(it["hess"], non_blocking=non_blocking)
-        k.reg.copy_(it["reg"], non_blocking=non_blocking)
-        k.du_diag.copy_(it["du_diag"], non_blocking=non_blocking)
-        k.l_diag.copy_(it["l_diag"], non_blocking=non_blocking)
-        k.u_diag.copy_(it["u_diag"], non_blocking=non_blocking)
-        k.l_lower.copy_(it["l_lower"], non_blocking=non_blocking)
-        k.u_lower.copy_(it["u_lower"], non_blocking=non_blocking)
-        self.p.values.copy_(it["rhs"], non_blocking=non_blocking)
+        pairs = ((k.get_jacobian(), it["jac"]), (k.get_hessian(), it["hess"]), (k.reg, it["reg"]), (k.du_diag, it["du_diag"]),
+                 (k.l_diag, it["l_diag"]), (k.u_diag, it["u_diag"]), (k.l_lower, it["l_lower"]), (k.u_lower, it["u_lower"]),
+                 (self.p.values, it["rhs"]))
+        if all(src.is_cuda for _, src in pairs):
+            # device-resident producer: one launch for the nine vectors
+            import ctypes as C
+            from .capi import lib, check, stream_ptr
+            cnt = len(pairs)
+            src = (C.c_void_p * cnt)(*[s_.data_ptr() for _, s_ in pairs])
+            dst = (C.c_void_p * cnt)(*[d_.data_ptr() for d_, _ in pairs])
+            ns = (C.c_int64 * cnt)(*[d_.numel() for d_, _ in pairs])
+            assert all(d_.numel() == s_.numel() and s_.dtype == torch.float64 and s_.is_contiguous() for d_, s_ in pairs)
+            check(lib.b2_copy_many(cnt, src, dst, ns, stream_ptr(getattr(k, "stream", None))))
+        else:
+            for d_, s_ in pairs:
+                d_.copy_(s_, non_blocking=non_blocking)
 
     def _prologue(self):
         k = self.kkt

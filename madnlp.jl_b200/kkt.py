@@ -374,6 +374,14 @@ class SparseCondensedKKTSystem(_KKTBase):
                                        float(alpha), float(beta), ptr(x.values), ptr(w.values), _sp(self.stream)))
         return w
 
+    def mul_norm(self, w, x, alpha, beta, norm_out):
+        """mul! that also accumulates ||w||_inf of the result into the (zeroed) device scalar `norm_out`"""
+        check(lib.b2_condensed_kkt_mul_norm(self._bounds.h, self._hess_spmv.h, self._jt_spmv.h, self.n, self.m,
+                                            ptr(self.hess_com.nzval), ptr(self.jt_csc.nzval), ptr(self.reg), ptr(self.du_diag),
+                                            ptr(self.l_lower), ptr(self.u_lower), ptr(self.l_diag), ptr(self.u_diag),
+                                            float(alpha), float(beta), ptr(x.values), ptr(w.values), ptr(norm_out), _sp(self.stream)))
+        return w
+
     def jtprod(self, y, x):
         """condensed.jl:150-156."""
         check(lib.b2_spmv_n(self._jt_spmv.h, ptr(self.jt_csc.nzval), ptr(x), ptr(y), 1.0, 0.0, _sp(self.stream)))

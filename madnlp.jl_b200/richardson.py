@@ -14,8 +14,8 @@ from .capi import lib, check, ptr
 
 
 class RichardsonIterator:
-    """`use_cuda_graph=True` replays the body of one refinement step (solve_kkt!, axpy, copy, mul!, two norms -- about a dozen
-    launches plus the solver's own graphs) as ONE CUDA graph: same kernels, same order, one launch from the host."""
+    """`use_cuda_graph=True` replays the body of one refinement step (solve_kkt!, the fused x += w / w = b / ||x|| pass, mul!
+    with the fused ||w||) as ONE CUDA graph: same arithmetic, same order, one launch from the host."""
 
     def __init__(self, kkt, tol=1e-8, richardson_max_iter=10, use_cuda_graph=True):
         self.kkt = kkt
@@ -36,11 +36,12 @@ class RichardsonIterator:
         stream = capi.stream_ptr(getattr(kkt, "stream", None))
         n = b.values.numel()
         kkt.solve_kkt(w)
-        check(lib.b2_axpy(n, 1.0, ptr(w.values), ptr(x.values), stream))
-        check(lib.b2_copy(n, ptr(b.values), ptr(w.values), stream))
-        kkt.mul(w, x, -1.0, 1.0)
-        check(lib.b2_norm_inf(n, ptr(w.values), ptr(self._norms[0:1]), stream))
-        check(lib.b2_norm_inf(n, ptr(x.values), ptr(self._norms[1:2]), stream))
+        check(lib.b2_richardson_update(n, ptr(b.values), ptr(w.values), ptr(x.values), ptr(self._norms), stream))   # x += w; w = b; ||x||
+        if hasattr(kkt, "mul_norm"):
+            kkt.mul_norm(w, x, -1.0, 1.0, self._norms[0:1])                                                         # w -= K x; ||w||
+        else:
+            kkt.mul(w, x, -1.0, 1.0)
+            check(lib.b2_norm_inf(n, ptr(w.values), ptr(self._norms[0:1]), stream))
 
     def _launch_iteration(self, x, b, w):
         """queue one refinement step and the D2H copy of its norms; no host synchronisation"""

@@ -395,3 +395,42 @@ def test_dense_matvec_kernels(rows, cols):
     check(lib.b2d_symv_lower(n, n, lowd.data_ptr(), xsd.data_ptr(), ys.data_ptr(), 0.75, -1.0, st))
     ref = 0.75 * (S @ xs) - ys0
     assert (np.abs(ys.cpu().numpy() - ref) / (np.abs(S) @ np.abs(xs) + np.abs(ys0) + 1.0)).max() < 1e-13
+
+
+def test_fused_richardson_kernels_are_bit_identical():
+    """b2_richardson_update == (axpy; copy; norm_inf) and b2_condensed_kkt_mul_norm == (mul; norm_inf), bit for bit;
+    b2_copy_many == the individual copies (ragged lengths, an empty segment)."""
+    _need_gpu()
+    import ctypes as C
+    from madnlp_jl_b200 import kkt as K
+    from madnlp_jl_b200.capi import lib, check
+    st = torch.cuda.current_stream().cuda_stream
+    rng = np.random.default_rng(11)
+    n = 100003
+    b, w, x = (_dev(rng.standard_normal(n)) for _ in range(3))
+    w2, x2 = w.clone(), x.clone()
+    norms = torch.full((2,), 7.0, dtype=torch.float64, device="cuda")
+    check(lib.b2_richardson_update(n, b.data_ptr(), w.data_ptr(), x.data_ptr(), norms.data_ptr(), st))
+    check(lib.b2_axpy(n, 1.0, w2.data_ptr(), x2.data_ptr(), st)); check(lib.b2_copy(n, b.data_ptr(), w2.data_ptr(), st))
+    assert torch.equal(x, x2) and torch.equal(w, w2)
+    assert float(norms[0]) == 0.0 and float(norms[1]) == float(x2.abs().max())
+    # mul with fused norm on a condensed KKT system
+    model, stt = W.acopf_case("case30_synth")
+    it = W.ipm_iterates(model, stt, 1, seed=5)[0]
+    kc = o.SparseCondensedKKTSystem(_cb(stt)); kg = K.SparseCondensedKKTSystem(_cb(stt))
+    _load(kg, kc, it)
+    xv = K.UnreducedKKTVector.for_kkt(kg); wa = K.UnreducedKKTVector.for_kkt(kg); wb = K.UnreducedKKTVector.for_kkt(kg)
+    xv.values.copy_(_dev(rng.standard_normal(xv.values.numel())))
+    r0 = _dev(rng.standard_normal(xv.values.numel())); wa.values.copy_(r0); wb.values.copy_(r0)
+    acc = torch.zeros(1, dtype=torch.float64, device="cuda")
+    kg.mul(wa, xv, -1.0, 1.0)
+    kg.mul_norm(wb, xv, -1.0, 1.0, acc)
+    assert torch.equal(wa.values, wb.values) and float(acc[0]) == float(wa.values.abs().max())
+    # copy_many
+    lens = [0, 1, 255, 70001]
+    src = [_dev(rng.standard_normal(max(k, 1)))[:k] for k in lens]
+    dst = [torch.zeros(max(k, 1), dtype=torch.float64, device="cuda")[:k] for k in lens]
+    cnt = len(lens)
+    check(lib.b2_copy_many(cnt, (C.c_void_p * cnt)(*[s.data_ptr() for s in src]), (C.c_void_p * cnt)(*[d.data_ptr() for d in dst]),
+                           (C.c_int64 * cnt)(*lens), st))
+    assert all(torch.equal(s, d) for s, d in zip(src, dst))
