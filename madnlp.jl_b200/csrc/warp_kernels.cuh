@@ -328,23 +328,52 @@ __device__ __forceinline__ void front_fwd_team(const SolveArgs& a, const ChildRe
     cp_async_wait_all();
     team_sync<NW>(team);
     double y = ys[tid];
-    for (int k0 = 0; k0 < w; k0 += 8) {
-        double l[8];
+    if (NW == 1) {
+        for (int k0 = 0; k0 < w; k0 += 8) {
+            double l[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) { const int k = k0 + u; l[u] = (k < w && tid > k && tid < f) ? P[k * f + tid] : 0.0; }
+            for (int u = 0; u < 8; ++u) { const int k = k0 + u; l[u] = (k < w && tid > k && tid < f) ? P[k * f + tid] : 0.0; }
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const int k = k0 + u;
-            if (k < w) {                                // team-uniform
-                double yk;
-                if (NW == 1) yk = __shfl_sync(0xffffffffu, y, k);
-                else {
-                    double* slot = yb + ((k & 1) * 8);
-                    if (tid == k) slot[0] = y;
-                    team_sync<NW>(team);
-                    yk = slot[0];
+            for (int u = 0; u < 8; ++u) {
+                const int k = k0 + u;
+                if (k < w) y = fma(-l[u], __shfl_sync(0xffffffffu, y, k), y);      // team-uniform
+            }
+        }
+    } else {
+        // two-warp team, blocked by warp: warp 0 eliminates pivots 0..31 among its own rows with shuffles and publishes
+        // them; warp 1 applies them in one parallel pass, then eliminates pivots 32.. among its rows -- two barriers per
+        // front instead of one per pivot
+        const int w0 = min(w, 32);
+        if (tid < 32) {
+            for (int k0 = 0; k0 < w0; k0 += 8) {
+                double l[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) { const int k = k0 + u; l[u] = (k < w0 && tid > k && tid < f) ? P[k * f + tid] : 0.0; }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int k = k0 + u;
+                    if (k < w0) y = fma(-l[u], __shfl_sync(0xffffffffu, y, k), y);
                 }
-                y = fma(-l[u], yk, y);
+            }
+            if (tid < w0) ys[tid] = y;
+        }
+        team_sync<NW>(team);
+        if (tid >= 32) {
+            if (tid < f) {
+                double acc = 0.0;
+#pragma unroll 8
+                for (int k = 0; k < w0; ++k) acc = fma(P[k * f + tid], ys[k], acc);
+                y -= acc;
+            }
+            for (int k0 = 32; k0 < w; k0 += 8) {
+                double l[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) { const int k = k0 + u; l[u] = (k < w && tid > k && tid < f) ? P[k * f + tid] : 0.0; }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int k = k0 + u;
+                    if (k < w) y = fma(-l[u], __shfl_sync(0xffffffffu, y, k - 32), y);
+                }
             }
         }
     }
@@ -387,23 +416,52 @@ __device__ __forceinline__ void front_bwd_team(const SolveArgs& a, int s, double
         t -= acc;
     }
     // back-substitution with L11': x_k final -> t_j -= L(k,j) x_k for j < k
-    for (int k0 = w - 1; k0 >= 1; k0 -= 8) {
-        double l[8];
+    if (NW == 1) {
+        for (int k0 = w - 1; k0 >= 1; k0 -= 8) {
+            double l[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) { const int k = k0 - u; l[u] = (k >= 1 && tid < k) ? P[k * w + tid] : 0.0; }
+            for (int u = 0; u < 8; ++u) { const int k = k0 - u; l[u] = (k >= 1 && tid < k) ? P[k * w + tid] : 0.0; }
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const int k = k0 - u;
-            if (k >= 1) {
-                double xk;
-                if (NW == 1) xk = __shfl_sync(0xffffffffu, t, k);
-                else {
-                    double* slot = xb + ((k & 1) * 8);
-                    if (tid == k) slot[0] = t;
-                    team_sync<NW>(team);
-                    xk = slot[0];
+            for (int u = 0; u < 8; ++u) {
+                const int k = k0 - u;
+                if (k >= 1) t = fma(-l[u], __shfl_sync(0xffffffffu, t, k), t);
+            }
+        }
+    } else {
+        // blocked by warp (see the forward sweep): warp 1 finishes columns 32.. with shuffles and publishes them in
+        // xs[32..] (the gathered ancestors occupy xs[0 .. f-w) with f - w < 32 here); warp 0 applies them in one pass
+        if (w > 32) {
+            if (tid >= 32) {
+                for (int k0 = w - 1; k0 >= 33; k0 -= 8) {
+                    double l[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) { const int k = k0 - u; l[u] = (k >= 33 && tid < k) ? P[k * w + tid] : 0.0; }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int k = k0 - u;
+                        if (k >= 33) t = fma(-l[u], __shfl_sync(0xffffffffu, t, k - 32), t);
+                    }
                 }
-                t = fma(-l[u], xk, t);
+                if (tid < w) xs[tid] = t;
+            }
+            team_sync<NW>(team);
+            if (tid < 32) {
+                double acc = 0.0;
+#pragma unroll 8
+                for (int k = 32; k < w; ++k) acc = fma(P[k * w + tid], xs[k], acc);
+                t -= acc;
+            }
+        }
+        if (tid < 32) {
+            for (int k0 = min(w, 32) - 1; k0 >= 1; k0 -= 8) {
+                double l[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) { const int k = k0 - u; l[u] = (k >= 1 && tid < k) ? P[k * w + tid] : 0.0; }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int k = k0 - u;
+                    if (k >= 1) t = fma(-l[u], __shfl_sync(0xffffffffu, t, k), t);
+                }
             }
         }
     }
