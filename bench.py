@@ -276,7 +276,9 @@ def run_b200(args, rank, world, local_rank):
             "ms_per_factorize": fac_ms, "ms_per_assemble": asm_ms, "ms_per_solve": sol_ms,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                     "ms_per_step": e2e_ms / args.steps},
-            "gpu_launches": int((stats["n_factor_launches"] + 5 + solves * (stats["n_solve_launches"] + 8)) * args.steps),
+            # own kernels per step: iterate load (1, device-resident run) + assembly (5) + numeric factorisation + start of the
+            # refinement (||b||, w = b: 2) + per refinement step: the triangular sweeps + pre1/pre2/post1/finish/update/mul (6)
+            "gpu_launches": int((1 + 5 + stats["n_factor_launches"] + 2 + solves * (stats["n_solve_launches"] + 6)) * args.steps),
             "roofline": {"kernel": "k_factor_dep: numeric multifrontal LDL^T of the whole elimination tree in one launch", "bound": "hbm",
                          "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": (achieved / hbm_peak) if achieved else None,
                          "traffic": 11.39e6 if (args.workload == "case10000_goc" and world == 1) else None,
