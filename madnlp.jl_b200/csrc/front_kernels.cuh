@@ -224,12 +224,6 @@ __global__ void k_big_extend_add(FactorArgs a, const int32_t* __restrict__ list,
     }
 }
 
-constexpr int BIG_NB = 32;       // pivot block width of the blocked right-looking factorisation
-constexpr int BIG_ROWS = 128;    // rows of the panel solved by one CTA
-
-// Step kb of every big front, part 1: unblocked LDL^T of the NB x NB diagonal block by ONE WARP, entirely in registers:
-// lane = row, a[] = sliding window of the row (a[0] is always the current pivot column), pivot column broadcast by
-// shuffles -- no shared memory, no barriers.  Writes L11 (unit lower, scaled) and D in place, D into dvec, inertia counts.
 __device__ __forceinline__ double fast_rcp_d(double x) {
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
@@ -237,164 +231,11 @@ __device__ __forceinline__ double fast_rcp_d(double x) {
     r = fma(r, fma(-x, r, 1.0), r);
     return r;
 }
-__global__ void __launch_bounds__(32) k_big_diag(FactorArgs a, const int32_t* __restrict__ list, int step) {
-    const FrontDesc d = a.desc[list[blockIdx.x]];
-    const int kb = step * BIG_NB;
-    if (kb >= d.w) return;
-    const int f = d.f;
-    const int nb = min(BIG_NB, d.w - kb);
-    const int lane = threadIdx.x;
-    double* Lp = a.L + d.lp_off;
-    double av[BIG_NB + 1];
-#pragma unroll
-    for (int j = 0; j < BIG_NB; ++j) av[j] = (j < nb && lane < nb && lane >= j) ? Lp[(size_t)(kb + j) * f + kb + lane] : 0.0;
-    av[BIG_NB] = 0.0;
-    int nneg = 0, npert = 0;
-    for (int k = 0; k < nb; ++k) {
-        double dk = __shfl_sync(0xffffffffu, av[0], k);
-        if (!(fabs(dk) >= a.eps)) { dk = (dk < 0.0) ? -a.eps : a.eps; ++npert; }
-        else if (dk < 0.0) ++nneg;
-        const double u = av[0];
-        const double l = u * fast_rcp_d(dk);
-        if (lane < nb) {
-            if (lane > k) Lp[(size_t)(kb + k) * f + kb + lane] = l;
-            else if (lane == k) { Lp[(size_t)(kb + k) * f + kb + k] = dk; a.dvec[d.col0 + kb + k] = dk; }
-        }
-#pragma unroll
-        for (int j = 0; j < BIG_NB; ++j) {
-            const double uj = __shfl_sync(0xffffffffu, u, (k + 1 + j) & 31);
-            av[j] = fma(-l, uj, av[j + 1]);
-        }
-    }
-    if (lane == 0) {
-        if (nneg) atomicAdd(a.counters + 0, nneg);
-        if (npert) atomicAdd(a.counters + 1, npert);
-    }
-}
-
-// Step kb, part 2: rows below the diagonal block:  L21 = A21 * L11^{-T} * D^{-1}; one thread per row,
-// BIG_ROWS rows per CTA, L11/D staged in shared memory.
-__global__ void __launch_bounds__(BIG_ROWS) k_big_panel(FactorArgs a, const int32_t* __restrict__ list, int step) {
-    const FrontDesc d = a.desc[list[blockIdx.y]];
-    const int kb = step * BIG_NB;
-    if (kb >= d.w) return;
-    const int f = d.f;
-    const int nb = min(BIG_NB, d.w - kb);
-    const int row0 = kb + nb + blockIdx.x * BIG_ROWS;
-    if (row0 >= f) return;
-    __shared__ double L11[BIG_NB][BIG_NB + 1];   // [k][j] = d_j * L11(k,j), j < k
-    __shared__ double dinv[BIG_NB];
-    const int tid = threadIdx.x;
-    double* Lp = a.L + d.lp_off;
-    for (int t = tid; t < BIG_NB * BIG_NB; t += BIG_ROWS) {
-        const int k = t % BIG_NB, j = t / BIG_NB;
-        double v = 0.0;
-        if (k < nb && j < k) v = Lp[(size_t)(kb + j) * f + kb + k] * Lp[(size_t)(kb + j) * f + kb + j];
-        L11[k][j] = v;
-    }
-    if (tid < BIG_NB) dinv[tid] = (tid < nb) ? 1.0 / Lp[(size_t)(kb + tid) * f + kb + tid] : 0.0;
-    __syncthreads();
-    const int i = row0 + tid;
-    if (i < f) {
-        double x[BIG_NB];
-#pragma unroll
-        for (int k = 0; k < BIG_NB; ++k) x[k] = (k < nb) ? Lp[(size_t)(kb + k) * f + i] : 0.0;
-        // a_k = sum_{j<=k} x_j d_j L11(k,j)  =>  x_k = (a_k - sum_{j<k} x_j * (d_j L11(k,j))) / d_k
-#pragma unroll
-        for (int k = 0; k < BIG_NB; ++k) {
-            double sacc = x[k];
-#pragma unroll
-            for (int j = 0; j < BIG_NB; ++j)
-                if (j < k) sacc = fma(-x[j], L11[k][j], sacc);
-            x[k] = sacc * dinv[k];
-        }
-#pragma unroll
-        for (int k = 0; k < BIG_NB; ++k)
-            if (k < nb) Lp[(size_t)(kb + k) * f + i] = x[k];
-    }
-}
-
-// Trailing update:  C(i,j) -= sum_{k in [kb0, kb0+kcount)} L(i,k) d_k L(j,k)   for i >= j, jlo <= j < jhi.
-// Two uses (two-level blocking): the NARROW update after each 32-column step touches only the rest of the current
-// 128-column outer panel (jhi = end of the outer panel); the WIDE update after the whole outer panel applies all 128
-// pivot columns at once to everything behind it (each C tile is read and written once per 128 pivots, not per 32).
-// 64x64 tiles, 256 threads (8 warps as 4x2, each warp 16x32 of m8n8k4 DMMA fragments), operands staged in shared
-// memory 32 pivots at a time.
-constexpr int UT = 64;
-__global__ void __launch_bounds__(256) k_big_update(FactorArgs a, const int32_t* __restrict__ list, int kb0, int kmax, int jlo_rel, int jhi_rel,
-                                                    int clip_jlo) {
-    const FrontDesc d = a.desc[list[blockIdx.z]];
-    if (kb0 >= d.w) return;
-    const int f = d.f;
-    const int kcount = min(kmax, d.w - kb0);
-    // first trailing column: right behind the pivots actually applied (narrow update, possibly a partial last block) or
-    // at the fixed end of the outer panel (wide update: columns before it were already served by the narrow updates)
-    const int jlo = kb0 + (clip_jlo ? min(jlo_rel, kcount) : jlo_rel);
-    const int jhi = min(f, kb0 + jhi_rel);         // one past the last column this launch may touch
-    const int ti = blockIdx.x, tj = blockIdx.y;
-    const int i0 = jlo + ti * UT, j0 = jlo + tj * UT;
-    if (tj > ti || i0 >= f || j0 >= jhi) return;
-    __shared__ double As[BIG_NB][UT + 4];         // As[k][i] = L(i0+i, kc+k)
-    __shared__ double Bs[BIG_NB][UT + 4];         // Bs[k][j] = d_k * L(j0+j, kc+k)
-    const double* Lp = a.L + d.lp_off;
-    const int tid = threadIdx.x;
-    const int warp = tid >> 5, lane = tid & 31;
-    const int wi = (warp & 3) * 16, wj = (warp >> 2) * 32;     // warp tile origin inside the 64x64 tile
-    const int g = lane >> 2, q = lane & 3;                      // DMMA fragment coordinates
-    double c[2][4][2];
-#pragma unroll
-    for (int x = 0; x < 2; ++x)
-#pragma unroll
-        for (int y = 0; y < 4; ++y) c[x][y][0] = c[x][y][1] = 0.0;
-    for (int kc = 0; kc < kcount; kc += BIG_NB) {
-        const int nb = min(BIG_NB, kcount - kc);
-        if (kc) __syncthreads();
-        for (int t = tid; t < BIG_NB * UT; t += 256) {
-            const int i = t % UT, k = t / UT;
-            double va = 0.0, vb = 0.0;
-            if (k < nb) {
-                const size_t colo = (size_t)(kb0 + kc + k) * f;
-                const double dk = Lp[colo + kb0 + kc + k];
-                if (i0 + i < f) va = Lp[colo + i0 + i];
-                if (j0 + i < f) vb = dk * Lp[colo + j0 + i];
-            }
-            As[k][i] = va;
-            Bs[k][i] = vb;
-        }
-        __syncthreads();
-#pragma unroll
-        for (int k0 = 0; k0 < BIG_NB; k0 += 4) {
-            double af[2], bf[4];
-#pragma unroll
-            for (int x = 0; x < 2; ++x) af[x] = As[k0 + q][wi + 8 * x + g];      // A frag: row g, col q
-#pragma unroll
-            for (int y = 0; y < 4; ++y) bf[y] = Bs[k0 + q][wj + 8 * y + g];      // B frag: row q, col g
-#pragma unroll
-            for (int x = 0; x < 2; ++x)
-#pragma unroll
-                for (int y = 0; y < 4; ++y)
-                    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-                                 : "+d"(c[x][y][0]), "+d"(c[x][y][1])
-                                 : "d"(af[x]), "d"(bf[y]));
-        }
-    }
-    // C fragment: row g, cols 2q, 2q+1
-#pragma unroll
-    for (int x = 0; x < 2; ++x)
-#pragma unroll
-        for (int y = 0; y < 4; ++y)
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const int i = i0 + wi + 8 * x + g;
-                const int j = j0 + wj + 8 * y + 2 * q + e;
-                if (i < f && j < jhi && i >= j) *front_ptr(a, d, i, j) -= c[x][y][e];
-            }
-}
-
 
 // ----------------------------------------------------------------------------------------------------------
-// Trailing update, pipelined variant (the WIDE updates carry > 95 % of the flops of a big front):
+// Trailing update of the blocked factorisation (> 95 % of the flops of a big front; see bigfactor_kernels.cuh):
 //   C(i,j) -= sum_{k in [kb0, kb0+kcount)} L(i,k) d_k L(j,k),  i >= j, jlo <= j < jhi
+// (jlo = kb0 + min(jlo_rel, kcount) when clip_jlo, else kb0 + jlo_rel; jhi = min(f, kb0 + jhi_rel))
 // 128 x 64 tiles, 8 warps as 4 x 2 (32 x 32 per warp = 4 x 4 m8n8k4 DMMA fragments).  Both operands are raw panel
 // columns of L streamed by cp.async through a GU_STAGES-deep ring of K = 16 slices (no register staging, loads stay in
 // flight under the tensor pipe); the -d_k scaling is applied to the A fragments in registers (4 DMUL per 16 DMMA), and

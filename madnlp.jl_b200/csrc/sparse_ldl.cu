@@ -27,7 +27,6 @@ struct LevelSched {
     WarpLaunch W, W2;                               // fronts of order <= 32 / <= 64
     int offM = 0, nM = 0, maxfM = 0;                // shared-memory CTA class
     int offB = 0, nB = 0, maxfB = 0, maxwB = 0, maxchildB = 0, maxamapB = 0, maxrB = 0;   // HBM-resident class
-    int partialB = 0;                               // some front's pivot count is not a multiple of BIG_NB
     int offC = 0, nC = 0, maxfC = 0, maxwC = 0;     // M and B fronts together, for the multi-CTA solve kernels
 };
 struct Phase {
@@ -86,19 +85,6 @@ struct b2_solver {
 
 namespace {
 
-// wide trailing update of every big front in `lb`: all `ob_cols` pivots of the outer panel at `ob` applied to the `rem`
-// rows/columns behind it (cp.async-pipelined DMMA kernel; B2_WIDE_PIPE=0 selects the unpipelined 64x64 kernel)
-bool wide_pipe_enabled() {
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("B2_WIDE_PIPE"); v = (e && e[0] == '0') ? 0 : 1; }
-    return v != 0;
-}
-// 128-column outer steps (k_big_diag128 / k_big_trsm / k_big_update_pipe); B2_BIG_V2=0 selects the 32-column chain
-bool big_v2_enabled() {
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("B2_BIG_V2"); v = (e && e[0] == '0') ? 0 : 1; }
-    return v != 0;
-}
 // one outer step of every big front in `lb`: diagonal block (factor + inverse), rows below, trailing update
 void launch_big_step(const FactorArgs& a, const int32_t* lb, int nfronts, int ob, int maxf, double* Linv, const int64_t* linv_off,
                      cudaStream_t st, int64_t* nl) {
@@ -116,32 +102,6 @@ void launch_big_step(const FactorArgs& a, const int32_t* lb, int nfronts, int ob
     k_big_trsm<<<dim3((rem + TR_ROWS - 1) / TR_ROWS, nfronts), 256, GU_SMEM, st>>>(a, lb, ob, Linv, linv_off);
     k_big_update_pipe<<<dim3((rem + GU_M - 1) / GU_M, (rem + GU_N - 1) / GU_N, nfronts), 256, GU_SMEM, st>>>(a, lb, ob, DB, DB, 1 << 30, 1);
     if (nl) *nl += 2;
-}
-bool narrow_pipe_enabled() {
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("B2_NARROW_PIPE"); v = (e && e[0] == '0') ? 0 : 1; }
-    return v != 0;
-}
-// narrow update after a 32-column step: the rest of the current outer panel only (columns [kb+nb, kb+32+ncols))
-void launch_narrow_update(const FactorArgs& a, const int32_t* lb, int nfronts, int kb, int ncols, int rem, cudaStream_t st) {
-    if (narrow_pipe_enabled()) {
-        static bool attr = false;
-        if (!attr) { cudaFuncSetAttribute(k_big_update_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GU_SMEM); attr = true; }
-        k_big_update_pipe<<<dim3((rem + GU_M - 1) / GU_M, (ncols + BIG_NB + GU_N - 1) / GU_N, nfronts), 256, GU_SMEM, st>>>(a, lb, kb, BIG_NB, BIG_NB, BIG_NB + ncols, 1);
-    } else {
-        const int nt = (rem + UT - 1) / UT;
-        k_big_update<<<dim3(nt, (ncols + BIG_NB + UT - 1) / UT, nfronts), 256, 0, st>>>(a, lb, kb, BIG_NB, BIG_NB, BIG_NB + ncols, 1);
-    }
-}
-void launch_wide_update(const FactorArgs& a, const int32_t* lb, int nfronts, int ob, int ob_cols, int rem, cudaStream_t st) {
-    if (wide_pipe_enabled()) {
-        static bool attr = false;
-        if (!attr) { cudaFuncSetAttribute(k_big_update_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GU_SMEM); attr = true; }
-        k_big_update_pipe<<<dim3((rem + GU_M - 1) / GU_M, (rem + GU_N - 1) / GU_N, nfronts), 256, GU_SMEM, st>>>(a, lb, ob, ob_cols, ob_cols, 1 << 30, 0);
-    } else {
-        const int nt = (rem + UT - 1) / UT;
-        k_big_update<<<dim3(nt, nt, nfronts), 256, 0, st>>>(a, lb, ob, ob_cols, ob_cols, 1 << 30, 0);
-    }
 }
 
 FactorArgs factor_args(b2_solver* s) {
@@ -222,31 +182,7 @@ int64_t enqueue_factor(b2_solver* s, int ph, cudaStream_t st) {
                 k_big_extend_add<<<dim3(std::max(1, std::min(2 * nsm / lv.nB + 1, (lv.maxrB * 32 + 255) / 256)), lv.nB), 256, 0, st>>>(a, lb, c);
                 ++nl;
             }
-            constexpr int OB = 128;                      // outer panel: 4 steps of BIG_NB columns
-            if (big_v2_enabled()) {
-                for (int ob = 0; ob < lv.maxwB; ob += DB) launch_big_step(a, lb, lv.nB, ob, lv.maxfB, s->d_Linv.p, s->d_linv_off.p, st, &nl);
-            } else
-            for (int ob = 0; ob < lv.maxwB; ob += OB) {
-                for (int kb = ob; kb < std::min(ob + OB, lv.maxwB); kb += BIG_NB) {
-                    const int step = kb / BIG_NB;
-                    k_big_diag<<<lv.nB, 32, 0, st>>>(a, lb, step);
-                    ++nl;
-                    const int rem = lv.maxfB - kb - 1;      // rows below the (possibly partial) pivot block, upper bound
-                    if (rem <= 0) continue;
-                    k_big_panel<<<dim3((rem + BIG_ROWS - 1) / BIG_ROWS, lv.nB), BIG_ROWS, 0, st>>>(a, lb, step);
-                    ++nl;
-                    const int ncols = ob + OB - (kb + BIG_NB);      // rest of the outer panel
-                    if (ncols > 0 || lv.partialB) {                 // (a partial last block leaves columns [kb+nb, kb+32) to serve)
-                        launch_narrow_update(a, lb, lv.nB, kb, ncols, rem, st);
-                        ++nl;
-                    }
-                }
-                const int rem = lv.maxfB - ob - OB;
-                if (rem > 0) {                              // everything behind the outer panel, all its pivots at once
-                    launch_wide_update(a, lb, lv.nB, ob, OB, rem, st);
-                    ++nl;
-                }
-            }
+            for (int ob = 0; ob < lv.maxwB; ob += DB) launch_big_step(a, lb, lv.nB, ob, lv.maxfB, s->d_Linv.p, s->d_linv_off.p, st, &nl);
         }
     }
     if (P.topfused.n_cta) warp_launch(P.topfused);
@@ -541,7 +477,6 @@ void build_schedule(b2_solver* s) {
                 else {
                     Bx.push_back(sn);
                     lv.maxfB = std::max(lv.maxfB, f); lv.maxwB = std::max(lv.maxwB, w);
-                    if (w % BIG_NB) lv.partialB = 1;
                     lv.maxchildB = std::max(lv.maxchildB, nch); lv.maxamapB = std::max(lv.maxamapB, nam);
                     for (int c = S.child_ptr[sn]; c < S.child_ptr[sn + 1]; ++c) {
                         int cw, cf; fdim(S.child_idx[c], cw, cf);
@@ -550,7 +485,7 @@ void build_schedule(b2_solver* s) {
                 }
                 if (f > wmax) {
                     lv.maxfC = std::max(lv.maxfC, f); lv.maxwC = std::max(lv.maxwC, w);
-                    if (f <= smax || !big_v2_enabled()) { allC.push_back(sn); P.maxwAllC = std::max(P.maxwAllC, w); }   // (B fronts invert in k_big_diag128)
+                    if (f <= smax) { allC.push_back(sn); P.maxwAllC = std::max(P.maxwAllC, w); }   // (B fronts invert in k_big_diag128)
                 }
             }
             auto level_launch = [&](const std::vector<int32_t>& X, int nw) {
@@ -1043,7 +978,7 @@ int b2_symbolic_owner(b2_solver* s, int32_t* owner) {
 // =========================================================================================================
 // b2d_*: dense LDL^T (DenseCondensedKKTSystem back-end; replaces cusolverDnDsytrf/Xsytrs, cusolver.jl:150-187,
 // and dsytrf/dsytrs, src/LinearSolvers/lapack.jl:164-172).  The dense matrix is one "big front" with w = f = N:
-// the same blocked right-looking kernels (k_big_diag / k_big_panel / k_big_update with the DMMA trailing update).
+// the same blocked right-looking kernels (k_big_diag128 / k_big_trsm / k_big_update_pipe, bigfactor_kernels.cuh).
 // =========================================================================================================
 struct b2d_solver {
     int32_t N = 0, lda = 0;
@@ -1078,27 +1013,7 @@ void enqueue_dense_factor(b2d_solver* s, cudaStream_t st) {
     const int N = s->N;
     cudaMemsetAsync(s->counters.p, 0, 4 * sizeof(int32_t), st);
     k_copy_lower<<<dim3(std::max(1, std::min(8, (N + 255) / 256)), N), 256, 0, st>>>(N, s->lda, s->A_d, s->fact.p);
-    constexpr int OB = 128;
-    if (big_v2_enabled()) {
-        for (int ob = 0; ob < N; ob += DB) launch_big_step(a, s->list.p, 1, ob, N, s->linv.p, s->linv_off.p, st, nullptr);
-        return;
-    }
-    for (int ob = 0; ob < N; ob += OB) {
-        for (int kb = ob; kb < std::min(ob + OB, N); kb += BIG_NB) {
-            const int step = kb / BIG_NB;
-            k_big_diag<<<1, 32, 0, st>>>(a, s->list.p, step);
-            const int rem = N - kb - 1;
-            if (rem <= 0) continue;
-            k_big_panel<<<dim3((rem + BIG_ROWS - 1) / BIG_ROWS, 1), BIG_ROWS, 0, st>>>(a, s->list.p, step);
-            const int ncols = ob + OB - (kb + BIG_NB);
-            if (ncols > 0 || (N % BIG_NB)) {
-                launch_narrow_update(a, s->list.p, 1, kb, ncols, rem, st);
-            }
-        }
-        const int rem = N - ob - OB;
-        if (rem > 0) launch_wide_update(a, s->list.p, 1, ob, OB, rem, st);
-    }
-    k_big_inv<<<dim3((N + BS - 1) / BS, 1), BS, (size_t)BS * (BS + 1) * sizeof(double), st>>>(s->desc.p, s->list.p, s->fact.p, s->linv.p, s->linv_off.p);
+    for (int ob = 0; ob < N; ob += DB) launch_big_step(a, s->list.p, 1, ob, N, s->linv.p, s->linv_off.p, st, nullptr);
 }
 }  // namespace
 

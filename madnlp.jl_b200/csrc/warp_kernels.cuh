@@ -190,22 +190,29 @@ __device__ __forceinline__ void front_factor_team(const FactorArgs& a, const Chi
 #pragma unroll
     for (int j = 0; j < FMAX; ++j) av[j] = (j < f && tid < f) ? F[tid + j * f] : 0.0;
     av[FMAX] = 0.0;
+    // pivot k: the (unscaled) pivot column is published WINDOW-RELATIVE -- cb[1] = d_k, cb[2 + j] = u(k+1+j) -- so that the
+    // register window av[j] <-> column k+1+j lines up with 16-byte pairs whatever the parity of k: one LDS.128 feeds two
+    // FMAs (shared-memory issue, not the FP64 pipe, bounds a lone warp: tools/microbench/fp64_pipes.cu)
     for (int k = 0; k < w; ++k) {
         double* cb = colbuf + (k & 1) * 2 * FMAX;
-        cb[tid] = av[0];
+        if (tid >= k) cb[tid - k + 1] = av[0];
         team_sync<NW>(team);
-        double dk = cb[k];
+        double dk = cb[1];
         if (!(fabs(dk) >= a.eps)) { dk = (dk < 0.0) ? -a.eps : a.eps; if (tid == 0) ++npert; }
         else if (dk < 0.0 && tid == 0) ++nneg;
         const double dinv = fast_rcp(dk);
         const double l = av[0] * dinv;
         if (tid < f) F[tid + k * f] = (tid == k) ? dk : l;    // finished column k of the panel (rows < k: scratch)
-        const double* ub = cb + k + 1;
+        const double2* ub = reinterpret_cast<const double2*>(cb + 2);
 #pragma unroll
         for (int j0 = 0; j0 < FMAX; j0 += 8) {
             if (k + 1 + j0 < f) {                       // team-uniform
 #pragma unroll
-                for (int j = j0; j < j0 + 8; ++j) av[j] = fma(-l, ub[j], av[j + 1]);
+                for (int j = j0; j < j0 + 8; j += 2) {
+                    const double2 u = ub[j >> 1];
+                    av[j] = fma(-l, u.x, av[j + 1]);
+                    av[j + 1] = fma(-l, u.y, av[j + 2]);
+                }
             }
         }
     }
