@@ -278,6 +278,8 @@ int b2_condensed_kkt_mul_norm(b2_bounds* b, b2_spmv_plan* hess, b2_spmv_plan* jt
                          const double* x_d, double* w_d, double* norm_inf_d, void* stream);
 
 /* infinity norm of a device vector into a device scalar (no host sync) */
+/* start of solve_refine! (src/LinearSolvers/backsolve.jl:36-44) in one pass: *norm_b_d = ||b||_inf ; x = 0 ; w = b */
+int b2_richardson_begin(int64_t n, const double* b_d, double* w_d, double* x_d, double* norm_b_d, void* stream);
 /* vector part of one Richardson step (src/LinearSolvers/backsolve.jl:45-48) in one pass: x += w ; w = b ;
  * norms_d[0] = 0 (accumulator for b2_condensed_kkt_mul_norm) ; norms_d[1] = ||x||_inf */
 int b2_richardson_update(int64_t n, const double* b_d, double* w_d, double* x_d, double* norms_d, void* stream);

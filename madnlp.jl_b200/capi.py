@@ -145,6 +145,7 @@ PROTOTYPES = {
     "b2_condensed_solve_post": (C.c_int, [_p, _p, _i64, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "b2_condensed_kkt_mul": (C.c_int, [_p, _p, _p, _i64, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _f64, _f64, _p, _p, _p]),
     "b2_condensed_kkt_mul_norm": (C.c_int, [_p, _p, _p, _i64, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _f64, _f64, _p, _p, _p, _p]),
+    "b2_richardson_begin": (C.c_int, [_i64, _p, _p, _p, _p, _p]),
     "b2_richardson_update": (C.c_int, [_i64, _p, _p, _p, _p, _p]),
     "b2_copy_many": (C.c_int, [_i32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(_i64), _p]),
     "b2_norm_inf": (C.c_int, [_i64, _p, _p, _p]),

@@ -61,6 +61,7 @@ struct b2_transfer_plan {
 
 __global__ void k_transfer(int64_t nslot, const int32_t* __restrict__ ptr, const int32_t* __restrict__ src,
                            const double* __restrict__ V, double* __restrict__ dst) {
+    pdl_sync();
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nslot; i += (int64_t)gridDim.x * blockDim.x) {
         const int a = ptr[i], b = ptr[i + 1];
         double acc = 0.0;
@@ -98,7 +99,7 @@ extern "C" int b2_transfer(b2_transfer_plan* p, double* dst_nz_d, const double* 
     if (!p || !dst_nz_d || !V_d) { set_error("b2_transfer: invalid argument"); return B2_ERR_INVALID; }
     if (p->nnz_csc == 0) return B2_OK;
     const int grid = (int)std::min<int64_t>((p->nnz_csc + 255) / 256, 8 * sm_count());
-    k_transfer<<<grid, 256, 0, as_stream(stream)>>>(p->nnz_csc, p->ptr.p, p->src.p, V_d, dst_nz_d);
+    launch_pdl(k_transfer, dim3(grid), dim3(256), 0, as_stream(stream), p->nnz_csc, p->ptr.p, p->src.p, V_d, dst_nz_d);
     B2_CUDA(cudaGetLastError());
     return B2_OK;
 }
@@ -115,6 +116,7 @@ struct b2_condensed_plan {
 };
 
 __global__ void k_diag_buffer(int64_t m, const double* __restrict__ Ss, const double* __restrict__ Sd, double* __restrict__ D) {
+    pdl_sync();
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x)
         D[i] = __ddiv_rn(Ss[i], __dsub_rn(1.0, __dmul_rn(Sd[i], Ss[i])));
 }
@@ -123,6 +125,7 @@ __global__ void k_condensed(int64_t nslot, const int32_t* __restrict__ hsrc, con
                             const int32_t* __restrict__ tptr, const int4* __restrict__ trip,
                             const double* __restrict__ Hnz, const double* __restrict__ pr, const double* __restrict__ D,
                             const double* __restrict__ Jt, double* __restrict__ nz) {
+    pdl_sync();
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nslot; i += (int64_t)gridDim.x * blockDim.x) {
         double acc = 0.0;
         const int h = hsrc[i], dd = dsrc[i];
@@ -222,10 +225,10 @@ extern "C" int b2_condensed_assemble(b2_condensed_plan* p, double* aug_nz_d, con
     cudaStream_t st = as_stream(stream);
     if (p->m > 0) {
         const int g = (int)std::min<int64_t>((p->m + 255) / 256, 8 * sm_count());
-        k_diag_buffer<<<g, 256, 0, st>>>(p->m, pr_diag_d + p->n, du_diag_d, diag_buffer_d);
+        launch_pdl(k_diag_buffer, dim3(g), dim3(256), 0, st, p->m, pr_diag_d + p->n, du_diag_d, diag_buffer_d);
     }
     const int grid = (int)std::min<int64_t>((p->nnz_aug + 255) / 256, 8 * sm_count());
-    k_condensed<<<grid, 256, 0, st>>>(p->nnz_aug, p->hsrc.p, p->dsrc.p, p->tptr.p, p->trip.p, H_nz_d, pr_diag_d, diag_buffer_d,
+    launch_pdl(k_condensed, dim3(grid), dim3(256), 0, st, p->nnz_aug, p->hsrc.p, p->dsrc.p, p->tptr.p, p->trip.p, H_nz_d, pr_diag_d, diag_buffer_d,
                                       Jt_nz_d, aug_nz_d);
     B2_CUDA(cudaGetLastError());
     return B2_OK;

@@ -52,6 +52,7 @@ static inline int grid_for(int64_t n) { return (int)std::max<int64_t>(1, std::mi
 __global__ void k_set_aug_diagonal(int64_t n_tot, const int32_t* __restrict__ lbpos, const int32_t* __restrict__ ubpos,
                                    const double* __restrict__ reg, const double* __restrict__ ll, const double* __restrict__ ld,
                                    const double* __restrict__ ul, const double* __restrict__ ud, double* __restrict__ pr) {
+    pdl_sync();
     GRID_STRIDE(i, n_tot) {
         double v = reg[i];
         const int p = lbpos[i], q = ubpos[i];
@@ -64,7 +65,7 @@ extern "C" int b2_set_aug_diagonal(b2_bounds* b, const double* reg_d, const doub
                                    const double* u_lower_d, const double* u_diag_d, double* pr_diag_d, void* stream) {
     if (!b || !reg_d || !pr_diag_d) { set_error("b2_set_aug_diagonal: invalid argument"); return B2_ERR_INVALID; }
     if (b->n_tot == 0) return B2_OK;
-    k_set_aug_diagonal<<<grid_for(b->n_tot), 256, 0, as_stream(stream)>>>(b->n_tot, b->lbpos.p, b->ubpos.p, reg_d, l_lower_d, l_diag_d,
+    launch_pdl(k_set_aug_diagonal, dim3(grid_for(b->n_tot)), dim3(256), 0, as_stream(stream), b->n_tot, b->lbpos.p, b->ubpos.p, reg_d, l_lower_d, l_diag_d,
                                                                          u_lower_d, u_diag_d, pr_diag_d);
     B2_CUDA(cudaGetLastError());
     return B2_OK;
@@ -110,6 +111,7 @@ extern "C" int b2_reduce_rhs(b2_bounds* b, int64_t m, const double* l_diag_d, co
 __global__ void k_finish_aug_solve(int64_t n_tot, int64_t m, int64_t nlb, int64_t nub, const int64_t* __restrict__ ind_lb,
                                    const int64_t* __restrict__ ind_ub, const double* __restrict__ ll, const double* __restrict__ ul,
                                    const double* __restrict__ ld, const double* __restrict__ ud, double* __restrict__ w) {
+    pdl_sync();
     double* dlb = w + n_tot + m;
     double* dub = dlb + nlb;
     GRID_STRIDE(t, nlb + nub) {
@@ -124,7 +126,7 @@ extern "C" int b2_finish_aug_solve(b2_bounds* b, int64_t m, const double* l_lowe
                                    const double* l_diag_d, const double* u_diag_d, double* w_d, void* stream) {
     if (!b || !w_d) { set_error("b2_finish_aug_solve: invalid argument"); return B2_ERR_INVALID; }
     if (b->nlb + b->nub == 0) return B2_OK;
-    k_finish_aug_solve<<<grid_for(b->nlb + b->nub), 256, 0, as_stream(stream)>>>(b->n_tot, m, b->nlb, b->nub, b->ind_lb.p, b->ind_ub.p,
+    launch_pdl(k_finish_aug_solve, dim3(grid_for(b->nlb + b->nub)), dim3(256), 0, as_stream(stream), b->n_tot, m, b->nlb, b->nub, b->ind_lb.p, b->ind_ub.p,
                                                                                l_lower_d, u_lower_d, l_diag_d, u_diag_d, w_d);
     B2_CUDA(cudaGetLastError());
     return B2_OK;
@@ -296,6 +298,7 @@ extern "C" int b2_kktmul(b2_bounds* b, int64_t m, const double* reg_d, const dou
 __global__ void k_cond_pre1(int64_t n, int64_t m, int64_t nlb, const int32_t* __restrict__ lbpos, const int32_t* __restrict__ ubpos,
                             const double* __restrict__ ld, const double* __restrict__ ud, const double* __restrict__ pr,
                             const double* __restrict__ D, double* __restrict__ buffer, double* __restrict__ w) {
+    pdl_sync();
     const int64_t n_tot = n + m;
     const double* wzl = w + n_tot + m;
     const double* wzu = wzl + nlb;
@@ -313,11 +316,13 @@ __global__ void k_cond_pre1(int64_t n, int64_t m, int64_t nlb, const int32_t* __
 }
 __global__ void k_cond_pre2(int64_t n, const int32_t* rowptr, const int32_t* colidx, const int32_t* valmap, const double* __restrict__ nz,
                             const double* __restrict__ buffer, double* w) {
+    pdl_sync();
     GRID_STRIDE(i, n) w[i] += row_dot(rowptr, colidx, valmap, nz, buffer, i);
 }
 __global__ void k_cond_post1(int64_t n, int64_t m, const int32_t* colptr, const int32_t* rowval, const double* __restrict__ nz,
                              const double* __restrict__ pr, const double* __restrict__ D, const double* __restrict__ buffer,
                              double* w) {
+    pdl_sync();
     GRID_STRIDE(j, m) {
         const double b2v = col_dot(colptr, rowval, nz, w, j);      // (Jt' * wx)_j ; wx = w[0:n]
         const double wz = -buffer[j] + D[j] * b2v;
@@ -333,8 +338,8 @@ extern "C" int b2_condensed_solve_pre(b2_bounds* b, b2_spmv_plan* jt, int64_t n,
         return B2_ERR_INVALID;
     }
     cudaStream_t st = as_stream(stream);
-    k_cond_pre1<<<grid_for(n + m), 256, 0, st>>>(n, m, b->nlb, b->lbpos.p, b->ubpos.p, l_diag_d, u_diag_d, pr_diag_d, diag_buffer_d, buffer_d, w_d);
-    k_cond_pre2<<<grid_for(n), 256, 0, st>>>(n, jt->rowptr.p, jt->colidx.p, jt->valmap.p, jt_nz_d, buffer_d, w_d);
+    launch_pdl(k_cond_pre1, dim3(grid_for(n + m)), dim3(256), 0, st, n, m, b->nlb, b->lbpos.p, b->ubpos.p, l_diag_d, u_diag_d, pr_diag_d, diag_buffer_d, buffer_d, w_d);
+    launch_pdl(k_cond_pre2, dim3(grid_for(n)), dim3(256), 0, st, n, jt->rowptr.p, jt->colidx.p, jt->valmap.p, jt_nz_d, buffer_d, w_d);
     B2_CUDA(cudaGetLastError());
     return B2_OK;
 }
@@ -344,7 +349,7 @@ extern "C" int b2_condensed_solve_post(b2_bounds* b, b2_spmv_plan* jt, int64_t n
                                        const double* buffer_d, double* w_d, void* stream) {
     if (!b || !jt || !w_d || !buffer_d || b->n_tot != n + m) { set_error("b2_condensed_solve_post: invalid argument"); return B2_ERR_INVALID; }
     cudaStream_t st = as_stream(stream);
-    if (m > 0) k_cond_post1<<<grid_for(m), 256, 0, st>>>(n, m, jt->colptr.p, jt->rowval.p, jt_nz_d, pr_diag_d, diag_buffer_d, buffer_d, w_d);
+    if (m > 0) launch_pdl(k_cond_post1, dim3(grid_for(m)), dim3(256), 0, st, n, m, jt->colptr.p, jt->rowval.p, jt_nz_d, pr_diag_d, diag_buffer_d, buffer_d, w_d);
     B2_CUDA(cudaGetLastError());
     return b2_finish_aug_solve(b, m, l_lower_d, u_lower_d, l_diag_d, u_diag_d, w_d, stream);
 }
@@ -362,6 +367,7 @@ __device__ __forceinline__ void norm_inf_commit(double mx, unsigned long long* o
     if ((threadIdx.x & 31) == 0) atomicMax(out, (unsigned long long)__double_as_longlong(mx));
 }
 __global__ void k_cond_mul(CondMulArgs c, KktMulArgs a, const double* __restrict__ x, double* __restrict__ w, unsigned long long* norm_out) {
+    pdl_sync();
     const int64_t n = c.n, m = c.m;
     double mx = 0.0;
     const double* xs = x + n;
@@ -400,7 +406,7 @@ extern "C" int b2_condensed_kkt_mul_norm(b2_bounds* b, b2_spmv_plan* hess, b2_sp
     c.h_nz = hess_nz_d; c.j_nz = jt_nz_d;
     KktMulArgs a = make_kktmul(b, m, reg_d, du_diag_d, l_lower_d, u_lower_d, l_diag_d, u_diag_d, alpha, beta);
     const int64_t tot = a.n_tot + a.m + a.nlb + a.nub;
-    k_cond_mul<<<grid_for(tot), 256, 0, as_stream(stream)>>>(c, a, x_d, w_d, (unsigned long long*)norm_inf_d);
+    launch_pdl(k_cond_mul, dim3(grid_for(tot)), dim3(256), 0, as_stream(stream), c, a, x_d, w_d, (unsigned long long*)norm_inf_d);
     B2_CUDA(cudaGetLastError());
     return B2_OK;
 }
@@ -423,6 +429,7 @@ __global__ void k_norm_inf(int64_t n, const double* __restrict__ x, unsigned lon
 // the vector part of one Richardson step (src/LinearSolvers/backsolve.jl:45-48) in one pass: x += w ; w = b ; ||x||_inf
 __global__ void k_richardson_update(int64_t n, const double* __restrict__ b, double* __restrict__ w, double* __restrict__ x,
                                     unsigned long long* norm_x) {
+    pdl_sync();
     double mx = 0.0;
     GRID_STRIDE(i, n) {
         const double xi = x[i] + w[i];
@@ -433,11 +440,33 @@ __global__ void k_richardson_update(int64_t n, const double* __restrict__ b, dou
     }
     norm_inf_commit(mx, norm_x);
 }
+// start of solve_refine! (backsolve.jl:36-44) in one pass: ||b||_inf ; x = 0 ; w = b
+__global__ void k_richardson_begin(int64_t n, const double* __restrict__ b, double* __restrict__ w, double* __restrict__ x,
+                                   unsigned long long* norm_b) {
+    pdl_sync();
+    double mx = 0.0;
+    GRID_STRIDE(i, n) {
+        const double bi = b[i];
+        w[i] = bi;
+        x[i] = 0.0;
+        const double v = fabs(bi);
+        if (v > mx || v != v) mx = v;
+    }
+    norm_inf_commit(mx, norm_b);
+}
+extern "C" int b2_richardson_begin(int64_t n, const double* b_d, double* w_d, double* x_d, double* norm_b_d, void* stream) {
+    if (n < 0 || !norm_b_d || (n && (!b_d || !w_d || !x_d))) { set_error("b2_richardson_begin: invalid argument"); return B2_ERR_INVALID; }
+    cudaStream_t st = as_stream(stream);
+    B2_CUDA(cudaMemsetAsync(norm_b_d, 0, sizeof(double), st));
+    if (n) k_richardson_begin<<<grid_for(n), 256, 0, st>>>(n, b_d, w_d, x_d, (unsigned long long*)norm_b_d);
+    B2_CUDA(cudaGetLastError());
+    return B2_OK;
+}
 extern "C" int b2_richardson_update(int64_t n, const double* b_d, double* w_d, double* x_d, double* norms_d, void* stream) {
     if (n < 0 || !norms_d || (n && (!b_d || !w_d || !x_d))) { set_error("b2_richardson_update: invalid argument"); return B2_ERR_INVALID; }
     cudaStream_t st = as_stream(stream);
     B2_CUDA(cudaMemsetAsync(norms_d, 0, 2 * sizeof(double), st));
-    if (n) k_richardson_update<<<grid_for(n), 256, 0, st>>>(n, b_d, w_d, x_d, (unsigned long long*)(norms_d + 1));
+    if (n) launch_pdl(k_richardson_update, dim3(grid_for(n)), dim3(256), 0, st, n, b_d, w_d, x_d, (unsigned long long*)(norms_d + 1));
     B2_CUDA(cudaGetLastError());
     return B2_OK;
 }

@@ -7,6 +7,7 @@
 // parent (pull + fixed child order => deterministic, no atomics); the backward sweep gathers already-final
 // ancestor values.  x lives in permuted order in `xp`.
 #pragma once
+#include "common.cuh"
 #include "front_kernels.cuh"
 
 namespace b2 {
@@ -25,9 +26,11 @@ struct SolveArgs {
 };
 
 __global__ void k_perm_in(int n, const int32_t* __restrict__ perm, const double* __restrict__ x, double* __restrict__ xp) {
+    pdl_sync();
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) xp[i] = x[perm[i]];
 }
 __global__ void k_perm_out(int n, const int32_t* __restrict__ perm, const double* __restrict__ xp, double* __restrict__ x) {
+    pdl_sync();
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) x[perm[i]] = xp[i];
 }
 // masked variant for the multi-GPU back-substitution: only rows this rank finalises are written, others zeroed

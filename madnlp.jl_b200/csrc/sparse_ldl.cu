@@ -200,7 +200,7 @@ int64_t enqueue_solve(b2_solver* s, int ph, bool forward, cudaStream_t st) {
     int64_t nl = 0;
     const Phase& P = s->phase[ph];
     // level kernels are launched programmatically dependent on their predecessor (see warp_kernels.cuh: pdl_wait)
-    static const bool pdl = [] { const char* e = getenv("B2_PDL"); return !(e && e[0] == '0'); }();
+    const bool pdl = pdl_enabled();
     cudaLaunchAttribute pattr[1];
     pattr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     pattr[0].val.programmaticStreamSerializationAllowed = 1;
@@ -808,7 +808,7 @@ int b2_solve_fwd_local(b2_solver* s, double* x_d, void* stream) {
     cudaStream_t st = as_stream(stream);
     const int n = s->S.n;
     const int grid = std::min(4 * sm_count(), (n + 255) / 256);
-    k_perm_in<<<grid, 256, 0, st>>>(n, s->d_perm.p, x_d, s->d_xp.p);
+    launch_pdl(k_perm_in, dim3(grid), dim3(256), 0, st, n, s->d_perm.p, x_d, s->d_xp.p);
     if (s->opt.n_parts > 1 && s->exch_cbv > 0) B2_CUDA(cudaMemsetAsync(s->d_cbv.p, 0, (size_t)s->exch_cbv * sizeof(double), st));
     return run_solve_phase(s, 0, true, st);
 }
@@ -829,7 +829,7 @@ int b2_solve_bwd_local(b2_solver* s, double* x_d, void* stream) {
     const int n = s->S.n;
     const int grid = std::min(4 * sm_count(), (n + 255) / 256);
     if (s->opt.n_parts > 1) k_perm_out_masked<<<grid, 256, 0, st>>>(n, s->d_perm.p, s->d_mask_p.p, s->d_xp.p, x_d);
-    else k_perm_out<<<grid, 256, 0, st>>>(n, s->d_perm.p, s->d_xp.p, x_d);
+    else launch_pdl(k_perm_out, dim3(grid), dim3(256), 0, st, n, s->d_perm.p, s->d_xp.p, x_d);
     B2_CUDA(cudaGetLastError());
     return B2_OK;
 }

@@ -12,6 +12,7 @@
 //     kernel launch; data handed from child to parent front travels through global memory (same SM, ordered by
 //     the barrier), so no pointer in here is const/__restrict__ for buffers written by these kernels.
 #pragma once
+#include "common.cuh"
 #include "front_kernels.cuh"
 #include "solve_kernels.cuh"
 
@@ -276,8 +277,7 @@ __global__ void __launch_bounds__(TeamsPerCta<NW>::value * NW * 32) k_factor_war
 // Programmatic dependent launch: a level's kernel is launched while the previous level still runs.  Everything that is
 // CONSTANT during a solve (descriptors, index lists, the factor panels) is fetched before pdl_wait(); only the values the
 // previous levels produce (xp, cbv) are read after it.  Both calls are no-ops for a launch without the attribute.
-__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// (pdl_trigger / pdl_wait: common.cuh)
 
 // A front's solve is three memory round trips, whatever its number of children or pivots:
 //   (1) descriptor;  (2) child records + the whole panel (cp.async into shared memory, in flight while (3) runs) + own

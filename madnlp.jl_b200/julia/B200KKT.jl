@@ -135,4 +135,28 @@ function b200_transfer!(dest_nz::CuVector{T}, V::CuVector{T}, plan::Ptr{Cvoid}) 
         plan, pointer(dest_nz), pointer(V), stream_ptr()), FactorizationException)
 end
 
+# ---------------------------------------------------------------------------------------------------------------------
+# Optional: the vector passes of RichardsonIterator (src/LinearSolvers/backsolve.jl:36-52) as single launches.
+#   b200_richardson_begin!(b, w, x, norms)   norms[3] = ||b||_inf ; x = 0 ; w = b
+#   b200_richardson_update!(b, w, x, norms)  x += w ; w = b ; norms[1] = 0 ; norms[2] = ||x||_inf
+# followed by mul!(w, kkt, x, -1, 1) through b2_condensed_kkt_mul_norm (accumulates ||w||_inf into norms[1]); one
+# 24-byte D2H copy then carries the three norms of the stopping rule.
+# ---------------------------------------------------------------------------------------------------------------------
+function b200_richardson_begin!(b::CuVector{T}, w::CuVector{T}, x::CuVector{T}, norms::CuVector{T}) where T
+    check(ccall((:b2_richardson_begin, libb200kkt), Cint, (Int64, CuPtr{T}, CuPtr{T}, CuPtr{T}, CuPtr{T}, Ptr{Cvoid}),
+        length(b), pointer(b), pointer(w), pointer(x), pointer(norms, 3), stream_ptr()), SolveException)
+end
+function b200_richardson_update!(b::CuVector{T}, w::CuVector{T}, x::CuVector{T}, norms::CuVector{T}) where T
+    check(ccall((:b2_richardson_update, libb200kkt), Cint, (Int64, CuPtr{T}, CuPtr{T}, CuPtr{T}, CuPtr{T}, Ptr{Cvoid}),
+        length(b), pointer(b), pointer(w), pointer(x), pointer(norms), stream_ptr()), SolveException)
+end
+
+# inertia read split in two (queue more work behind factorize!, block once): b2_inertia_enqueue / b2_inertia_fetch
+inertia_enqueue!(M::B200Solver) = check(ccall((:b2_inertia_enqueue, libb200kkt), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), M.handle, stream_ptr()), FactorizationException)
+function inertia_fetch(M::B200Solver)
+    p = Ref{Int64}(0); z = Ref{Int64}(0); n = Ref{Int64}(0)
+    check(ccall((:b2_inertia_fetch, libb200kkt), Cint, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}), M.handle, p, z, n), FactorizationException)
+    return (Int(p[]), Int(z[]), Int(n[]))
+end
+
 end # module

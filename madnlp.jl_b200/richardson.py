@@ -76,9 +76,7 @@ class RichardsonIterator:
         factorisation is rejected the queued step is simply discarded (solve_refine! always restarts from x = 0)."""
         stream = capi.stream_ptr(getattr(self.kkt, "stream", None))
         n = b.values.numel()
-        check(lib.b2_norm_inf(n, ptr(b.values), ptr(self._norms[2:3]), stream))
-        x.values.zero_()
-        check(lib.b2_copy(n, ptr(b.values), ptr(w.values), stream))
+        check(lib.b2_richardson_begin(n, ptr(b.values), ptr(w.values), ptr(x.values), ptr(self._norms[2:3]), stream))   # ||b||; x = 0; w = b
         self._launch_iteration(x, b, w)
         self._started = True
 

@@ -398,7 +398,7 @@ def test_dense_matvec_kernels(rows, cols):
 
 
 def test_fused_richardson_kernels_are_bit_identical():
-    """b2_richardson_update == (axpy; copy; norm_inf) and b2_condensed_kkt_mul_norm == (mul; norm_inf), bit for bit;
+    """b2_richardson_begin/update == (norm_inf; fill; copy / axpy; copy; norm_inf) and b2_condensed_kkt_mul_norm == (mul; norm_inf), bit for bit;
     b2_copy_many == the individual copies (ragged lengths, an empty segment)."""
     _need_gpu()
     import ctypes as C
@@ -414,6 +414,9 @@ def test_fused_richardson_kernels_are_bit_identical():
     check(lib.b2_axpy(n, 1.0, w2.data_ptr(), x2.data_ptr(), st)); check(lib.b2_copy(n, b.data_ptr(), w2.data_ptr(), st))
     assert torch.equal(x, x2) and torch.equal(w, w2)
     assert float(norms[0]) == 0.0 and float(norms[1]) == float(x2.abs().max())
+    nb = torch.full((1,), 3.0, dtype=torch.float64, device="cuda")
+    check(lib.b2_richardson_begin(n, b.data_ptr(), w.data_ptr(), x.data_ptr(), nb.data_ptr(), st))     # ||b||; x = 0; w = b
+    assert torch.equal(w, b) and float(x.abs().max()) == 0.0 and float(nb[0]) == float(b.abs().max())
     # mul with fused norm on a condensed KKT system
     model, stt = W.acopf_case("case30_synth")
     it = W.ipm_iterates(model, stt, 1, seed=5)[0]
