@@ -39,7 +39,7 @@ FIELDS = ("jac", "hess", "reg", "du_diag", "l_diag", "u_diag", "l_lower", "u_low
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=48)
+    ap.add_argument("--steps", type=int, default=240)
     ap.add_argument("--warmup", type=int, default=6)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="case10000_goc")
@@ -78,7 +78,7 @@ class ClockSampler:
                         self.rows.append([x.strip() for x in out.split(",")])
                 except Exception:
                     pass
-                self._stop.wait(0.2)
+                self._stop.wait(0.02)
         self._t = threading.Thread(target=run, daemon=True)
         self._t.start()
 
