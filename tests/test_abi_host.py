@@ -100,3 +100,22 @@ def test_condensed_symbolic_matches_oracle(case):
     capi.check(lib.b2_condensed_plan_sizes(h, C.byref(a), C.byref(b), C.byref(c)))
     assert (a.value, b.value, c.value) == (len(k.dptr), len(k.hptr), len(k.jptr))
     lib.b2_condensed_plan_destroy(h)
+
+
+def test_argument_validation_never_touches_the_device():
+    """Invalid arguments are rejected on the host (B2_ERR_INVALID + message) before any CUDA call -- also on a box
+    without a GPU; numeric calls on handles that were never created fail loudly instead of falling back."""
+    E = capi.B2_ERR_INVALID
+    assert lib.b2_copy_many(17, None, None, None, None) == E and b"16" in lib.b2_last_error()
+    assert lib.b2_copy_many(1, None, None, None, None) == E
+    assert lib.b2_copy_many(0, None, None, None, None) == capi.B2_OK
+    assert lib.b2_richardson_update(-1, None, None, None, None, None) == E
+    assert lib.b2_richardson_update(4, None, None, None, None, None) == E
+    assert lib.b2_richardson_begin(4, None, None, None, None, None) == E
+    assert lib.b2d_gemv_n(4, 4, 2, None, None, None, 1.0, 0.0, None) == E          # lda < rows
+    assert lib.b2d_gemv_t(-1, 4, 4, None, None, None, 1.0, 0.0, None) == E
+    assert lib.b2d_symv_lower(4, 4, None, None, None, 1.0, 0.0, None) == E
+    assert lib.b2d_symv_lower(0, 0, None, None, None, 1.0, 0.0, None) == capi.B2_OK
+    assert lib.b2_norm_inf(3, None, None, None) == E
+    assert lib.b2_inertia_enqueue(None, None) != capi.B2_OK and lib.b2_inertia_fetch(None, None, None, None) != capi.B2_OK
+    assert lib.b2d_inertia_enqueue(None, None) != capi.B2_OK and lib.b2d_inertia_fetch(None, None, None, None) != capi.B2_OK
