@@ -1,5 +1,7 @@
-"""Multi-GPU path on real devices (skipped with < 2 GPUs): DistributedSparseSolver (subtree sharding + NCCL all-reduce of
-the separator update blocks) must give the same inertia and solution as the single-GPU solver."""
+"""Multi-GPU path on real devices: DistributedSparseSolver (subtree sharding + all-reduce of the separator update blocks)
+must give the same inertia and solution as the single-GPU solver.  With >= 2 GPUs the ranks use one device each over NCCL;
+on a single-GPU box the same two-rank protocol runs with both ranks on cuda:0 and the gloo backend (CUDA tensors), so the
+sharded factor/solve phases are exercised on real kernels wherever the GPU tests run."""
 import os
 import sys
 
@@ -11,7 +13,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, one_device=False):
     for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
         if p not in sys.path:
             sys.path.insert(0, p)
@@ -21,9 +23,13 @@ def _worker(rank, world, port, q):
     import madnlp_jl_b200 as pkg
     from madnlp_jl_b200.linear_solvers import B200SparseSolver, DeviceCSC
     from madnlp_jl_b200.parallel import DistributedSparseSolver
-    torch.cuda.set_device(rank)
-    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world,
-                            device_id=torch.device("cuda", rank))
+    if one_device:
+        torch.cuda.set_device(0)
+        dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    else:
+        torch.cuda.set_device(rank)
+        dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world,
+                                device_id=torch.device("cuda", rank))
     try:
         W = pkg.workloads
         out = []
@@ -52,14 +58,17 @@ def _worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
-def test_two_gpu_sharded_factorization_matches_single_gpu():
-    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+@pytest.mark.parametrize("mode", ["nccl_two_devices", "gloo_one_device"])
+def test_two_rank_sharded_factorization_matches_single_gpu(mode):
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    if mode == "nccl_two_devices" and torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29700 + (os.getpid() % 1000)
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    port = 29700 + (os.getpid() % 1000) + (7 if mode == "gloo_one_device" else 0)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, mode == "gloo_one_device")) for r in range(2)]
     for p in procs:
         p.start()
     for p in procs:
