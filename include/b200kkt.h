@@ -293,6 +293,37 @@ int b2_copy(int64_t n, const double* x_d, double* y_d, void* stream);
 int b2_copy_many(int32_t count, const double* const* src_d, double* const* dst_d, const int64_t* n, void* stream);
 int b2_fill(int64_t n, double v, double* x_d, void* stream);
 
+/* ------------------------------------------------------------------ IPM reductions
+ * The scalars the filter line-search reads every iteration, one single-pass kernel each; same names and argument meaning
+ * as src/IPM/kernels.jl (x, xl, xu, f, zl, zu, jacl, dx: length n_tot with +-Inf for absent bounds; zl/zu FULL length,
+ * the *_r views of the reference are taken through ind_lb / ind_ub of `b`; dzl/dzu, l: compressed lengths nlb/nub, m).
+ * The result is ONE device double at out_d (fetch several with one D2H copy).  Deterministic (fixed reduction tree),
+ * NaN-propagating min/max like Julia.  A b2_bounds object serialises its reductions: use it from one stream at a time. */
+int b2_get_alpha_max(b2_bounds* b, const double* x_d, const double* xl_d, const double* xu_d, const double* dx_d, double tau,
+                     double* out_d, void* stream);                                   /* kernels.jl:356-371 */
+int b2_get_alpha_z(b2_bounds* b, const double* zl_d, const double* zu_d, const double* dzl_d, const double* dzu_d, double tau,
+                   double* out_d, void* stream);                                     /* :373-388 */
+int b2_get_varphi(b2_bounds* b, double obj_val, const double* x_d, const double* xl_d, const double* xu_d, double mu, double* out_d,
+                  void* stream);                                                     /* :263-283 */
+int b2_get_varphi_d(b2_bounds* b, const double* f_d, const double* x_d, const double* xl_d, const double* xu_d, const double* dx_d,
+                    double mu, double* out_d, void* stream);                         /* :341-354 */
+int b2_get_inf_du(b2_bounds* b, const double* f_d, const double* zl_d, const double* zu_d, const double* jacl_d, double sd,
+                  double* out_d, void* stream);                                      /* :285-291 */
+int b2_get_inf_compl(b2_bounds* b, const double* x_d, const double* xl_d, const double* xu_d, const double* zl_d, const double* zu_d,
+                     double mu, double sc, double* out_d, void* stream);             /* :293-303 */
+int b2_get_average_complementarity(b2_bounds* b, const double* x_d, const double* xl_d, const double* xu_d, const double* zl_d,
+                                   const double* zu_d, double* out_d, void* stream); /* :305-314 */
+int b2_get_min_complementarity(b2_bounds* b, const double* x_d, const double* xl_d, const double* xu_d, const double* zl_d,
+                               const double* zu_d, double* out_d, void* stream);     /* :322-333 */
+int b2_get_rel_search_norm(b2_bounds* b, int64_t n, const double* x_d, const double* dx_d, double* out_d, void* stream);   /* :675-681 */
+int b2_get_sd(b2_bounds* b, int64_t m, const double* l_d, const double* zl_d, const double* zu_d, double s_max, double* out_d,
+              void* stream);                                                         /* :684-689 */
+int b2_get_sc(b2_bounds* b, const double* zl_d, const double* zu_d, double s_max, double* out_d, void* stream);            /* :690-695 */
+/* set_aug_rhs! (:113-130): p = [ -f + zl - zu - jacl | -c | (xl_r - x_lr) zl_r + mu | (xu_r - x_ur) zu_r - mu ] */
+int b2_set_aug_rhs(b2_bounds* b, int64_t m, const double* x_d, const double* xl_d, const double* xu_d, const double* f_d,
+                   const double* zl_d, const double* zu_d, const double* jacl_d, const double* c_d, double mu, double* p_d, void* stream);
+
+
 #ifdef __cplusplus
 }
 #endif

@@ -145,6 +145,18 @@ PROTOTYPES = {
     "b2_condensed_solve_post": (C.c_int, [_p, _p, _i64, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "b2_condensed_kkt_mul": (C.c_int, [_p, _p, _p, _i64, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _f64, _f64, _p, _p, _p]),
     "b2_condensed_kkt_mul_norm": (C.c_int, [_p, _p, _p, _i64, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _f64, _f64, _p, _p, _p, _p]),
+    "b2_get_alpha_max": (C.c_int, [_p, _p, _p, _p, _p, _f64, _p, _p]),
+    "b2_get_alpha_z": (C.c_int, [_p, _p, _p, _p, _p, _f64, _p, _p]),
+    "b2_get_varphi": (C.c_int, [_p, _f64, _p, _p, _p, _f64, _p, _p]),
+    "b2_get_varphi_d": (C.c_int, [_p, _p, _p, _p, _p, _p, _f64, _p, _p]),
+    "b2_get_inf_du": (C.c_int, [_p, _p, _p, _p, _p, _f64, _p, _p]),
+    "b2_get_inf_compl": (C.c_int, [_p, _p, _p, _p, _p, _p, _f64, _f64, _p, _p]),
+    "b2_get_average_complementarity": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p]),
+    "b2_get_min_complementarity": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p]),
+    "b2_get_rel_search_norm": (C.c_int, [_p, _i64, _p, _p, _p, _p]),
+    "b2_get_sd": (C.c_int, [_p, _i64, _p, _p, _p, _f64, _p, _p]),
+    "b2_get_sc": (C.c_int, [_p, _p, _p, _f64, _p, _p]),
+    "b2_set_aug_rhs": (C.c_int, [_p, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _f64, _p, _p]),
     "b2_richardson_begin": (C.c_int, [_i64, _p, _p, _p, _p, _p]),
     "b2_richardson_update": (C.c_int, [_i64, _p, _p, _p, _p, _p]),
     "b2_copy_many": (C.c_int, [_i32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(_i64), _p]),

@@ -8,15 +8,10 @@
 #include <cstring>
 #include <vector>
 
+#include "bounds.cuh"
 #include "common.cuh"
 
 using namespace b2;
-
-struct b2_bounds {
-    int64_t n_tot = 0, nlb = 0, nub = 0;
-    DevBuf<int64_t> ind_lb, ind_ub;
-    DevBuf<int32_t> lbpos, ubpos;   // [n_tot] position in ind_lb / ind_ub or -1
-};
 
 extern "C" int b2_bounds_create(int64_t n_tot, int64_t nlb, int64_t nub, const int64_t* ind_lb_h, const int64_t* ind_ub_h,
                                 b2_bounds** out) {
@@ -36,7 +31,9 @@ extern "C" int b2_bounds_create(int64_t n_tot, int64_t nlb, int64_t nub, const i
     auto* b = new b2_bounds();
     b->n_tot = n_tot; b->nlb = nlb; b->nub = nub;
     if (b->ind_lb.upload(ind_lb_h, nlb) != cudaSuccess || b->ind_ub.upload(ind_ub_h, nub) != cudaSuccess ||
-        b->lbpos.upload(lp.data(), lp.size()) != cudaSuccess || b->ubpos.upload(up.data(), up.size()) != cudaSuccess) {
+        b->lbpos.upload(lp.data(), lp.size()) != cudaSuccess || b->ubpos.upload(up.data(), up.size()) != cudaSuccess ||
+        b->red_part.alloc(B2_RED_BLOCKS) != cudaSuccess || b->red_ticket.alloc(1) != cudaSuccess ||
+        cudaMemset(b->red_ticket.p, 0, sizeof(unsigned)) != cudaSuccess) {
         delete b;
         return cuda_fail(cudaGetLastError(), "bounds upload", __FILE__, __LINE__);
     }

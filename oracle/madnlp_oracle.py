@@ -846,3 +846,106 @@ def test_kkt_system(kkt, model, dense=False):
     kkt.mul(y, x)
     inertia = kkt.linear_solver.inertia() if kkt.linear_solver.is_inertia() else None
     return x, y, inertia
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# IPM reductions and set_aug_rhs!: scalar restatements of src/IPM/kernels.jl, used to check the single-pass
+# device reductions.  Arguments as in the reference: x, xl, xu, f, zl, zu, jacl, dx are full primal vectors (+-inf for
+# absent bounds); ind_lb / ind_ub are the 0-based index sets of the finite bounds; dzl, dzu, l are compressed.
+# ------------------------------------------------------------------------------------------------------------------
+def _jl_min(*vals):
+    """Julia's min: NaN-propagating"""
+    out = np.inf
+    for v in vals:
+        if np.isnan(v) or np.isnan(out):
+            out = np.nan
+        else:
+            out = min(out, v)
+    return out
+
+
+def get_alpha_max(x, xl, xu, dx, tau):
+    """src/IPM/kernels.jl:356-371"""
+    alpha = 1.0
+    for i in range(len(x)):
+        a = (-x[i] + xl[i]) * tau / dx[i] if dx[i] < 0 else np.inf
+        c = (-x[i] + xu[i]) * tau / dx[i] if dx[i] > 0 else np.inf
+        alpha = _jl_min(alpha, a, c)
+    return alpha
+
+
+def get_alpha_z(zl_r, zu_r, dzl, dzu, tau):
+    """src/IPM/kernels.jl:373-388"""
+    alpha = 1.0
+    for i in range(len(zl_r)):
+        alpha = _jl_min(alpha, (-zl_r[i]) * tau / dzl[i] if dzl[i] < 0 else np.inf)
+    for i in range(len(zu_r)):
+        alpha = _jl_min(alpha, (-zu_r[i]) * tau / dzu[i] if dzu[i] < 0 else np.inf)
+    return alpha
+
+
+def get_varphi(obj_val, x_lr, xl_r, xu_r, x_ur, mu):
+    """src/IPM/kernels.jl:263-283"""
+    def one(a, b):
+        d = a - b
+        return np.inf if d < 0 else (-mu * np.log(d) if d > 0 else np.inf)
+    v = obj_val
+    for a, b in zip(x_lr, xl_r):
+        v += one(a, b)
+    for a, b in zip(xu_r, x_ur):
+        v += one(a, b)
+    return v
+
+
+def get_varphi_d(f, x, xl, xu, dx, mu):
+    """src/IPM/kernels.jl:341-354"""
+    return float(np.sum((f - mu / (x - xl) + mu / (xu - x)) * dx))
+
+
+def get_inf_du(f, zl, zu, jacl, sd):
+    """src/IPM/kernels.jl:285-291"""
+    return float(np.max(np.abs(f - zl + zu + jacl), initial=0.0)) / sd
+
+
+def get_inf_compl(x_lr, xl_r, zl_r, xu_r, x_ur, zu_r, mu, sc):
+    """src/IPM/kernels.jl:293-303"""
+    a = np.max(np.abs((x_lr - xl_r) * zl_r - mu), initial=0.0)
+    b = np.max(np.abs((xu_r - x_ur) * zu_r - mu), initial=0.0)
+    return float(max(a, b)) / sc
+
+
+def get_average_complementarity(x_lr, xl_r, zl_r, x_ur, xu_r, zu_r):
+    """src/IPM/kernels.jl:305-314"""
+    n = len(x_lr) + len(x_ur)
+    if n == 0:
+        return 0.0
+    return float((np.dot(x_lr, zl_r) - np.dot(xl_r, zl_r) + np.dot(xu_r, zu_r) - np.dot(x_ur, zu_r)) / n)
+
+
+def get_min_complementarity(x_lr, xl_r, zl_r, x_ur, xu_r, zu_r):
+    """src/IPM/kernels.jl:322-333"""
+    return float(min(np.min((x_lr - xl_r) * zl_r, initial=np.inf), np.min((xu_r - x_ur) * zu_r, initial=np.inf)))
+
+
+def get_rel_search_norm(x, dx):
+    """src/IPM/kernels.jl:675-681"""
+    return float(np.max(np.abs(dx) / (1.0 + np.abs(x)), initial=0.0))
+
+
+def get_sd(l, zl_r, zu_r, s_max):
+    """src/IPM/kernels.jl:684-689"""
+    return max(s_max, (np.abs(l).sum() + np.abs(zl_r).sum() + np.abs(zu_r).sum()) / max(1, len(l) + len(zl_r) + len(zu_r))) / s_max
+
+
+def get_sc(zl_r, zu_r, s_max):
+    """src/IPM/kernels.jl:690-695"""
+    return max(s_max, (np.abs(zl_r).sum() + np.abs(zu_r).sum()) / max(1, len(zl_r) + len(zu_r))) / s_max
+
+
+def set_aug_rhs(x, xl, xu, f, zl, zu, jacl, c, mu, ind_lb, ind_ub):
+    """src/IPM/kernels.jl:113-130 -> [px | py | pzl | pzu]"""
+    px = -f + zl - zu - jacl
+    py = -c
+    pzl = (xl[ind_lb] - x[ind_lb]) * zl[ind_lb] + mu
+    pzu = (xu[ind_ub] - x[ind_ub]) * zu[ind_ub] - mu
+    return np.concatenate([px, py, pzl, pzu])

@@ -437,3 +437,72 @@ def test_fused_richardson_kernels_are_bit_identical():
     check(lib.b2_copy_many(cnt, (C.c_void_p * cnt)(*[s.data_ptr() for s in src]), (C.c_void_p * cnt)(*[d.data_ptr() for d in dst]),
                            (C.c_int64 * cnt)(*lens), st))
     assert all(torch.equal(s, d) for s, d in zip(src, dst))
+
+
+@pytest.mark.parametrize("n_tot,m,seed", [(0, 0, 0), (7, 3, 1), (1000, 400, 2), (300001, 120007, 3)])
+def test_ipm_reductions_match_the_reference_formulas(n_tot, m, seed):
+    """the line-search scalars (src/IPM/kernels.jl:263-388,675-695) and set_aug_rhs! (:113-130) as
+    single-pass device kernels vs their scalar restatement.  min/max results: exact (same terms, order-free);
+    sums: relative 1e-12 of the sum of magnitudes (different association); twice the same call: bit-identical."""
+    _need_gpu()
+    import ctypes as C
+    from madnlp_jl_b200.capi import lib, check
+    rng = np.random.default_rng(seed)
+    st = torch.cuda.current_stream().cuda_stream
+    has_lb = rng.random(n_tot) < 0.6; has_ub = rng.random(n_tot) < 0.5
+    ind_lb = np.flatnonzero(has_lb).astype(np.int64); ind_ub = np.flatnonzero(has_ub).astype(np.int64)
+    nlb, nub = len(ind_lb), len(ind_ub)
+    x = rng.standard_normal(n_tot)
+    xl = np.where(has_lb, x - rng.uniform(1e-6, 2.0, n_tot), -np.inf)
+    xu = np.where(has_ub, x + rng.uniform(1e-6, 2.0, n_tot), np.inf)
+    zl = np.where(has_lb, rng.uniform(1e-8, 3.0, n_tot), 0.0); zu = np.where(has_ub, rng.uniform(1e-8, 3.0, n_tot), 0.0)
+    f, jacl, dx = (rng.standard_normal(n_tot) for _ in range(3))
+    dzl, dzu = rng.standard_normal(nlb), rng.standard_normal(nub)
+    c, l = rng.standard_normal(m), rng.standard_normal(m)
+    mu, tau, sd, sc, s_max, obj = 1e-3, 0.99, 1.7, 2.3, 100.0, 4.25
+    h = C.c_void_p()
+    check(lib.b2_bounds_create(n_tot, nlb, nub, ind_lb.ctypes.data, ind_ub.ctypes.data, C.byref(h)))
+    D = {k: _dev(v) for k, v in dict(x=x, xl=xl, xu=xu, zl=zl, zu=zu, f=f, jacl=jacl, dx=dx, dzl=dzl, dzu=dzu, c=c, l=l).items()}
+    P = lambda k: D[k].data_ptr()
+    out = torch.zeros(16, dtype=torch.float64, device="cuda")
+    O = lambda k: out[k:k + 1].data_ptr()
+
+    def run():
+        check(lib.b2_get_alpha_max(h, P("x"), P("xl"), P("xu"), P("dx"), tau, O(0), st))
+        check(lib.b2_get_alpha_z(h, P("zl"), P("zu"), P("dzl"), P("dzu"), tau, O(1), st))
+        check(lib.b2_get_varphi(h, obj, P("x"), P("xl"), P("xu"), mu, O(2), st))
+        check(lib.b2_get_varphi_d(h, P("f"), P("x"), P("xl"), P("xu"), P("dx"), mu, O(3), st))
+        check(lib.b2_get_inf_du(h, P("f"), P("zl"), P("zu"), P("jacl"), sd, O(4), st))
+        check(lib.b2_get_inf_compl(h, P("x"), P("xl"), P("xu"), P("zl"), P("zu"), mu, sc, O(5), st))
+        check(lib.b2_get_average_complementarity(h, P("x"), P("xl"), P("xu"), P("zl"), P("zu"), O(6), st))
+        check(lib.b2_get_min_complementarity(h, P("x"), P("xl"), P("xu"), P("zl"), P("zu"), O(7), st))
+        check(lib.b2_get_rel_search_norm(h, n_tot, P("x"), P("dx"), O(8), st))
+        check(lib.b2_get_sd(h, m, P("l"), P("zl"), P("zu"), s_max, O(9), st))
+        check(lib.b2_get_sc(h, P("zl"), P("zu"), s_max, O(10), st))
+        return out.cpu().numpy().copy()
+
+    g = run()
+    assert (run() == g).all()                                               # deterministic reduction tree
+    xlr, xur = x[ind_lb], x[ind_ub]
+    ref = [o.get_alpha_max(x, xl, xu, dx, tau), o.get_alpha_z(zl[ind_lb], zu[ind_ub], dzl, dzu, tau),
+           o.get_varphi(obj, xlr, xl[ind_lb], xu[ind_ub], xur, mu), o.get_varphi_d(f, x, xl, xu, dx, mu),
+           o.get_inf_du(f, zl, zu, jacl, sd), o.get_inf_compl(xlr, xl[ind_lb], zl[ind_lb], xu[ind_ub], xur, zu[ind_ub], mu, sc),
+           o.get_average_complementarity(xlr, xl[ind_lb], zl[ind_lb], xur, xu[ind_ub], zu[ind_ub]),
+           o.get_min_complementarity(xlr, xl[ind_lb], zl[ind_lb], xur, xu[ind_ub], zu[ind_ub]),
+           o.get_rel_search_norm(x, dx), o.get_sd(l, zl[ind_lb], zu[ind_ub], s_max), o.get_sc(zl[ind_lb], zu[ind_ub], s_max)]
+    for k in (0, 1, 4, 5, 7, 8):                                            # min / max: exact
+        assert g[k] == ref[k], (k, g[k], ref[k])
+    mags = {2: abs(obj) + np.abs(mu * np.log(np.concatenate([xlr - xl[ind_lb], xu[ind_ub] - xur]))).sum() if nlb + nub else abs(obj),
+            3: np.abs((f - mu / (x - xl) + mu / (xu - x)) * dx).sum(), 6: 3.0 * 2.0, 9: 1.0 + g[9], 10: 1.0 + g[10]}
+    for k in (2, 3, 6, 9, 10):                                              # sums: association differs
+        assert abs(g[k] - ref[k]) <= 1e-12 * (mags[k] + 1.0), (k, g[k], ref[k])
+    # set_aug_rhs!: elementwise, bit-exact
+    p = torch.zeros(n_tot + m + nlb + nub, dtype=torch.float64, device="cuda")
+    check(lib.b2_set_aug_rhs(h, m, P("x"), P("xl"), P("xu"), P("f"), P("zl"), P("zu"), P("jacl"), P("c"), mu, p.data_ptr(), st))
+    assert (p.cpu().numpy() == o.set_aug_rhs(x, xl, xu, f, zl, zu, jacl, c, mu, ind_lb, ind_ub)).all()
+    # a NaN anywhere propagates through min like Julia's
+    if n_tot > 3:
+        D["dx"][3] = float("nan")
+        check(lib.b2_get_alpha_max(h, P("x"), P("xl"), P("xu"), P("dx"), tau, O(0), st))
+        assert np.isnan(float(out[0])) == np.isnan(o.get_alpha_max(x, xl, xu, np.where(np.arange(n_tot) == 3, np.nan, dx), tau))
+    lib.b2_bounds_destroy(h)
