@@ -112,3 +112,30 @@ def test_committed_golden_fixture_matches_oracle():
     xc, yc, ic = o.test_kkt_system(kc, o.HS15Model)
     assert np.abs(xc.full() - np.array(g["hs15_condensed"]["solve_kkt_of_ones"])).max() < 1e-14
     assert np.abs(kc.aug_nz - np.array(g["hs15_condensed"]["nzval"])).max() == 0.0
+
+
+def test_ipm_reduction_restatements_known_answers():
+    """Hand-derived values for the restated line-search scalars (src/IPM/kernels.jl:113-130,263-388,675-695): two variables,
+    x = (0.5, 1), bounds 0 <= x1 <= 1, x2 <= 3 (ind_lb = [0], ind_ub = [0, 1])."""
+    import numpy as np
+    x = np.array([0.5, 1.0]); xl = np.array([0.0, -np.inf]); xu = np.array([1.0, 3.0])
+    dx = np.array([-1.0, 4.0]); f = np.array([2.0, -1.0]); jacl = np.array([0.25, 0.5])
+    zl = np.array([0.2, 0.0]); zu = np.array([0.4, 0.1])
+    ind_lb = np.array([0]); ind_ub = np.array([0, 1])
+    mu, tau = 0.1, 0.99
+    assert o.get_alpha_max(x, xl, xu, dx, tau) == min(1.0, 0.5 * tau / 1.0, 2.0 * tau / 4.0)
+    assert o.get_alpha_z(zl[ind_lb], zu[ind_ub], np.array([-0.4]), np.array([0.3, -0.05]), tau) == min(1.0, 0.2 * tau / 0.4, 0.1 * tau / 0.05)
+    assert np.isclose(o.get_varphi(1.0, x[ind_lb], xl[ind_lb], xu[ind_ub], x[ind_ub], mu), 1.0 - mu * (np.log(0.5) + np.log(0.5) + np.log(2.0)), rtol=0, atol=1e-15)
+    assert o.get_varphi(1.0, np.array([-1.0]), np.array([0.0]), np.array([]), np.array([]), mu) == np.inf        # infeasible slack
+    # (f - mu/(x-xl) + mu/(xu-x)) * dx : x1: (2 - 0.2 + 0.2) * -1 = -2 ; x2: (-1 - 0 + 0.05) * 4 = -3.8
+    assert np.isclose(o.get_varphi_d(f, x, xl, xu, dx, mu), -5.8, rtol=0, atol=1e-14)
+    assert np.isclose(o.get_inf_du(f, zl, zu, jacl, 2.0), max(abs(2 - 0.2 + 0.4 + 0.25), abs(-1 - 0 + 0.1 + 0.5)) / 2.0)
+    # complementarity products: lb: 0.5*0.2 = 0.1 ; ub: 0.5*0.4 = 0.2, 2*0.1 = 0.2
+    assert np.isclose(o.get_inf_compl(x[ind_lb], xl[ind_lb], zl[ind_lb], xu[ind_ub], x[ind_ub], zu[ind_ub], mu, 4.0), 0.1 / 4.0)
+    assert np.isclose(o.get_average_complementarity(x[ind_lb], xl[ind_lb], zl[ind_lb], x[ind_ub], xu[ind_ub], zu[ind_ub]), 0.5 / 3)
+    assert np.isclose(o.get_min_complementarity(x[ind_lb], xl[ind_lb], zl[ind_lb], x[ind_ub], xu[ind_ub], zu[ind_ub]), 0.1)
+    assert o.get_average_complementarity(*(np.array([]),) * 6) == 0.0 and o.get_min_complementarity(*(np.array([]),) * 6) == np.inf
+    assert o.get_rel_search_norm(x, dx) == 4.0 / 2.0
+    assert o.get_sd(np.array([3.0, -5.0]), zl[ind_lb], zu[ind_ub], 100.0) == 1.0 and o.get_sc(np.array([600.0]), np.array([]), 100.0) == 6.0
+    p = o.set_aug_rhs(x, xl, xu, f, zl, zu, jacl, np.array([0.7]), mu, ind_lb, ind_ub)
+    assert np.allclose(p, [-2 + 0.2 - 0.4 - 0.25, 1 + 0 - 0.1 - 0.5, -0.7, (0 - 0.5) * 0.2 + mu, (1 - 0.5) * 0.4 - mu, (3 - 1) * 0.1 - mu], rtol=0, atol=1e-15)
