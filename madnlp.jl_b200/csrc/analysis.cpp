@@ -9,6 +9,9 @@
 #include "analysis.hpp"
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <climits>
 #include <cstdio>
 #include <cstring>
@@ -197,6 +200,18 @@ void colcounts(int32_t n, const std::vector<int64_t>& rptr, const std::vector<in
 
 inline int64_t trap_nnz(int64_t w, int64_t f) { return w * f - w * (w - 1) / 2; }
 
+// B2_ANALYSIS_TIMING=1: print the wall time of each phase of analyse() to stderr
+struct PhaseTimer {
+    bool on;
+    std::chrono::steady_clock::time_point t0;
+    PhaseTimer() : on(getenv("B2_ANALYSIS_TIMING") != nullptr), t0(std::chrono::steady_clock::now()) {}
+    void lap(const char* what) {
+        if (!on) return;
+        const auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[b2 analyse] %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
 }  // namespace
 
 void analyse(int32_t n, const int32_t* colptr, const int32_t* rowval, const AnalysisOptions& opt,
@@ -206,6 +221,7 @@ void analyse(int32_t n, const int32_t* colptr, const int32_t* rowval, const Anal
     S.n = n;
     S.nnz_a = colptr[n];
     const int64_t nnz = colptr[n];
+    PhaseTimer timer;
 
     // ---- 1. ordering
     std::vector<int32_t> perm0;
@@ -229,6 +245,7 @@ void analyse(int32_t n, const int32_t* colptr, const int32_t* rowval, const Anal
     std::vector<int32_t> iperm(n);
     for (int32_t i = 0; i < n; ++i) iperm[perm0[i]] = i;
 
+    timer.lap("ordering");
     // ---- 1b. augmented-KKT constraint: a dual row that would be eliminated before all of its (primal) neighbours is
     //          moved to just after its earliest neighbour (its pivot is then -a^2/d instead of the raw, possibly zero,
     //          diagonal entry).  Quasi-definite / condensed matrices do not need this (kkt_n_primal = 0).
@@ -255,6 +272,7 @@ void analyse(int32_t n, const int32_t* colptr, const int32_t* rowval, const Anal
         for (int32_t i = 0; i < n; ++i) iperm[perm0[i]] = i;
     }
 
+    timer.lap("kkt ordering constraint");
     // ---- 2. etree + postorder
     std::vector<int64_t> rptr;
     std::vector<int32_t> rcol, parent, post;
@@ -265,12 +283,14 @@ void analyse(int32_t n, const int32_t* colptr, const int32_t* rowval, const Anal
     for (int32_t k = 0; k < n; ++k) perm1[k] = perm0[post[k]];
     for (int32_t i = 0; i < n; ++i) iperm[perm1[i]] = i;
 
+    timer.lap("etree + postorder");
     // ---- 3. structures under perm1
     permuted_lower_rows(n, colptr, rowval, iperm, rptr, rcol);
     etree(n, rptr, rcol, parent);
     std::vector<int64_t> cc;
     colcounts(n, rptr, rcol, parent, cc);
 
+    timer.lap("structures / colcounts");
     // ---- 4. maximal supernodes under perm1
     std::vector<int32_t> fs_first;  // first column of each fundamental/maximal supernode
     for (int32_t j = 0; j < n; ++j) {
@@ -288,6 +308,7 @@ void analyse(int32_t n, const int32_t* colptr, const int32_t* rowval, const Anal
         if (parent[last] != -1) fpar[s] = col2fs[parent[last]];
     }
 
+    timer.lap("supernodes");
     // ---- 5. relaxed amalgamation on the supernode tree
     struct Node {
         int64_t w, f, zeros;
@@ -336,6 +357,7 @@ void analyse(int32_t n, const int32_t* colptr, const int32_t* rowval, const Anal
         }
     }
 
+    timer.lap("amalgamation");
     // ---- 6. final permutation: DFS of the merged tree (subtrees first, then the node's own columns)
     std::vector<int32_t> ord2; ord2.reserve(n);
     std::vector<int32_t> sn_first;  // in final numbering
@@ -372,6 +394,7 @@ void analyse(int32_t n, const int32_t* colptr, const int32_t* rowval, const Anal
     std::vector<int32_t> col2sn(n);
     for (int32_t s = 0; s < ns; ++s) for (int32_t j = sn_first[s]; j < sn_first[s + 1]; ++j) col2sn[j] = s;
 
+    timer.lap("final permutation");
     // ---- 7. permuted lower CSC (by column) with source positions
     std::vector<int64_t> cptr(n + 1, 0);
     std::vector<int32_t> crow(nnz);
@@ -393,6 +416,7 @@ void analyse(int32_t n, const int32_t* colptr, const int32_t* rowval, const Anal
             }
     }
 
+    timer.lap("permuted CSC");
     // ---- 8. front row structures (children before parents by construction of the numbering)
     S.rows_ptr.assign(ns + 1, 0);
     S.sn_parent.assign(ns, -1);
@@ -446,6 +470,7 @@ void analyse(int32_t n, const int32_t* colptr, const int32_t* rowval, const Anal
         std::copy(kids[s].begin(), kids[s].end(), S.child_idx.begin() + S.child_ptr[s]);
     }
 
+    timer.lap("front row structures");
     // ---- 9. relative indices child -> parent front
     S.rel_ptr.assign(ns + 1, 0);
     for (int32_t s = 0; s < ns; ++s) S.rel_ptr[s + 1] = S.rel_ptr[s] + (int64_t)below[s].size();
@@ -467,6 +492,7 @@ void analyse(int32_t n, const int32_t* colptr, const int32_t* rowval, const Anal
         }
     }
 
+    timer.lap("relative indices");
     // ---- 10. A -> panel scatter map, grouped by supernode
     S.amap_ptr.assign(ns + 1, 0);
     for (int32_t s = 0; s < ns; ++s) S.amap_ptr[s + 1] = S.amap_ptr[s] + (cptr[sn_first[s + 1]] - cptr[sn_first[s]]);
@@ -492,6 +518,7 @@ void analyse(int32_t n, const int32_t* colptr, const int32_t* rowval, const Anal
             }
     }
 
+    timer.lap("scatter map");
     // ---- 11. levels
     S.sn_level.assign(ns, 0);
     for (int32_t s = 0; s < ns; ++s) {
@@ -509,6 +536,7 @@ void analyse(int32_t n, const int32_t* colptr, const int32_t* rowval, const Anal
         for (int32_t s = 0; s < ns; ++s) S.level_sn[pos[S.sn_level[s]]++] = s;
     }
 
+    timer.lap("levels");
     // ---- 12. subtree-to-rank partition
     S.owner.assign(ns, 0);
     S.top_rows = 0;
@@ -559,6 +587,7 @@ void analyse(int32_t n, const int32_t* colptr, const int32_t* rowval, const Anal
         }
     }
 
+    timer.lap("partition");
     // ---- 13. update-block offsets: blocks crossing from an owned subtree into the shared top tree first
     S.cb_off.assign(ns + 1, 0);
     {
