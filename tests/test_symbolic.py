@@ -143,3 +143,33 @@ def test_subtree_partition(parts):
     full = o.tril_to_full(cp, rv, nz, n).toarray()
     b = rng.standard_normal(n)
     assert np.abs(S.solve(b) - np.linalg.solve(full, b)).max() < 1e-9
+
+
+# ---- randomised patterns (hypothesis): arbitrary symmetric sparsity incl. disconnected graphs, dense rows, empty columns
+from hypothesis import given, settings, strategies as st_  # noqa: E402
+
+
+@settings(max_examples=150, deadline=None)
+@given(n=st_.integers(min_value=1, max_value=90), density=st_.floats(min_value=0.0, max_value=0.35),
+       n_neg=st_.integers(min_value=0, max_value=10), ordering=st_.sampled_from([0, 1, 2]),
+       nemin=st_.sampled_from([1, 8, 32]), parts=st_.sampled_from([1, 2, 3]), seed=st_.integers(min_value=0, max_value=10**6))
+def test_random_patterns_factor_and_solve(n, density, n_neg, ordering, nemin, parts, seed):
+    """Any symmetric pattern, any ordering / amalgamation / partition setting: the exported symbolic structure replayed in
+    numpy reproduces the dense solution and the exact inertia, and satisfies the structural invariants."""
+    rng = np.random.default_rng(seed)
+    n_neg = min(n_neg, n)
+    mask = np.tril(rng.random((n, n)) < density, -1)
+    if n > 3 and rng.random() < 0.3:
+        mask[-1, :-1] = True                                  # one dense row (arrowhead)
+    mask |= np.eye(n, dtype=bool)
+    rows, cols = np.nonzero(mask.T)                           # walk column by column
+    cols_, rows_ = rows, cols                                  # (mask.T nonzero gives (col, row) pairs sorted by col)
+    order = np.lexsort((rows_, cols_))
+    cols_, rows_ = cols_[order], rows_[order]
+    colptr = np.zeros(n + 1, dtype=np.int32)
+    np.add.at(colptr, cols_ + 1, 1)
+    colptr = np.cumsum(colptr).astype(np.int32)
+    rowval = rows_.astype(np.int32)
+    assert (rowval >= np.repeat(np.arange(n), np.diff(colptr))).all()          # lower triangle, sorted rows
+    nz = _well_conditioned_values(colptr, rowval, n, rng, n_neg=n_neg)
+    _check(n, colptr, rowval, nz, n_neg, tol=1e-8, ordering=ordering, nemin=nemin, n_parts=parts, part_rank=0)
