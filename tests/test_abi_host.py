@@ -119,3 +119,52 @@ def test_argument_validation_never_touches_the_device():
     assert lib.b2_norm_inf(3, None, None, None) == E
     assert lib.b2_inertia_enqueue(None, None) != capi.B2_OK and lib.b2_inertia_fetch(None, None, None, None) != capi.B2_OK
     assert lib.b2d_inertia_enqueue(None, None) != capi.B2_OK and lib.b2d_inertia_fetch(None, None, None, None) != capi.B2_OK
+
+
+from hypothesis import given, settings, strategies as st_  # noqa: E402
+
+
+@settings(max_examples=100, deadline=None)
+@given(n=st_.integers(min_value=1, max_value=40), m=st_.integers(min_value=0, max_value=50),
+       dh=st_.floats(min_value=0.0, max_value=0.5), dj=st_.floats(min_value=0.0, max_value=0.4), seed=st_.integers(0, 10**6))
+def test_condensed_symbolic_random_patterns(n, m, dh, dj, seed):
+    """b2_condensed_symbolic on arbitrary H (lower) / Jt (n x m) patterns -- empty constraint columns, empty Hessian, dense
+    columns -- gives the same lower-CSC pattern and map sizes as the restated build_condensed_aug_symbolic (condensed.jl:201-301)."""
+    rng = np.random.default_rng(seed)
+
+    def csc_of(mask):                                           # mask[row, col] -> (colptr, rowval) with sorted rows
+        nrow, ncol = mask.shape
+        cols, rows = np.nonzero(mask.T)
+        colptr = np.zeros(ncol + 1, dtype=np.int32)
+        np.add.at(colptr, cols + 1, 1)
+        return np.cumsum(colptr).astype(np.int32), rows.astype(np.int32)
+
+    hcp, hrv = csc_of(np.tril(rng.random((n, n)) < dh))
+    jcp, jrv = csc_of(rng.random((n, m)) < dj)
+    cp0, rv0, dptr, hptr, jptr = o.build_condensed_aug_symbolic(hcp, hrv, n, jcp, jrv, m)
+    h = C.c_void_p(); nnz = C.c_int64(0)
+    capi.check(lib.b2_condensed_symbolic(n, m, hcp.ctypes.data, hrv.ctypes.data if len(hrv) else None,
+                                         jcp.ctypes.data, jrv.ctypes.data if len(jrv) else None, C.byref(h), C.byref(nnz)))
+    assert nnz.value == len(rv0)
+    cp = np.zeros(n + 1, dtype=np.int32); rv = np.zeros(max(nnz.value, 1), dtype=np.int32)
+    capi.check(lib.b2_condensed_pattern(h, cp.ctypes.data, rv.ctypes.data))
+    assert (cp == cp0).all() and (rv[:nnz.value] == rv0).all()
+    a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
+    capi.check(lib.b2_condensed_plan_sizes(h, C.byref(a), C.byref(b), C.byref(c)))
+    assert (a.value, b.value, c.value) == (len(dptr), len(hptr), len(jptr))
+    lib.b2_condensed_plan_destroy(h)
+
+
+@settings(max_examples=100, deadline=None)
+@given(m=st_.integers(1, 30), n=st_.integers(1, 30), nnz=st_.integers(0, 200), seed=st_.integers(0, 10**6))
+def test_coo_to_csc_random(m, n, nnz, seed):
+    """b2_coo_to_csc on arbitrary COO lists (duplicates, empty columns, any order) == src/matrixtools.jl:55-95 restated."""
+    rng = np.random.default_rng(seed)
+    I = rng.integers(0, m, nnz); J = rng.integers(0, n, nnz)
+    cp0, rv0, mp0 = o.coo_to_csc(I, J, m, n)
+    I32, J32 = I.astype(np.int32), J.astype(np.int32)
+    cp = np.zeros(n + 1, dtype=np.int32); rv = np.zeros(max(nnz, 1), dtype=np.int32); mp = np.zeros(max(nnz, 1), dtype=np.int64)
+    k = C.c_int64(0)
+    capi.check(lib.b2_coo_to_csc(m, n, nnz, I32.ctypes.data if nnz else None, J32.ctypes.data if nnz else None,
+                                 cp.ctypes.data, rv.ctypes.data, mp.ctypes.data, C.byref(k)))
+    assert k.value == len(rv0) and (cp == cp0).all() and (rv[:k.value] == rv0).all() and (mp[:nnz] == mp0).all()
