@@ -5,17 +5,21 @@ A "step" = one pass of the hot path over one synthetic interior-point iterate, i
 `regular!` (src/IPM/solver.jl:216-298): compress_jacobian!/compress_hessian! -> set_aug_diagonal! -> build_kkt! ->
 factorize! -> inertia -> [regularise + refactor while the inertia is wrong] -> Richardson(solve_kkt! + KKT mat-vec).
 Workload: synthetic AC-OPF with the (nbus, nbranch, ngen) counts of pglib case10000_goc (no pglib data offline),
-SparseCondensedKKTSystem, 24 distinct iterates (mu: 1e-1 -> 1e-9) cycled.
+SparseCondensedKKTSystem, 24 distinct iterates (mu: 1e-1 -> 1e-9) cycled; iterate NONCONVEX_AT is nonconvex (wrong inertia
+at first) so the regularise -> refactor branch of inertia_correction! runs inside the timed region.
 
   value : steps/sec with the iterate's inputs already resident in HBM (device-to-device staging only)
   e2e   : same metric through the host-facing path: inputs in pinned HOST memory, H2D of (jac, hess, reg, du_diag,
           l_diag, u_diag, l_lower, u_lower, rhs) and D2H of the step direction d INSIDE the timed region, every step
-  --impl reference : the CPU oracle (numpy assembly + SuperLU standing in for UMFPACK, 1 core) on the same workload
+  --impl reference : the CPU restatement of the reference's path (oracle: the reference's scalar assembly loops in C +
+          `LDLSolver` = Davis' LDL^T, sequential like the reference) on the same workload, same --steps/--warmup
+  secondary : configs[1], [2], [4] of BASELINE.json measured in the same run (N = 1), and the sharded C5 factorisation (N > 1)
 
 Timing: every step is bracketed by CUDA events on the launching stream; between steps (untimed) L2 is flushed by
 writing a 256 MiB buffer; the K steps are bracketed by barrier + synchronize; multi-GPU = max over ranks.
 """
 import argparse
+import importlib.util
 import json
 import os
 import subprocess
@@ -33,7 +37,11 @@ import numpy as np  # noqa: E402
 METRIC = "ipm_iters_per_sec"
 UNIT = "iter/s"
 N_ITERATES = 24
+NONCONVEX_AT = 11
 FIELDS = ("jac", "hess", "reg", "du_diag", "l_diag", "u_diag", "l_lower", "u_lower", "rhs")
+# below this many flops per factorisation the elimination tree is not sharded: every rank runs the whole (latency-bound)
+# factorisation itself, because one NVLink round trip costs more than the work it would save (measured: DESIGN.md section 6)
+SHARD_MIN_FLOPS = float(os.environ.get("B2_SHARD_MIN_FLOPS", 2e9))
 
 
 def parse():
@@ -44,16 +52,41 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="case10000_goc")
     ap.add_argument("--no-flush", action="store_true")
-    ap.add_argument("--cpu-sample-steps", type=int, default=8)
+    ap.add_argument("--cpu-sample-steps", type=int, default=60)
+    ap.add_argument("--no-secondary", action="store_true")
+    ap.add_argument("--force-shard", action="store_true", help="shard the elimination tree even below SHARD_MIN_FLOPS")
     return ap.parse_args()
 
 
+def load_workloads():
+    """workloads.py is plain numpy; loaded by PATH so that the reference arm never imports the package (whose __init__
+    loads libb200kkt.so)"""
+    name = "b2_workloads_standalone"
+    if name in sys.modules:
+        return sys.modules[name]
+    spec = importlib.util.spec_from_file_location(name, os.path.join(ROOT, "madnlp.jl_b200", "workloads.py"))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[name] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
 def make_workload(name):
-    import madnlp_jl_b200 as pkg
-    W = pkg.workloads
+    W = load_workloads()
     model, st = W.acopf_case(name)
     its = W.ipm_iterates(model, st, N_ITERATES, seed=0)
+    bad = W.ipm_iterates(model, st, 1, seed=2, y_scale=1e2, eq_box=(1e-1, 1.0))[0]
+    bad.mu = its[NONCONVEX_AT].mu
+    its[NONCONVEX_AT] = bad
     return model, st, its
+
+
+def config_of(args, st, world):
+    """identical for both arms (it depends on the arguments and the workload only)"""
+    return {"workload": f"acopf_{args.workload}_synthetic_condensed_kkt", "kkt": "SparseCondensedKKTSystem",
+            "n": int(st.nvar), "m": int(st.ncon), "iterates": N_ITERATES, "nonconvex_iterates": [NONCONVEX_AT],
+            "l2": "flushed between steps (256 MiB write, untimed)" if not args.no_flush else "not flushed",
+            "parallelism": f"{world} GPU(s): elimination tree sharded by subtrees when flops/factorisation >= {SHARD_MIN_FLOPS:.0e}, else replicated"}
 
 
 # ----------------------------------------------------------------------------------------------------- clocks
@@ -98,50 +131,89 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-# ----------------------------------------------------------------------------------------------------- reference arm
+# ----------------------------------------------------------------------------------------------------- CPU legs (oracle)
+def _cpu_replay(st):
+    """the reference's CPU path restated: scalar assembly loops (C), LDLSolver (src/LinearSolvers/ldl.jl over Davis' LDL^T, C),
+    Richardson + inertia correction (oracle/madnlp_oracle.py::IPMLinearAlgebraCPU).  Sequential, like the reference."""
+    import madnlp_oracle as o
+    cb = o.Callback(st.nvar, st.ncon, st.jac_I, st.jac_J, st.hess_I, st.hess_J, st.ind_ineq, st.ind_lb, st.ind_ub)
+    kkt = o.SparseCondensedKKTSystem(cb, o.LDLSolver)
+    kkt.initialize()
+    return o.IPMLinearAlgebraCPU(kkt)
+
+
+def _cpu_run(la, its, warm, steps):
+    for i in range(warm):
+        la.load_iterate(its[i % len(its)]); assert la.step(mu=its[i % len(its)].mu)
+    la.t_factorize = 0.0
+    f0 = la.cnt["factorizations"]
+    t0 = time.perf_counter()
+    for i in range(steps):
+        it = its[(warm + i) % len(its)]
+        la.load_iterate(it)
+        assert la.step(mu=it.mu)
+    dt = time.perf_counter() - t0
+    return dt, 1e3 * la.t_factorize / max(1, la.cnt["factorizations"] - f0)
+
+
+CPU_KIND_NOTE = ("oracle port: the reference's scalar assembly/vector loops and its LDLSolver (LDLFactorizations.jl = Davis' LDL^T, "
+                 "minimum-degree ordering) restated in C, Richardson + inertia correction in Python; sequential like the reference "
+                 "(blas_num_threads = 1 default, src/options.jl:127; fronts <= 47 leave BLAS threads nothing to do)")
+
+
+def _all_cores_worker(args_tuple):
+    name, steps = args_tuple
+    model, st, its = make_workload(name)
+    la = _cpu_replay(st)
+    dt, _ = _cpu_run(la, its, 1, steps)
+    return dt
+
+
+def cpu_all_cores_throughput(name, steps=12):
+    """what ALL host cores can deliver on this workload: one independent IPM replay per core (the factorisation itself is
+    sequential in the reference), aggregate steps/s.  Not a single-problem speed: a throughput ceiling for context."""
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    ctx = mp.get_context("spawn")
+    t0 = time.perf_counter()
+    with ctx.Pool(cores) as pool:
+        dts = pool.map(_all_cores_worker, [(name, steps)] * cores)
+    return {"value": cores * steps / max(dts), "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{cores} independent replays x {steps} steps in parallel (one per core); aggregate steps/s over the slowest",
+            "wall_s": time.perf_counter() - t0}
+
+
 def run_reference(args, rank, world):
-    """The reference's CPU path restated (oracle): numpy assembly, SuperLU (UMFPACK stand-in) factor/solve, Richardson.
-    Rank 0 only; bounded sample per the --steps/--warmup given."""
+    """--impl reference: rank 0 only; honours --steps/--warmup."""
     if rank != 0:
         return
-    import madnlp_oracle as o
     model, st, its = make_workload(args.workload)
-    cb = o.Callback(st.nvar, st.ncon, st.jac_I, st.jac_J, st.hess_I, st.hess_J, st.ind_ineq, st.ind_lb, st.ind_ub)
-    kkt = o.SparseCondensedKKTSystem(cb, o.UmfpackStandInSolver)
-    kkt.initialize()
-    steps = min(args.steps, max(1, args.cpu_sample_steps))
-    warm = min(args.warmup, 1)
-
-    def step(it):
-        kkt.get_jacobian()[:] = it.jac; kkt.get_hessian()[:] = it.hess
-        kkt.reg[:] = it.reg; kkt.du_diag[:] = it.du_diag
-        kkt.l_diag[:] = it.l_diag; kkt.u_diag[:] = it.u_diag; kkt.l_lower[:] = it.l_lower; kkt.u_lower[:] = it.u_lower
-        kkt.compress_jacobian(); kkt.compress_hessian()
-        o.set_aug_diagonal_(kkt)
-        kkt.build_kkt()
-        t0 = time.perf_counter()
-        kkt.linear_solver.factorize()
-        tf = time.perf_counter() - t0
-        b = o.UnreducedKKTVector.for_kkt(kkt); b.full()[:] = it.rhs
-        x = o.UnreducedKKTVector.for_kkt(kkt); w = o.UnreducedKKTVector.for_kkt(kkt)
-        o.solve_refine(x, kkt, b, w)
-        return tf
-    for i in range(warm):
-        step(its[i % len(its)])
-    t0 = time.perf_counter()
-    tfs = [step(its[(warm + i) % len(its)]) for i in range(steps)]
-    dt = time.perf_counter() - t0
-    val = steps / dt
+    la = _cpu_replay(st)
+    dt, ms_fac = _cpu_run(la, its, args.warmup, args.steps)
+    val = args.steps / dt
     line = {
-        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warm,
-        "ms_per_step": 1e3 * dt / steps, "ms_per_factorize": 1e3 * float(np.mean(tfs)), "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"acopf_{args.workload}_synthetic_condensed_kkt", "n": st.nvar, "m": st.ncon, "iterates": N_ITERATES},
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * dt / args.steps, "ms_per_factorize": ms_fac, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_of(args, st, args.gpus),
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "port",
-                         "sample": f"{steps} IPM steps of the same workload: numpy assembly + SuperLU (UMFPACK stand-in) + Richardson"},
+                         "sample": f"{args.steps} IPM steps of the same workload; " + CPU_KIND_NOTE},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "counters": la.cnt, "nnz_l_cpu": la.kkt.linear_solver.nnz_l,
     }
     print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_sample(args, st, its):
+    la = _cpu_replay(st)
+    nstep = max(1, args.cpu_sample_steps)
+    dt, ms_fac = _cpu_run(la, its, 2, nstep)
+    out = {"value": nstep / dt, "unit": UNIT, "cores": 1, "kind": "port", "ms_per_factorize": ms_fac,
+           "sample": f"{nstep} IPM steps of the same workload; " + CPU_KIND_NOTE}
+    try:
+        out["all_cores"] = cpu_all_cores_throughput(args.workload)
+    except Exception as e:      # never let the context number break the bench line
+        out["all_cores"] = {"error": repr(e)}
+    return out
 
 
 # ----------------------------------------------------------------------------------------------------- B200 arm
@@ -165,21 +237,27 @@ def run_b200(args, rank, world, local_rank):
     cb.jac_I, cb.jac_J, cb.hess_I, cb.hess_J = st.jac_I, st.jac_J, st.hess_I, st.hess_J
     cb.ind_ineq, cb.ind_lb, cb.ind_ub = st.ind_ineq, st.ind_lb, st.ind_ub
 
-    if world > 1:
-        from madnlp_jl_b200.parallel import DistributedSparseSolver
-        solver_cls = lambda csc, opt: DistributedSparseSolver(csc, opt, rank=rank, world=world)   # noqa: E731
-    else:
-        solver_cls = None
     opt = pkg.capi.default_options()
-    if os.environ.get("B2_FUSE_MAX"):
-        opt.fuse_max_fronts = int(os.environ["B2_FUSE_MAX"])
-    if os.environ.get("B2_DEP"):
-        opt.dep_schedule = int(os.environ["B2_DEP"])
-    if os.environ.get("B2_NEMIN"):
-        opt.nemin = int(os.environ["B2_NEMIN"])
-    kkt = K.create_kkt_system(K.SparseCondensedKKTSystem, cb, solver_cls, opt)
+    for env, field in (("B2_FUSE_MAX", "fuse_max_fronts"), ("B2_DEP", "dep_schedule"), ("B2_NEMIN", "nemin")):
+        if os.environ.get(env):
+            setattr(opt, field, int(os.environ[env]))
+    sharded = False
+    if world > 1:
+        # decide from the symbolic analysis whether sharding the tree can pay at all
+        probe = K.create_kkt_system(K.SparseCondensedKKTSystem, cb, None, opt)
+        flops = probe.linear_solver.stats()["flops"]
+        sharded = args.force_shard or flops >= SHARD_MIN_FLOPS
+        if sharded:
+            from madnlp_jl_b200.parallel import DistributedSparseSolver
+            del probe
+            kkt = K.create_kkt_system(K.SparseCondensedKKTSystem, cb,
+                                      lambda csc, o_: DistributedSparseSolver(csc, o_, rank=rank, world=world), opt)
+        else:
+            kkt = probe
+    else:
+        kkt = K.create_kkt_system(K.SparseCondensedKKTSystem, cb, None, opt)
     kkt.initialize()
-    la = IPMLinearAlgebra(kkt, use_cuda_graph=(world == 1 and not os.environ.get("B2_NO_STEP_GRAPH")))
+    la = IPMLinearAlgebra(kkt, use_cuda_graph=(not sharded and not os.environ.get("B2_NO_STEP_GRAPH")))
     stats = kkt.linear_solver.stats()
 
     host = [{k: torch.from_numpy(np.ascontiguousarray(getattr(it, k))).pin_memory() for k in FIELDS} for it in its]
@@ -201,13 +279,15 @@ def run_b200(args, rank, world, local_rank):
             ts.append(a0.elapsed_time(a1))
         return float(np.median(ts))
 
-    def one_step(i, e2e, record):
-        it = (host if e2e else devit)[i % N_ITERATES]
+    def one_step(i, e2e):
         if not args.no_flush:
             flush_buf.fill_(1.0)
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        la.load_iterate(it)
+        if e2e:
+            la.load_iterate_host(host, i % N_ITERATES)
+        else:
+            la.load_iterate(devit[i % N_ITERATES])
         ok = la.step(mu=its[i % N_ITERATES].mu)
         if e2e:
             d_host.copy_(la.d.values, non_blocking=True)
@@ -221,12 +301,12 @@ def run_b200(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed_run(e2e, record=False):
+    def timed_run(e2e):
         for i in range(args.warmup):
-            one_step(i, e2e, False)
+            one_step(i, e2e)
         barrier()
         t0 = time.perf_counter()
-        ms = [one_step(args.warmup + i, e2e, record) for i in range(args.steps)]
+        ms = [one_step(args.warmup + i, e2e) for i in range(args.steps)]
         barrier()
         wall = time.perf_counter() - t0
         tot = torch.tensor([sum(ms)], dtype=torch.float64, device=dev)
@@ -237,9 +317,12 @@ def run_b200(args, rank, world, local_rank):
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
-    dev_ms, dev_wall = timed_run(False, record=True)
+    dev_ms, dev_wall = timed_run(False)
+    cnt_dev = dict(la.cnt)
     e2e_ms, e2e_wall = timed_run(True)
+
     # phase timings of the hot path's three metrics, measured separately from the step loop
+    la.load_iterate(devit[0])
     def assemble():
         kkt.compress_jacobian(); kkt.compress_hessian(); kkt.set_aug_diagonal_(); kkt.build_kkt()
     xsol = torch.randn(kkt.n, dtype=torch.float64, device=dev)
@@ -247,6 +330,10 @@ def run_b200(args, rank, world, local_rank):
     fac_ms = time_phase(kkt.linear_solver.factorize)
     sol_ms = time_phase(lambda: kkt.linear_solver.solve_linear_system(xsol))
     clocks = sampler.stop() if sampler else None
+
+    secondary = None
+    if not args.no_secondary:
+        secondary = run_secondary(args, rank, world, dev)
 
     if rank == 0:
         peaks = {}
@@ -256,67 +343,78 @@ def run_b200(args, rank, world, local_rank):
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
-        # algorithmic bytes of one numeric factorisation (SURVEY.md 8d, A9 sparse): 8*(nnz K + nnz L)
+        # algorithmic bytes: numeric factorisation 8*(nnz K + nnz L); one solve 2 sweeps x (8+4) B x nnz L
         alg_bytes = 8.0 * (stats["nnz_a"] + stats["nnz_l"])
         achieved = alg_bytes / (fac_ms * 1e-3) / 1e9 if fac_ms else None
+        sol_bytes = 24.0 * stats["nnz_l"]
+        sol_ach = sol_bytes / (sol_ms * 1e-3) / 1e9 if sol_ms else None
         value = args.steps / (dev_ms * 1e-3)
         e2e_val = args.steps / (e2e_ms * 1e-3)
-        n_launch = stats["n_factor_launches"] + 2 + 3      # factor graph kernels + diag/condensed assembly + transfers/diag
-        solves = la.cnt["backsolves"] / max(1, la.cnt["factorizations"])
+        nfac = max(1, cnt_dev["factorizations"])
+        solves = cnt_dev["backsolves"] / nfac
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload if world == 1 else "", None)
+        except Exception:
+            pass
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"acopf_{args.workload}_synthetic_condensed_kkt", "kkt": "SparseCondensedKKTSystem",
-                       "n": st.nvar, "m": st.ncon, "nnz_kkt": stats["nnz_a"], "nnz_l": stats["nnz_l"], "factor_flops": stats["flops"],
-                       "supernodes": stats["n_supernodes"], "levels": stats["n_levels"], "max_front": stats["max_front"],
-                       "iterates": N_ITERATES, "l2": "flushed between steps (256 MiB write, untimed)" if not args.no_flush else "not flushed",
-                       "parallelism": f"subtree-sharded x{world}" if world > 1 else "single GPU",
-                       "refinement_solves_per_factorization": solves},
+            "dtype": "f64", "data": "synthetic", "config": config_of(args, st, world),
+            "solver": {"nnz_kkt": stats["nnz_a"], "nnz_l": stats["nnz_l"], "factor_flops": stats["flops"], "supernodes": stats["n_supernodes"],
+                       "levels": stats["n_levels"], "max_front": stats["max_front"], "tree_sharded": bool(sharded),
+                       "refinement_solves_per_factorization": solves,
+                       "factorizations_per_step": cnt_dev["factorizations"] / float(args.steps + args.warmup)},
             "ms_per_factorize": fac_ms, "ms_per_assemble": asm_ms, "ms_per_solve": sol_ms,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                     "ms_per_step": e2e_ms / args.steps},
-            # own kernels per step: iterate load (1, device-resident run) + assembly (5) + numeric factorisation + start of the
-            # refinement (||b||, w = b: 2) + per refinement step: the triangular sweeps + pre1/pre2/post1/finish/update/mul (6)
-            "gpu_launches": int((1 + 5 + stats["n_factor_launches"] + 2 + solves * (stats["n_solve_launches"] + 6)) * args.steps),
-            "roofline": {"kernel": "k_factor_dep: numeric multifrontal LDL^T of the whole elimination tree in one launch", "bound": "hbm",
+            # own kernels per step: iterate load (1) + assembly (5) + numeric factorisation + start of the refinement (1) +
+            # per refinement step: the triangular sweeps + pre/post/update/mul kernels (6)
+            "gpu_launches": int((1 + (5 + stats["n_factor_launches"]) * (cnt_dev["factorizations"] / float(args.steps + args.warmup)) + 1
+                                 + solves * (stats["n_solve_launches"] + 6)) * args.steps),
+            "roofline": {"kernel": "numeric multifrontal LDL^T of the whole elimination tree (k_factor_dep, one launch)", "bound": "hbm",
                          "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": (achieved / hbm_peak) if achieved else None,
-                         "traffic": 11.39e6 if (args.workload == "case10000_goc" and world == 1) else None,
-                         "traffic_source": "profiles/r01_prof_factor_dep_summary.txt (ncu --set full: dram read 11.32 MB + write 0.07 MB per launch)",
+                         "traffic": traffic, "traffic_source": "profiles/traffic.json (ncu --set full dram read+write per launch)",
                          "algorithmic_bytes": alg_bytes, "peak_source": peak_src,
                          "note": "latency-bound: %d fronts of order <= %d in %d levels, %.3g Mflop" % (
                              stats["n_supernodes"], stats["max_front"], stats["n_levels"], stats["flops"] / 1e6)},
+            "roofline_solve": {"kernel": "one solve_linear_system! (forward + diagonal + backward sweeps)", "bound": "hbm",
+                               "achieved": sol_ach, "peak": hbm_peak, "unit": "GB/s", "frac": (sol_ach / hbm_peak) if sol_ach else None,
+                               "algorithmic_bytes": sol_bytes},
             "clocks": clocks,
             "wall_s": {"device_resident": dev_wall, "e2e": e2e_wall},
             "counters": la.cnt,
         }
-        line["cpu_baseline"] = cpu_baseline_sample(args, st, its)
+        if secondary is not None:
+            line["secondary"] = secondary
+        if world == 1:
+            line["cpu_baseline"] = cpu_baseline_sample(args, st, its)
         print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
-def cpu_baseline_sample(args, st, its):
-    """oracle ('port') timed on this box's host cores on a bounded sample of the same workload"""
-    import madnlp_oracle as o
-    cb = o.Callback(st.nvar, st.ncon, st.jac_I, st.jac_J, st.hess_I, st.hess_J, st.ind_ineq, st.ind_lb, st.ind_ub)
-    kkt = o.SparseCondensedKKTSystem(cb, o.UmfpackStandInSolver)
-    kkt.initialize()
-    nstep = max(1, min(args.cpu_sample_steps, 6))
-    t0 = time.perf_counter()
-    for i in range(nstep):
-        it = its[i % len(its)]
-        kkt.get_jacobian()[:] = it.jac; kkt.get_hessian()[:] = it.hess
-        kkt.reg[:] = it.reg; kkt.du_diag[:] = it.du_diag
-        kkt.l_diag[:] = it.l_diag; kkt.u_diag[:] = it.u_diag; kkt.l_lower[:] = it.l_lower; kkt.u_lower[:] = it.u_lower
-        kkt.compress_jacobian(); kkt.compress_hessian(); o.set_aug_diagonal_(kkt); kkt.build_kkt()
-        kkt.linear_solver.factorize()
-        b = o.UnreducedKKTVector.for_kkt(kkt); b.full()[:] = it.rhs
-        x = o.UnreducedKKTVector.for_kkt(kkt); w = o.UnreducedKKTVector.for_kkt(kkt)
-        o.solve_refine(x, kkt, b, w)
-    dt = time.perf_counter() - t0
-    return {"value": nstep / dt, "unit": UNIT, "cores": 1, "kind": "port",
-            "sample": f"{nstep} IPM steps of the same workload through the numpy/SuperLU oracle"}
+def run_secondary(args, rank, world, dev):
+    """BASELINE.json configs[1], [2], [4] in the driver-run line (median of CUDA-event timings, L2 flushed; see
+    tools/bench_configs.py) and, at N > 1, the subtree-sharded C5 factorisation (max over ranks)."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    out = {}
+    try:
+        import bench_configs as BC
+        if world == 1:
+            out["fp64_peak_tflops"] = {"cublas_dgemm_8192": BC.dgemm_peak(), "dmma_issue_peak": 37.0,
+                                       "note": "fp64 roofline denominators (MEASURED_PEAKS.json has none)"}
+            out["c2_dense_n4096_m2048"] = BC.config2(cpu=True)
+            out["c2_dense_n4096_m2048_neq256"] = BC.config2(n_eq=256, cpu=False, lib=False)
+            out["c3_case1354_pegase"] = BC.config_sparse_opf("case1354_pegase")
+            out["c5_grid_64"] = BC.config5(64)
+        else:
+            out["c5_grid_64_sharded"] = BC.config5_dist(64, rank, world)
+    except Exception as e:
+        import traceback
+        out["error"] = repr(e) + " | " + traceback.format_exc(limit=3)
+    return out
 
 
 def main():

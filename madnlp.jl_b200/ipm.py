@@ -70,6 +70,37 @@ class IPMLinearAlgebra:
             for d_, s_ in pairs:
                 d_.copy_(s_, non_blocking=non_blocking)
 
+    def load_iterate_host(self, host_iterates, idx):
+        """Host-facing staging of one iterate (the role of SparseWrapperModel's pinned buffers, lib/MadNLPGPU/src/wrappers.jl:
+        173-196): `host_iterates[idx]` holds PINNED host tensors.  The copies run on a dedicated copy stream in the order the
+        step consumes them; the compute stream waits for the assembly inputs before the prologue and for the right-hand side
+        only before the refinement, so the H2D of `rhs` overlaps assembly + factorisation."""
+        k = self.kkt
+        it = host_iterates[idx]
+        if not hasattr(self, "_copy_stream"):
+            self._copy_stream = torch.cuda.Stream()
+            self._ev_inputs = torch.cuda.Event()
+            self._ev_rhs = torch.cuda.Event()
+            self._ev_free = torch.cuda.Event()
+        main = torch.cuda.current_stream()
+        self._ev_free.record(main)                       # the previous step has finished reading the buffers
+        cs = self._copy_stream
+        cs.wait_event(self._ev_free)
+        with torch.cuda.stream(cs):
+            for dst, name in ((k.get_jacobian(), "jac"), (k.get_hessian(), "hess"), (k.reg, "reg"), (k.du_diag, "du_diag"),
+                              (k.l_diag, "l_diag"), (k.u_diag, "u_diag"), (k.l_lower, "l_lower"), (k.u_lower, "u_lower")):
+                dst.copy_(it[name], non_blocking=True)
+            self._ev_inputs.record(cs)
+            self.p.values.copy_(it["rhs"], non_blocking=True)
+            self._ev_rhs.record(cs)
+        main.wait_event(self._ev_inputs)
+        self._rhs_pending = True
+
+    def _wait_rhs(self):
+        if getattr(self, "_rhs_pending", False):
+            torch.cuda.current_stream().wait_event(self._ev_rhs)
+            self._rhs_pending = False
+
     def _prologue(self):
         k = self.kkt
         k.compress_jacobian()
@@ -86,6 +117,9 @@ class IPMLinearAlgebra:
     def _solve_refine_wrapper(self):
         ok = self.iterator.solve_refine(self.d, self.p, self.w)
         if not ok and self.kkt.linear_solver.improve():
+            # improve!() changed a factorisation parameter (pivot threshold) that the captured prologue has baked in:
+            # drop the captured graph so that every later step factorises with the new setting
+            self._prologue_graph = None
             self.kkt.linear_solver.factorize()
             ok = self.iterator.solve_refine(self.d, self.p, self.w)
         self.cnt["backsolves"] += self.iterator.ir
@@ -110,6 +144,7 @@ class IPMLinearAlgebra:
         else:
             self._prologue_graph.replay()
         self.cnt["factorizations"] += 1
+        self._wait_rhs()
         # inertia_correction!(InertiaBased)
         o = self.opt
         n_trial = 0

@@ -445,24 +445,48 @@ def dense_qp_iterate(qp: DenseQP, mu: float, seed: int = 2):
 # --------------------------------------------------------------------------------------------
 # Large sparse indefinite system of BASELINE.json configs[4] (SparseKKTSystem-style augmented matrix)
 # --------------------------------------------------------------------------------------------
-def augmented_grid_kkt(nx: int, ny: int, nz: int, cons_per_node: float = 0.43, seed: int = 4, delta: float = 1e-8):
+def augmented_grid_kkt(nx: int, ny: int, nz: int, cons_per_node: float = 0.43, seed: int = 4, delta: float = 1e-8,
+                       dense_stencil: bool = False):
     """K = [[H + Sigma, J'], [J, -delta I]] as lower-triangular COO.  H: 7-point stencil on an nx*ny*nz grid with
     SPD values; J: each constraint couples a grid node with ~6 nodes of its neighbourhood (local coupling,
     so that a sparse factorisation exists at all -- a uniformly random J would fill completely).
+    `dense_stencil=True` is the BASELINE.json configs[4] density (N ~ 1e6 <-> nnz(tril K) ~ 1.6e7 at 89^3): H is the
+    27-point stencil (13 lower neighbours per node) and a constraint row couples its node with 18 neighbours
+    (faces + edges of the surrounding cube) -- 20 entries per dual row.
     Returns (N, n_tot, m, I, J, V)."""
     rng = np.random.default_rng(seed)
     n_tot = nx * ny * nz
     idx = np.arange(n_tot).reshape(nx, ny, nz)
     I, Jc, V = [], [], []
-    diag = 6.5 + rng.random(n_tot) + np.exp(rng.uniform(np.log(1e-6), np.log(1e2), n_tot))
-    I.append(np.arange(n_tot)); Jc.append(np.arange(n_tot)); V.append(diag)
-    for a, b in ((idx[1:, :, :], idx[:-1, :, :]), (idx[:, 1:, :], idx[:, :-1, :]), (idx[:, :, 1:], idx[:, :, :-1])):
-        a = a.ravel(); b = b.ravel()
-        I.append(np.maximum(a, b)); Jc.append(np.minimum(a, b)); V.append(-rng.random(len(a)))
+    if dense_stencil:
+        lower = [(dx, dy, dz) for dx in (-1, 0, 1) for dy in (-1, 0, 1) for dz in (-1, 0, 1) if (dx, dy, dz) > (0, 0, 0)]
+        absrow = np.zeros(n_tot)
+        offd = []
+        for (dx, dy, dz) in lower:
+            sa = idx[max(dx, 0):nx + min(dx, 0), max(dy, 0):ny + min(dy, 0), max(dz, 0):nz + min(dz, 0)].ravel()
+            sb = idx[max(-dx, 0):nx + min(-dx, 0), max(-dy, 0):ny + min(-dy, 0), max(-dz, 0):nz + min(-dz, 0)].ravel()
+            v = -rng.random(len(sa)) * (1.0 if abs(dx) + abs(dy) + abs(dz) == 1 else 0.25)
+            np.add.at(absrow, sa, -v); np.add.at(absrow, sb, -v)
+            offd.append((np.maximum(sa, sb), np.minimum(sa, sb), v))
+        diag = absrow + 0.5 + rng.random(n_tot) + np.exp(rng.uniform(np.log(1e-6), np.log(1e2), n_tot))
+        I.append(np.arange(n_tot)); Jc.append(np.arange(n_tot)); V.append(diag)
+        for a, b, v in offd:
+            I.append(a); Jc.append(b); V.append(v)
+    else:
+        diag = 6.5 + rng.random(n_tot) + np.exp(rng.uniform(np.log(1e-6), np.log(1e2), n_tot))
+        I.append(np.arange(n_tot)); Jc.append(np.arange(n_tot)); V.append(diag)
+        for a, b in ((idx[1:, :, :], idx[:-1, :, :]), (idx[:, 1:, :], idx[:, :-1, :]), (idx[:, :, 1:], idx[:, :, :-1])):
+            a = a.ravel(); b = b.ravel()
+            I.append(np.maximum(a, b)); Jc.append(np.minimum(a, b)); V.append(-rng.random(len(a)))
     m = int(cons_per_node * n_tot)
     centers = rng.choice(n_tot, m, replace=False)
     cx, cy, cz = np.unravel_index(centers, (nx, ny, nz))
-    offs = np.array([(0, 0, 0), (1, 0, 0), (-1, 0, 0), (0, 1, 0), (0, -1, 0), (0, 0, 1), (0, 0, -1)])
+    if dense_stencil:
+        offs = np.array([(dx, dy, dz) for dx in (-1, 0, 1) for dy in (-1, 0, 1) for dz in (-1, 0, 1)
+                         if abs(dx) + abs(dy) + abs(dz) <= 2])
+    else:
+        offs = np.array([(0, 0, 0), (1, 0, 0), (-1, 0, 0), (0, 1, 0), (0, -1, 0), (0, 0, 1), (0, 0, -1)])
+    seen = None
     for o in offs:
         px = np.clip(cx + o[0], 0, nx - 1); py = np.clip(cy + o[1], 0, ny - 1); pz = np.clip(cz + o[2], 0, nz - 1)
         cols = idx[px, py, pz]

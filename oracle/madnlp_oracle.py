@@ -22,15 +22,73 @@ Beyond these the reference holds no golden numbers for this path (factor/solve
 arithmetic lives in LAPACK/UMFPACK binaries outside the tree): step directions on
 the larger configurations are "parity unpinned" by the reference and defined by
 this oracle (LAPACK ``dsytrf/dsytrs`` through scipy -- the same routine
-``LapackCPUSolver`` calls, src/LinearSolvers/lapack.jl:164-172 -- and SuperLU
-standing in for UMFPACK's unsymmetric LU, src/LinearSolvers/umfpack.jl:28-55).
+``LapackCPUSolver`` calls, src/LinearSolvers/lapack.jl:164-172 -- SuperLU
+standing in for UMFPACK's unsymmetric LU, src/LinearSolvers/umfpack.jl:28-55 -- and
+``LDLSolver``: the reference's src/LinearSolvers/ldl.jl over a C restatement of the
+published LDL algorithm that LDLFactorizations.jl translates, oracle/kkt_oracle.c).
+
+C part (oracle/kkt_oracle.c -> oracle/libkkt_oracle.so, built by oracle/Makefile): the
+reference's sequential scalar loops (``_transfer!``, ``_build_condensed_aug_coord!``, CSC
+mat-vecs) and the sparse LDL^T.  When the library is present the loops below run through
+it (same order of additions as the numpy ``add.at`` statements they replace -- checked
+bit-for-bit in tests/test_oracle_golden.py); ``USE_C = False`` forces the numpy path.
 """
 from __future__ import annotations
+
+import ctypes as _C
+import os as _os
 
 import numpy as np
 import scipy.linalg.lapack as _lapack
 import scipy.sparse as sp
 import scipy.sparse.linalg as spla
+
+_CLIB_PATH = _os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "libkkt_oracle.so")
+USE_C = True
+
+
+def _load_clib():
+    if not _os.path.exists(_CLIB_PATH):
+        return None
+    lib = _C.CDLL(_CLIB_PATH)
+    p, i32, i64, f64 = _C.c_void_p, _C.c_int32, _C.c_int64, _C.c_double
+    lib.okkt_transfer.argtypes = [i64, p, i64, p, p]
+    lib.okkt_condensed_coord.argtypes = [i64, p, p, p, p, p, i64, p, i64, p, i64, p]
+    lib.okkt_csc_mul_n.argtypes = [i32, i32, p, p, p, p, p, f64, f64]
+    lib.okkt_csc_mul_t.argtypes = [i32, i32, p, p, p, p, p, f64, f64]
+    lib.okkt_csc_symv_lower.argtypes = [i32, p, p, p, p, p, f64, f64]
+    lib.okkt_ldl_symbolic.restype = p
+    lib.okkt_ldl_symbolic.argtypes = [i32, p, p, p]
+    lib.okkt_ldl_free.argtypes = [p]
+    lib.okkt_ldl_nnz.restype = i64
+    lib.okkt_ldl_nnz.argtypes = [p]
+    lib.okkt_ldl_numeric.restype = i32
+    lib.okkt_ldl_numeric.argtypes = [p, p, p, p]
+    lib.okkt_ldl_solve.argtypes = [p, p]
+    lib.okkt_ldl_inertia.argtypes = [p, _C.POINTER(i64), _C.POINTER(i64), _C.POINTER(i64)]
+    lib.okkt_ldl_D.restype = _C.POINTER(f64)
+    lib.okkt_ldl_D.argtypes = [p]
+    lib.okkt_set_aug_diagonal.argtypes = [i64, i64, i64] + [p] * 8
+    lib.okkt_reduce_rhs.argtypes = [i64, i64] + [p] * 7
+    lib.okkt_finish_aug_solve.argtypes = [i64, i64] + [p] * 9
+    lib.okkt_kktmul.argtypes = [i64, i64, i64, i64] + [p] * 8 + [f64, f64, p, p]
+    for f in (lib.okkt_set_aug_diagonal, lib.okkt_reduce_rhs, lib.okkt_finish_aug_solve, lib.okkt_kktmul):
+        f.restype = None
+    for f in (lib.okkt_transfer, lib.okkt_condensed_coord, lib.okkt_csc_mul_n, lib.okkt_csc_mul_t, lib.okkt_csc_symv_lower,
+              lib.okkt_ldl_free, lib.okkt_ldl_solve, lib.okkt_ldl_inertia):
+        f.restype = None
+    return lib
+
+
+clib = _load_clib()
+
+
+def _c_ok(*arrays):
+    return USE_C and clib is not None and all(a.flags.c_contiguous for a in arrays)
+
+
+def _ptr(a):
+    return a.ctypes.data
 
 
 # --------------------------------------------------------------------------
@@ -65,6 +123,9 @@ def coo_to_csc(I, J, m, n):
 
 def transfer(nz, V, cmap):
     """src/matrixtools.jl:79-88 -- ``nz .= 0; nz[map[k]] += V[k]`` in COO order."""
+    if _c_ok(nz, V, cmap) and nz.dtype == np.float64 and V.dtype == np.float64 and cmap.dtype == np.int64:
+        clib.okkt_transfer(len(nz), _ptr(nz), len(V), _ptr(V), _ptr(cmap))
+        return nz
     nz[:] = 0.0
     np.add.at(nz, cmap, V)
     return nz
@@ -147,6 +208,11 @@ class UnreducedKKTVector:
 # --------------------------------------------------------------------------
 def set_aug_diagonal_(kkt):
     """src/IPM/kernels.jl:22-27  (_set_aug_diagonal!)."""
+    if _c_ok(kkt.pr_diag, kkt.reg, kkt.ind_lb, kkt.ind_ub):
+        clib.okkt_set_aug_diagonal(len(kkt.pr_diag), len(kkt.ind_lb), len(kkt.ind_ub), _ptr(kkt.ind_lb), _ptr(kkt.ind_ub),
+                                   _ptr(kkt.reg), _ptr(kkt.l_lower), _ptr(kkt.l_diag), _ptr(kkt.u_lower), _ptr(kkt.u_diag),
+                                   _ptr(kkt.pr_diag))
+        return
     kkt.pr_diag[:] = kkt.reg
     kkt.pr_diag[kkt.ind_lb] -= kkt.l_lower / kkt.l_diag
     kkt.pr_diag[kkt.ind_ub] -= kkt.u_lower / kkt.u_diag
@@ -162,6 +228,10 @@ def regularize_diagonal(kkt, primal, dual):
 def reduce_rhs(kkt, d):
     """src/IPM/kernels.jl:182-195."""
     xp = d.primal()
+    if _c_ok(d.values, kkt.ind_lb, kkt.ind_ub):
+        clib.okkt_reduce_rhs(len(kkt.ind_lb), len(kkt.ind_ub), _ptr(kkt.ind_lb), _ptr(kkt.ind_ub), _ptr(kkt.l_diag),
+                             _ptr(kkt.u_diag), _ptr(xp), _ptr(d.dual_lb()), _ptr(d.dual_ub()))
+        return
     xp[kkt.ind_lb] -= d.dual_lb() / kkt.l_diag
     xp[kkt.ind_ub] -= d.dual_ub() / kkt.u_diag
 
@@ -171,12 +241,21 @@ def finish_aug_solve(kkt, d):
     xp = d.primal()
     dlb = d.dual_lb()
     dub = d.dual_ub()
+    if _c_ok(d.values, kkt.ind_lb, kkt.ind_ub):
+        clib.okkt_finish_aug_solve(len(kkt.ind_lb), len(kkt.ind_ub), _ptr(kkt.ind_lb), _ptr(kkt.ind_ub), _ptr(kkt.l_lower),
+                                   _ptr(kkt.u_lower), _ptr(kkt.l_diag), _ptr(kkt.u_diag), _ptr(xp), _ptr(dlb), _ptr(dub))
+        return
     dlb[:] = (-dlb + kkt.l_lower * xp[kkt.ind_lb]) / kkt.l_diag
     dub[:] = (dub - kkt.u_lower * xp[kkt.ind_ub]) / kkt.u_diag
 
 
 def kktmul_(w, x, kkt, alpha, beta):
     """src/IPM/kernels.jl:161-180  (_kktmul!)."""
+    if _c_ok(w.values, x.values, kkt.ind_lb, kkt.ind_ub, kkt.reg, kkt.du_diag):
+        clib.okkt_kktmul(len(kkt.reg), len(kkt.du_diag), len(kkt.ind_lb), len(kkt.ind_ub), _ptr(kkt.ind_lb), _ptr(kkt.ind_ub),
+                         _ptr(kkt.reg), _ptr(kkt.du_diag), _ptr(kkt.l_lower), _ptr(kkt.u_lower), _ptr(kkt.l_diag),
+                         _ptr(kkt.u_diag), float(alpha), float(beta), _ptr(x.values), _ptr(w.values))
+        return
     w.primal()[:] += alpha * kkt.reg * x.primal()
     w.dual()[:] += alpha * kkt.du_diag * x.dual()
     wp = w.primal()
@@ -309,6 +388,107 @@ class UmfpackStandInSolver:
 
     def introduce(self):
         return "umfpack stand-in (SuperLU)"
+
+
+class LDLSolver:
+    """src/LinearSolvers/ldl.jl:5-62 (LDLSolver over LDLFactorizations.jl): tril -> full (ldl.jl:21), symbolic analysis at
+    construction, ``factorize`` = ``full.nzval .= tril_to_full_view; ldl_factorize!`` (ldl.jl:29-33), in-place ``ldiv!``
+    (ldl.jl:35-40), inertia = signs of D (ldl.jl:43-58).  The numeric kernel is oracle/kkt_oracle.c (Davis' LDL, the
+    algorithm LDLFactorizations.jl translates).  Ordering: the reference calls AMD.jl; AMD is not in this image, so the
+    minimum-degree ordering SuperLU computes on the same pattern (MMD on A'+A) stands in -- the ordering changes fill and
+    rounding, not the mathematics.  Sequential, like the reference."""
+    input_type = "csc"
+
+    def __init__(self, colptr, rowval, nzval, n, perm=None):
+        if clib is None:
+            raise RuntimeError("oracle/libkkt_oracle.so missing: run `make -C oracle`")
+        self.colptr, self.rowval, self.nzval, self.n = colptr, rowval, nzval, n
+        # get_tril_to_full (src/matrixtools.jl:17-46): full pattern + a view that maps tril values into it
+        nnz = len(rowval)
+        cols = np.repeat(np.arange(n, dtype=np.int64), np.diff(colptr))
+        rows = np.asarray(rowval, dtype=np.int64)
+        off = rows != cols
+        I = np.concatenate([rows, cols[off]]); J = np.concatenate([cols, rows[off]])
+        src = np.concatenate([np.arange(nnz), np.arange(nnz)[off]])
+        order = np.lexsort((I, J))
+        self._full_rowval = np.ascontiguousarray(I[order], dtype=np.int32)
+        cp = np.zeros(n + 1, dtype=np.int64); np.add.at(cp, J + 1, 1)
+        self._full_colptr = np.ascontiguousarray(np.cumsum(cp), dtype=np.int32)
+        self._tril_to_full = src[order]
+        self._full_nz = np.zeros(len(order))
+        if perm is None:
+            pat = sp.csc_matrix((np.ones(len(order)), self._full_rowval, self._full_colptr), shape=(n, n))
+            pat = pat + sp.diags(np.asarray(abs(pat).sum(axis=0)).ravel() + 1.0)       # values irrelevant: ordering only
+            perm = spla.splu(pat.tocsc(), permc_spec="MMD_AT_PLUS_A", diag_pivot_thresh=0.0,
+                             options=dict(SymmetricMode=True)).perm_c
+            # SuperLU: column perm_c[j] of A becomes column j... perm_c maps old -> new position; we need new -> old
+            perm = np.argsort(perm)
+        self.perm = np.ascontiguousarray(perm, dtype=np.int32)
+        self._h = clib.okkt_ldl_symbolic(n, _ptr(self._full_colptr), _ptr(self._full_rowval), _ptr(self.perm))
+        self.nnz_l = int(clib.okkt_ldl_nnz(self._h))
+        self.ok = False
+
+    def __del__(self):
+        if getattr(self, "_h", None) and clib is not None:
+            clib.okkt_ldl_free(self._h)
+            self._h = None
+
+    def factorize(self):
+        np.take(self.nzval, self._tril_to_full, out=self._full_nz)               # ldl.jl:30
+        r = clib.okkt_ldl_numeric(self._h, _ptr(self._full_colptr), _ptr(self._full_rowval), _ptr(self._full_nz))
+        self.ok = (r == self.n)
+        return self
+
+    def is_inertia(self):
+        return True
+
+    def inertia(self):
+        a, b, c = _C.c_int64(), _C.c_int64(), _C.c_int64()
+        clib.okkt_ldl_inertia(self._h, _C.byref(a), _C.byref(b), _C.byref(c))
+        if not self.ok:                          # stopped at an exactly-zero pivot: the remaining D entries are stale
+            return (0, self.n, 0)
+        return (a.value, b.value, c.value)
+
+    def solve(self, x):
+        if not self.ok:                          # ldl.jl:37-39: failed factorisation leaves the rhs unchanged
+            return x
+        assert x.flags.c_contiguous and x.dtype == np.float64
+        clib.okkt_ldl_solve(self._h, _ptr(x))
+        return x
+
+    def improve(self):
+        return False
+
+    def introduce(self):
+        return "LDL (Davis Alg. 849, C restatement of LDLFactorizations.jl)"
+
+
+def csc_mul_n(colptr, rowval, nz, shape, x, y, alpha, beta):
+    """y = alpha*A*x + beta*y for a CSC matrix (SparseArrays mul!)."""
+    if _c_ok(nz, x, y):
+        clib.okkt_csc_mul_n(shape[0], shape[1], _ptr(colptr), _ptr(rowval), _ptr(nz), _ptr(x), _ptr(y), alpha, beta)
+    else:
+        y[:] = alpha * (csc_to_scipy(colptr, rowval, nz, shape) @ x) + (beta * y if beta != 0.0 else 0.0)
+    return y
+
+
+def csc_mul_t(colptr, rowval, nz, shape, x, y, alpha, beta):
+    """y = alpha*A'*x + beta*y."""
+    if _c_ok(nz, x, y):
+        clib.okkt_csc_mul_t(shape[0], shape[1], _ptr(colptr), _ptr(rowval), _ptr(nz), _ptr(x), _ptr(y), alpha, beta)
+    else:
+        y[:] = alpha * (csc_to_scipy(colptr, rowval, nz, shape).T @ x) + (beta * y if beta != 0.0 else 0.0)
+    return y
+
+
+def csc_symv_lower(colptr, rowval, nz, n, x, y, alpha, beta):
+    """y = alpha*Symmetric(A,:L)*x + beta*y."""
+    if _c_ok(nz, x, y):
+        clib.okkt_csc_symv_lower(n, _ptr(colptr), _ptr(rowval), _ptr(nz), _ptr(x), _ptr(y), alpha, beta)
+    else:
+        H = csc_to_scipy(colptr, rowval, nz, (n, n))
+        y[:] = alpha * ((H + sp.tril(H, -1).T) @ x) + (beta * y if beta != 0.0 else 0.0)
+    return y
 
 
 class DenseLDLInertiaSolver:
@@ -520,6 +700,10 @@ def build_condensed_aug_symbolic(H_colptr, H_rowval, n, Jt_colptr, Jt_rowval, m)
 def build_condensed_aug_coord(nz, pr_diag, H_nz, Jt_nz, diag_buffer, dptr, hptr, jptr):
     """src/KKT/Sparse/condensed.jl:328-345 -- same three accumulation passes in the
     same order (hess, diag, JtDJ), sequential adds inside each pass."""
+    if _c_ok(nz, pr_diag, H_nz, Jt_nz, diag_buffer, dptr, hptr, jptr) and dptr.dtype == hptr.dtype == jptr.dtype == np.int64:
+        clib.okkt_condensed_coord(len(nz), _ptr(nz), _ptr(pr_diag), _ptr(H_nz), _ptr(Jt_nz), _ptr(diag_buffer),
+                                  len(dptr), _ptr(dptr), len(hptr), _ptr(hptr), len(jptr), _ptr(jptr))
+        return nz
     nz[:] = 0.0
     np.add.at(nz, hptr[:, 0], H_nz[hptr[:, 1]])
     np.add.at(nz, dptr[:, 0], pr_diag[dptr[:, 1]])
@@ -592,6 +776,10 @@ class SparseCondensedKKTSystem:
         """condensed.jl:138-140."""
         return z == 0 and p == self.n
 
+    def should_regularize_dual(self, p, z, ng):
+        """condensed.jl:141."""
+        return True
+
     def jt_csc(self):
         return csc_to_scipy(self.jt_colptr, self.jt_rowval, self.jt_nz, (self.n, self.m))
 
@@ -606,10 +794,10 @@ class SparseCondensedKKTSystem:
         Ss = self.pr_diag[n:n + m]
         reduce_rhs(self, w)
         self.buffer[:] = self.diag_buffer * (wz + ws / Ss)
-        Jt = self.jt_csc()
-        wx[:] += Jt @ self.buffer
+        jt = (self.jt_colptr, self.jt_rowval, self.jt_nz, (n, m))
+        csc_mul_n(*jt, self.buffer, wx, 1.0, 1.0)                   # mul!(wx, jt_csc, buffer, 1, 1)
         self.linear_solver.solve(wx)
-        self.buffer2[:] = Jt.T @ wx
+        csc_mul_t(*jt, wx, self.buffer2, 1.0, 0.0)                  # mul!(buffer2, jt_csc', wx)
         wz[:] = -self.buffer + self.diag_buffer * self.buffer2
         ws[:] = (ws + wz) / Ss
         finish_aug_solve(self, w)
@@ -621,11 +809,10 @@ class SparseCondensedKKTSystem:
         xf, wf = x.full(), w.full()
         xx = xf[:n]; xs = xf[n:n + m]; xz = xf[n + m:n + 2 * m]
         wx = wf[:n]; ws = wf[n:n + m]; wz = wf[n + m:n + 2 * m]
-        H = self.hess_com(); Hs = H + sp.tril(H, -1).T
-        Jt = self.jt_csc()
-        wx[:] = alpha * (Hs @ xx) + beta * wx
-        wx[:] += alpha * (Jt @ xz)
-        wz[:] = alpha * (Jt.T @ xx) + beta * wz
+        jt = (self.jt_colptr, self.jt_rowval, self.jt_nz, (n, m))
+        csc_symv_lower(self.hess_colptr, self.hess_rowval, self.hess_nz, n, xx, wx, alpha, beta)   # Symmetric(hess_com,:L)
+        csc_mul_n(*jt, xz, wx, alpha, 1.0)
+        csc_mul_t(*jt, xx, wz, alpha, beta)
         wz[:] -= alpha * xs
         ws[:] = beta * ws - alpha * xz
         kktmul_(w, x, self, alpha, beta)
@@ -949,3 +1136,83 @@ def set_aug_rhs(x, xl, xu, f, zl, zu, jacl, c, mu, ind_lb, ind_ub):
     pzl = (xl[ind_lb] - x[ind_lb]) * zl[ind_lb] + mu
     pzu = (xu[ind_ub] - x[ind_ub]) * zu[ind_ub] - mu
     return np.concatenate([px, py, pzl, pzu])
+
+
+# --------------------------------------------------------------------------
+# replay of one IPM iteration's linear algebra on the CPU (the reference-arm counterpart of
+# madnlp.jl_b200/ipm.py::IPMLinearAlgebra): regular! src/IPM/solver.jl:216-298 with
+# inertia_correction!(InertiaBased) src/IPM/solver.jl:611-670 and the perturbation schedule of
+# src/IPM/options.jl:168-175
+# --------------------------------------------------------------------------
+class IPMLinearAlgebraCPU:
+    first_hessian_perturbation = 1e-4
+    min_hessian_perturbation = 1e-20
+    max_hessian_perturbation = 1e20
+    perturb_inc_fact_first = 1e2
+    perturb_inc_fact = 8.0
+    perturb_dec_fact = 1 / 3
+    jacobian_regularization_value = 1e-8
+    jacobian_regularization_exponent = 0.25
+
+    def __init__(self, kkt, tol=1e-8):
+        self.kkt = kkt
+        self.tol = tol
+        self.d = UnreducedKKTVector.for_kkt(kkt)
+        self.p = UnreducedKKTVector.for_kkt(kkt)
+        self.w = UnreducedKKTVector.for_kkt(kkt)
+        self.del_w_last = 0.0
+        self.cnt = dict(factorizations=0, backsolves=0, regularized=0, failed=0)
+        self.t_factorize = 0.0
+
+    def load_iterate(self, it):
+        k = self.kkt
+        g = (lambda name: it[name]) if isinstance(it, dict) else (lambda name: getattr(it, name))
+        k.get_jacobian()[:] = g("jac"); k.get_hessian()[:] = g("hess")
+        k.reg[:] = g("reg"); k.du_diag[:] = g("du_diag")
+        k.l_diag[:] = g("l_diag"); k.u_diag[:] = g("u_diag"); k.l_lower[:] = g("l_lower"); k.u_lower[:] = g("u_lower")
+        self.p.full()[:] = g("rhs")
+
+    def _factorize_wrapper(self):
+        import time as _t
+        self.kkt.build_kkt()
+        t0 = _t.perf_counter()
+        self.kkt.linear_solver.factorize()
+        self.t_factorize += _t.perf_counter() - t0
+        self.cnt["factorizations"] += 1
+
+    def _solve_refine_wrapper(self):
+        ok, nit, _ = solve_refine(self.d, self.kkt, self.p, self.w, tol=self.tol)
+        self.cnt["backsolves"] += nit
+        return ok
+
+    def step(self, mu=1e-2):
+        k = self.kkt
+        k.compress_jacobian(); k.compress_hessian()
+        set_aug_diagonal_(k)
+        self._factorize_wrapper()
+        n_trial = 0
+        del_w = del_c = del_w_prev = del_c_prev = 0.0
+        inertia = k.linear_solver.inertia()
+        ok = self._solve_refine_wrapper() if k.is_inertia_correct(*inertia) else False
+        while not ok:
+            if n_trial == 0:
+                del_w = self.first_hessian_perturbation if self.del_w_last == 0.0 else max(
+                    self.min_hessian_perturbation, self.perturb_dec_fact * self.del_w_last)
+            else:
+                del_w *= self.perturb_inc_fact_first if self.del_w_last == 0.0 else self.perturb_inc_fact
+                if del_w > self.max_hessian_perturbation:
+                    self.cnt["failed"] += 1
+                    return False
+            should_dual = getattr(k, "should_regularize_dual", lambda *a: a[1] != 0)(*inertia)
+            del_c = self.jacobian_regularization_value * mu ** self.jacobian_regularization_exponent if should_dual else 0.0
+            regularize_diagonal(k, del_w - del_w_prev, del_c - del_c_prev)
+            del_w_prev, del_c_prev = del_w, del_c
+            self._factorize_wrapper()
+            inertia = k.linear_solver.inertia()
+            ok = self._solve_refine_wrapper() if k.is_inertia_correct(*inertia) else False
+            n_trial += 1
+            self.cnt["regularized"] += 1
+        if del_w != 0.0:
+            self.del_w_last = del_w
+        self.last_inertia = inertia
+        return True

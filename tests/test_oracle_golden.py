@@ -139,3 +139,82 @@ def test_ipm_reduction_restatements_known_answers():
     assert o.get_sd(np.array([3.0, -5.0]), zl[ind_lb], zu[ind_ub], 100.0) == 1.0 and o.get_sc(np.array([600.0]), np.array([]), 100.0) == 6.0
     p = o.set_aug_rhs(x, xl, xu, f, zl, zu, jacl, np.array([0.7]), mu, ind_lb, ind_ub)
     assert np.allclose(p, [-2 + 0.2 - 0.4 - 0.25, 1 + 0 - 0.1 - 0.5, -0.7, (0 - 0.5) * 0.2 + mu, (1 - 0.5) * 0.4 - mu, (3 - 1) * 0.1 - mu], rtol=0, atol=1e-15)
+
+
+# ------------------------------------------------------------------------------------------------ C part of the oracle
+def _standalone_workloads():
+    """workloads.py is plain numpy: load it by path so that oracle-only tests do not need the CUDA library"""
+    import importlib.util, os, sys
+    if "b2_workloads_standalone" in sys.modules:
+        return sys.modules["b2_workloads_standalone"]
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "madnlp.jl_b200", "workloads.py")
+    spec = importlib.util.spec_from_file_location("b2_workloads_standalone", path)
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules["b2_workloads_standalone"] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_c_oracle_is_loaded_and_pinned_to_the_2x2_kat():
+    """oracle/kkt_oracle.c (LDLSolver = src/LinearSolvers/ldl.jl) against the reference's KAT (MadNLPTests.jl:24-51)."""
+    assert o.clib is not None, "oracle/libkkt_oracle.so missing (make -C oracle)"
+    row, col, val = np.array([0, 1, 1]), np.array([0, 0, 1]), np.array([1.0, 0.1, 2.0])
+    cp, rv, mp = o.coo_to_csc(row, col, 2, 2)
+    nz = np.zeros(len(rv)); o.transfer(nz, val, mp)
+    M = o.LDLSolver(cp, rv, nz, 2).factorize()
+    assert M.inertia() == (2, 0, 0)
+    x = M.solve(np.array([1.0, 3.0]))
+    assert np.abs(x - np.array([0.8542713567839195, 1.4572864321608041])).max() < 1e-15
+
+
+def test_c_loops_are_bit_identical_to_the_numpy_statements():
+    """_transfer!, _build_condensed_aug_coord!, _set_aug_diagonal!, reduce_rhs!/finish_aug_solve!/_kktmul! in C ==
+    the numpy add.at statements (same sequential order of additions); mat-vecs to rounding."""
+    W = _standalone_workloads()
+    model, st = W.acopf_case("case300_synth")
+    it = W.ipm_iterates(model, st, 3, seed=7)[1]
+    cb = o.Callback(st.nvar, st.ncon, st.jac_I, st.jac_J, st.hess_I, st.hess_J, st.ind_ineq, st.ind_lb, st.ind_ub)
+    out = {}
+    try:
+        for use_c in (True, False):
+            o.USE_C = use_c
+            kkt = o.SparseCondensedKKTSystem(cb, o.DenseLDLInertiaSolver)
+            kkt.initialize()
+            kkt.get_jacobian()[:] = it.jac; kkt.get_hessian()[:] = it.hess
+            kkt.reg[:] = it.reg; kkt.du_diag[:] = it.du_diag
+            kkt.l_diag[:] = it.l_diag; kkt.u_diag[:] = it.u_diag; kkt.l_lower[:] = it.l_lower; kkt.u_lower[:] = it.u_lower
+            kkt.compress_jacobian(); kkt.compress_hessian(); o.set_aug_diagonal_(kkt); kkt.build_kkt()
+            kkt.linear_solver.factorize()
+            x = o.UnreducedKKTVector.for_kkt(kkt); x.full()[:] = it.rhs
+            w = o.UnreducedKKTVector.for_kkt(kkt); w.full()[:] = 1.0
+            kkt.mul(w, x, -0.5, 2.0)
+            r = x.copy(); o.reduce_rhs(kkt, r)
+            f = x.copy(); o.finish_aug_solve(kkt, f)
+            out[use_c] = dict(aug=kkt.aug_nz.copy(), jt=kkt.jt_nz.copy(), h=kkt.hess_nz.copy(), pr=kkt.pr_diag.copy(),
+                              r=r.full().copy(), f=f.full().copy(), w=w.full().copy())
+    finally:
+        o.USE_C = True
+    for k in ("aug", "jt", "h", "pr", "r", "f"):
+        assert (out[True][k] == out[False][k]).all(), k
+    assert np.abs(out[True]["w"] - out[False]["w"]).max() <= 1e-14 * np.abs(out[False]["w"]).max()
+
+
+def test_ldl_solver_inertia_and_solution_against_lapack():
+    """LDLSolver (Davis LDL) vs dsytrf-based truth: same inertia on an indefinite quasi-definite KKT, same solution."""
+    rng = np.random.default_rng(5)
+    n, m = 60, 25
+    H = rng.standard_normal((n, n)); H = H @ H.T + n * np.eye(n)
+    J = rng.standard_normal((m, n)) * (rng.random((m, n)) < 0.2)
+    K = np.block([[H, J.T], [J, -1e-3 * np.eye(m)]])
+    Kl = np.tril(K)
+    I, Jc = np.nonzero(Kl)
+    cp, rv, mp = o.coo_to_csc(I, Jc, n + m, n + m)
+    nz = np.zeros(len(rv)); o.transfer(nz, Kl[I, Jc], mp)
+    M = o.LDLSolver(cp, rv, nz, n + m, perm=np.arange(n + m)).factorize()     # natural order: primal block first
+    T = o.DenseLDLInertiaSolver(cp, rv, nz, n + m).factorize()
+    assert M.inertia() == T.inertia() == (n, 0, m)
+    b = rng.standard_normal(n + m)
+    assert np.abs(M.solve(b.copy()) - T.solve(b.copy())).max() < 1e-10
+    M2 = o.LDLSolver(cp, rv, nz, n + m).factorize()                           # minimum-degree stand-in ordering
+    assert sorted(M2.perm.tolist()) == list(range(n + m))
+    assert np.abs(M2.solve(b.copy()) - T.solve(b.copy())).max() < 1e-9
