@@ -218,6 +218,26 @@ int b2d_gemv_n(int32_t rows, int32_t cols, int32_t lda, const double* A_d, const
 int b2d_gemv_t(int32_t rows, int32_t cols, int32_t lda, const double* A_d, const double* x_d, double* y_d, double alpha, double beta, void* stream);
 int b2d_symv_lower(int32_t n, int32_t lda, const double* A_d, const double* x_d, double* y_d, double alpha, double beta, void* stream);
 
+/* solve_kkt!(::DenseCondensedKKTSystem, w) (src/IPM/factorization.jl:190-229) and mul!(w, ::AbstractDenseKKTSystem, x, alpha, beta)
+ * (:303-324) around b2d_solve.  `b2d_kkt` holds ind_ineq (host, 0-based, ns entries), the derived ind_eq and their inverse map on
+ * the device.  jac: m x n column-major (ld m); hess: n x n (lower triangle read, ld n); pd_buffer: n + n_eq; buffer: m;
+ * w, x: UnreducedKKTVector buffers [x (n) s (ns) | y (m) | zl | zu].
+ *   pre : reduce_rhs!; buffer = 0; buffer[ind_ineq] = D .* (wz + ws ./ Ss); xx = jac' * buffer + wx; xy = wy
+ *   (caller: b2d_solve(pd_buffer))
+ *   post: wx = xx; dual(w) = jac * wx; wy = xy; wz .*= D; dual(w) .-= buffer; ws = (ws + wz) ./ Ss; finish_aug_solve! */
+typedef struct b2_bounds b2_bounds;   /* created by b2_bounds_create, below */
+typedef struct b2d_kkt b2d_kkt;
+int b2d_kkt_create(int32_t n, int32_t m, int32_t ns, const int64_t* ind_ineq_h, b2d_kkt** out);
+int b2d_kkt_destroy(b2d_kkt* k);
+int b2d_kkt_solve_pre(b2d_kkt* k, b2_bounds* b, const double* jac_d, const double* pr_diag_d, const double* diag_buffer_d,
+                      const double* l_diag_d, const double* u_diag_d, double* buffer_d, double* pd_buffer_d, double* w_d, void* stream);
+int b2d_kkt_solve_post(b2d_kkt* k, b2_bounds* b, const double* jac_d, const double* pr_diag_d, const double* diag_buffer_d,
+                       const double* l_lower_d, const double* u_lower_d, const double* l_diag_d, const double* u_diag_d,
+                       const double* buffer_d, const double* pd_buffer_d, double* w_d, void* stream);
+int b2d_kkt_mul(b2d_kkt* k, b2_bounds* b, const double* hess_d, const double* jac_d, const double* reg_d, const double* du_diag_d,
+                const double* l_lower_d, const double* u_lower_d, const double* l_diag_d, const double* u_diag_d,
+                double alpha, double beta, const double* x_d, double* w_d, void* stream);
+
 /* ------------------------------------------------------------------ IPM vector kernels */
 /* Index sets ind_lb / ind_ub over the primal vector (x,s) (src/Callbacks/nlpmodels.jl:369-406), uploaded once
  * together with their inverse maps so that every kernel below is a single race-free pass over n_tot. */

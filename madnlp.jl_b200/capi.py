@@ -116,6 +116,11 @@ PROTOTYPES = {
     "b2d_inertia_enqueue": (C.c_int, [_p, _p]),
     "b2d_inertia_fetch": (C.c_int, [_p, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64)]),
     "b2d_solve": (C.c_int, [_p, _p, _i32, _p]),
+    "b2d_kkt_create": (C.c_int, [_i32, _i32, _i32, _p, _PP]),
+    "b2d_kkt_destroy": (C.c_int, [_p]),
+    "b2d_kkt_solve_pre": (C.c_int, [_p] * 10 + [_p]),
+    "b2d_kkt_solve_post": (C.c_int, [_p] * 12 + [_p]),
+    "b2d_kkt_mul": (C.c_int, [_p] * 10 + [_f64, _f64, _p, _p, _p]),
     "b2d_gemv_n": (C.c_int, [_i32, _i32, _i32, _p, _p, _p, _f64, _f64, _p]),
     "b2d_gemv_t": (C.c_int, [_i32, _i32, _i32, _p, _p, _p, _f64, _f64, _p]),
     "b2d_symv_lower": (C.c_int, [_i32, _i32, _p, _p, _p, _f64, _f64, _p]),

@@ -246,24 +246,44 @@ void analyse(int32_t n, const int32_t* colptr, const int32_t* rowval, const Anal
     for (int32_t i = 0; i < n; ++i) iperm[perm0[i]] = i;
 
     timer.lap("ordering");
-    // ---- 1b. augmented-KKT constraint: a dual row that would be eliminated before all of its (primal) neighbours is
-    //          moved to just after its earliest neighbour (its pivot is then -a^2/d instead of the raw, possibly zero,
-    //          diagonal entry).  Quasi-definite / condensed matrices do not need this (kkt_n_primal = 0).
+    // ---- 1b. augmented-KKT constraint.  With static (1 x 1) pivoting a dual row of [[H, J'], [J, -D]] (D possibly zero) gets a
+    //          usable pivot only from primal neighbours eliminated BEFORE it, and two duals must not rely on the same single
+    //          neighbour u: after u their Schur block is the rank-one -(a_i a_j)/d_u and the second pivot cancels exactly.
+    //          So every dual is MATCHED with a distinct primal neighbour that precedes it (in effect a 2 x 2 pivot {u, v} spread
+    //          over two consecutive 1 x 1 steps): duals are visited in elimination order; a dual keeps its place if an unused
+    //          neighbour already precedes it, otherwise it is moved to just after its earliest unused neighbour (or, if every
+    //          neighbour is taken, after its last neighbour).  Quasi-definite / condensed matrices do not need this (kkt_n_primal = 0).
     if (opt.kkt_n_primal > 0 && opt.kkt_n_primal < n && opt.ordering != 3) {
         const int32_t np_ = opt.kkt_n_primal;
-        std::vector<int32_t> first_nb(n, INT32_MAX);
-        for (int32_t j = 0; j < n; ++j)
-            for (int32_t p = colptr[j]; p < colptr[j + 1]; ++p) {
-                const int32_t i = rowval[p];
-                if (i == j) continue;
-                first_nb[i] = std::min(first_nb[i], iperm[j]);
-                first_nb[j] = std::min(first_nb[j], iperm[i]);
-            }
+        const int32_t nd_ = n - np_;
+        // primal neighbours of every dual (lower CSC: entry (i, j), i >= np_ > j, sits in column j)
+        std::vector<int64_t> dptr(nd_ + 1, 0);
+        for (int32_t j = 0; j < np_; ++j)
+            for (int32_t p = colptr[j]; p < colptr[j + 1]; ++p) if (rowval[p] >= np_) dptr[rowval[p] - np_ + 1]++;
+        for (int32_t v = 0; v < nd_; ++v) dptr[v + 1] += dptr[v];
+        std::vector<int32_t> dnb(dptr[nd_]);
+        {
+            std::vector<int64_t> fill(dptr.begin(), dptr.end() - 1);
+            for (int32_t j = 0; j < np_; ++j)
+                for (int32_t p = colptr[j]; p < colptr[j + 1]; ++p) if (rowval[p] >= np_) dnb[fill[rowval[p] - np_]++] = j;
+        }
+        for (int32_t v = 0; v < nd_; ++v)                     // neighbours in elimination order
+            std::sort(dnb.begin() + dptr[v], dnb.begin() + dptr[v + 1], [&](int32_t a, int32_t b) { return iperm[a] < iperm[b]; });
+        std::vector<int32_t> duals(nd_);
+        std::iota(duals.begin(), duals.end(), np_);
+        std::sort(duals.begin(), duals.end(), [&](int32_t a, int32_t b) { return iperm[a] < iperm[b]; });
+        std::vector<char> used(np_, 0);
         std::vector<std::pair<int64_t, int32_t>> key(n);
-        for (int32_t v = 0; v < n; ++v) {
-            int64_t k = 2 * (int64_t)iperm[v];
-            if (v >= np_ && first_nb[v] != INT32_MAX && iperm[v] < first_nb[v]) k = 2 * (int64_t)first_nb[v] + 1;
-            key[v] = {k, iperm[v]};
+        for (int32_t v = 0; v < n; ++v) key[v] = {2 * (int64_t)iperm[v], iperm[v]};
+        for (int32_t v : duals) {
+            const int64_t a = dptr[v - np_], b = dptr[v - np_ + 1];
+            if (a == b) continue;                              // isolated dual row: nothing can help it
+            int32_t partner = -1;
+            for (int64_t q = a; q < b && iperm[dnb[q]] < iperm[v]; ++q) if (!used[dnb[q]]) { partner = dnb[q]; break; }
+            if (partner >= 0) { used[partner] = 1; continue; } // an own preceding neighbour exists: the dual stays where it is
+            for (int64_t q = a; q < b; ++q) if (!used[dnb[q]]) { partner = dnb[q]; break; }
+            if (partner >= 0) { used[partner] = 1; key[v] = {2 * (int64_t)iperm[partner] + 1, iperm[v]}; }
+            else key[v] = {2 * (int64_t)std::max(iperm[dnb[b - 1]], iperm[v]) + 1, iperm[v]};
         }
         std::vector<int32_t> ord(n);
         std::iota(ord.begin(), ord.end(), 0);

@@ -527,32 +527,37 @@ extern "C" int b2_fill(int64_t n, double v, double* x_d, void* stream) {
 // ---------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ double scl2(double beta, double w) { return beta == 0.0 ? 0.0 : beta * w; }
 
-// y_i = alpha * sum_j A(i,j) x_j + beta y_i : thread = row (coalesced along a column), 256 rows per CTA, columns split
-// over gridDim.y chunks and combined with a second pass when gridDim.y > 1 is avoided: each CTA owns its rows fully.
+// y_i = alpha * sum_j A(i,j) x_j + beta y_i : a CTA owns 32 rows; its 8 warps take interleaved column slices (lane = row:
+// a warp reads 256 contiguous bytes of a column, 8 columns in flight per lane), partial sums meet in shared memory and are
+// added in warp order -- deterministic, no atomics, rows/32 CTAs.
+constexpr int GEMV_ROWS = 32;
 __global__ void __launch_bounds__(256) k_gemv_n(int rows, int cols, int lda, const double* __restrict__ A, const double* __restrict__ x,
                                                 double* __restrict__ y, double alpha, double beta) {
-    __shared__ double xs[256];
-    const int i = blockIdx.x * 256 + threadIdx.x;
+    __shared__ double part[8][GEMV_ROWS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int i = blockIdx.x * GEMV_ROWS + lane;
+    const bool ok = i < rows;
+    const double* base = A + (ok ? i : 0);
     double acc = 0.0;
-    for (int j0 = 0; j0 < cols; j0 += 256) {
-        __syncthreads();
-        if (j0 + threadIdx.x < cols) xs[threadIdx.x] = x[j0 + threadIdx.x];
-        __syncthreads();
-        const int nj = min(256, cols - j0);
-        if (i < rows) {
-            const double* col = A + (size_t)j0 * lda + i;
-            int j = 0;
-            for (; j + 8 <= nj; j += 8) {
-                double v[8];
+    int j = warp * 8;
+    for (; j + 8 <= cols; j += 64) {                    // this warp's 8-column groups: j, j+64, ...
+        double v[8], xv[8];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) v[u] = col[(size_t)(j + u) * lda];
+        for (int u = 0; u < 8; ++u) { v[u] = ok ? base[(size_t)(j + u) * lda] : 0.0; xv[u] = x[j + u]; }
 #pragma unroll
-                for (int u = 0; u < 8; ++u) acc = fma(v[u], xs[j + u], acc);
-            }
-            for (; j < nj; ++j) acc = fma(col[(size_t)j * lda], xs[j], acc);
-        }
+        for (int u = 0; u < 8; ++u) acc = fma(v[u], xv[u], acc);
     }
-    if (i < rows) y[i] = alpha * acc + scl2(beta, y[i]);
+    if (j < cols) {                                     // ragged tail of the last group
+        for (int u = 0; j + u < cols; ++u) acc = fma(ok ? base[(size_t)(j + u) * lda] : 0.0, x[j + u], acc);
+    }
+    part[warp][lane] = acc;
+    __syncthreads();
+    if (warp == 0 && ok) {
+        double tot = 0.0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) tot += part[q][lane];
+        y[i] = alpha * tot + scl2(beta, y[i]);
+    }
 }
 // y_j = alpha * sum_i A(i,j) x_i + beta y_j : one warp per column, lanes stride the rows
 __global__ void __launch_bounds__(256) k_gemv_t(int rows, int cols, int lda, const double* __restrict__ A, const double* __restrict__ x,
@@ -595,7 +600,7 @@ extern "C" int b2d_gemv_n(int32_t rows, int32_t cols, int32_t lda, const double*
                           double beta, void* stream) {
     if (rows < 0 || cols < 0 || lda < rows || (rows && (!y_d || (cols && (!A_d || !x_d))))) { set_error("b2d_gemv_n: invalid argument"); return B2_ERR_INVALID; }
     if (rows == 0) return B2_OK;
-    k_gemv_n<<<(rows + 255) / 256, 256, 0, as_stream(stream)>>>(rows, cols, lda, A_d, x_d, y_d, alpha, beta);
+    k_gemv_n<<<(rows + GEMV_ROWS - 1) / GEMV_ROWS, 256, 0, as_stream(stream)>>>(rows, cols, lda, A_d, x_d, y_d, alpha, beta);
     B2_CUDA(cudaGetLastError());
     return B2_OK;
 }
@@ -612,6 +617,149 @@ extern "C" int b2d_symv_lower(int32_t n, int32_t lda, const double* A_d, const d
     if (n < 0 || lda < n || (n && (!A_d || !x_d || !y_d))) { set_error("b2d_symv_lower: invalid argument"); return B2_ERR_INVALID; }
     if (n == 0) return B2_OK;
     k_symv_lower<<<(n + 7) / 8, 256, 0, as_stream(stream)>>>(n, lda, A_d, x_d, y_d, alpha, beta);
+    B2_CUDA(cudaGetLastError());
+    return B2_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// DenseCondensedKKTSystem wrappers: solve_kkt! (src/IPM/factorization.jl:190-229) and mul! (:303-324) as own kernels.
+//   solve_kkt! = k_dcond_pre (reduce_rhs! + buffer + xx = wx + xy = wy) ; gemv_t (xx += jac' buffer) ; [b2d_solve] ;
+//                gemv_n (dual = jac xx) ; k_dcond_post (wx = xx, wy = xy, wz = wz .* D - buffer, ws = (ws + wz) ./ Ss) ;
+//                k_finish_aug_solve
+//   mul!       = symv_lower ; gemv_t ; gemv_n ; k_dcond_mul_tail (ws / wz updates + _kktmul!)
+// The reference issues the same steps as ~12 broadcast kernels + 2 cuBLAS gemv (+ symv) per call.
+// ---------------------------------------------------------------------------------------------------------
+struct b2d_kkt {
+    int32_t n = 0, m = 0, ns = 0, n_eq = 0;
+    b2::DevBuf<int64_t> ind_ineq, ind_eq;
+    b2::DevBuf<int32_t> ineq_pos;         // [m] position of constraint j in ind_ineq, or -1 (equality)
+};
+
+extern "C" int b2d_kkt_create(int32_t n, int32_t m, int32_t ns, const int64_t* ind_ineq_h, b2d_kkt** out) {
+    if (!out || n < 0 || m < 0 || ns < 0 || ns > m || (ns && !ind_ineq_h)) { set_error("b2d_kkt_create: invalid argument"); return B2_ERR_INVALID; }
+    std::vector<int32_t> pos(std::max(m, 1), -1);
+    for (int32_t k = 0; k < ns; ++k) {
+        if (ind_ineq_h[k] < 0 || ind_ineq_h[k] >= m || pos[ind_ineq_h[k]] != -1) { set_error("b2d_kkt_create: bad ind_ineq"); return B2_ERR_INVALID; }
+        pos[ind_ineq_h[k]] = k;
+    }
+    std::vector<int64_t> eq;
+    for (int32_t j = 0; j < m; ++j) if (pos[j] < 0) eq.push_back(j);
+    auto* k = new b2d_kkt();
+    k->n = n; k->m = m; k->ns = ns; k->n_eq = m - ns;
+    if (k->ind_ineq.upload(ind_ineq_h, ns) != cudaSuccess || k->ind_eq.upload(eq.data(), eq.size()) != cudaSuccess ||
+        k->ineq_pos.upload(pos.data(), pos.size()) != cudaSuccess) {
+        delete k;
+        return cuda_fail(cudaGetLastError(), "b2d_kkt upload", __FILE__, __LINE__);
+    }
+    *out = k;
+    return B2_OK;
+}
+extern "C" int b2d_kkt_destroy(b2d_kkt* k) { delete k; return B2_OK; }
+
+__global__ void k_dcond_pre(int n, int m, int ns, int n_eq, int64_t nlb, const int32_t* __restrict__ lbpos, const int32_t* __restrict__ ubpos,
+                            const int64_t* __restrict__ ind_ineq, const int64_t* __restrict__ ind_eq, const double* __restrict__ ld,
+                            const double* __restrict__ ud, const double* __restrict__ pr, const double* __restrict__ D,
+                            double* __restrict__ buffer, double* __restrict__ x, double* __restrict__ w) {
+    const int64_t n_tot = (int64_t)n + ns;
+    const double* wzl = w + n_tot + m;
+    const double* wzu = wzl + nlb;
+    GRID_STRIDE(t, n_tot + n_eq) {
+        if (t < n_tot) {
+            double v = w[t];                                           // reduce_rhs!
+            const int p = lbpos[t], q = ubpos[t];
+            if (p >= 0) v = __dsub_rn(v, __ddiv_rn(wzl[p], ld[p]));
+            if (q >= 0) v = __dsub_rn(v, __ddiv_rn(wzu[q], ud[q]));
+            if (p >= 0 || q >= 0) w[t] = v;
+            if (t < n) x[t] = v;                                       // xx starts as wx; gemv_t adds jac' * buffer
+            else {
+                const int64_t k = t - n, j = ind_ineq[k];
+                buffer[j] = __dmul_rn(D[k], __dadd_rn(w[n_tot + j], __ddiv_rn(v, pr[t])));    // D .* (wz + ws ./ Ss)
+            }
+        } else {
+            const int64_t e = t - n_tot, j = ind_eq[e];
+            buffer[j] = 0.0;
+            x[n + e] = w[n_tot + j];                                   // xy .= wy
+        }
+    }
+}
+
+__global__ void k_dcond_post(int n, int m, int ns, int n_eq, const int64_t* __restrict__ ind_ineq, const int64_t* __restrict__ ind_eq,
+                             const double* __restrict__ pr, const double* __restrict__ D, const double* __restrict__ buffer,
+                             const double* __restrict__ x, double* __restrict__ w) {
+    const int64_t n_tot = (int64_t)n + ns;
+    GRID_STRIDE(t, n_tot + n_eq) {
+        if (t < n) w[t] = x[t];                                        // wx .= xx
+        else if (t < n_tot) {
+            const int64_t k = t - n, j = ind_ineq[k];
+            const double wz = __dsub_rn(__dmul_rn(w[n_tot + j], D[k]), buffer[j]);     // wz .*= D ; dual .-= buffer
+            w[n_tot + j] = wz;
+            w[t] = __ddiv_rn(__dadd_rn(w[t], wz), pr[t]);              // ws .= (ws .+ wz) ./ Ss
+        } else {
+            const int64_t e = t - n_tot, j = ind_eq[e];
+            w[n_tot + j] = x[n + e];                                   // wy .= xy  (buffer is zero on equality rows)
+        }
+    }
+}
+
+__global__ void k_dcond_mul_tail(KktMulArgs a, int n, const int32_t* __restrict__ ineq_pos, const int64_t* __restrict__ ind_ineq,
+                                 const double* __restrict__ x, double* __restrict__ w) {
+    GRID_STRIDE(t, a.n_tot + a.m + a.nlb + a.nub) {
+        double wt = w[t];
+        if (t >= n && t < a.n_tot) wt = scl(a.beta, wt) - a.alpha * x[a.n_tot + ind_ineq[t - n]];         // ws = beta ws - alpha xz
+        else if (t >= a.n_tot && t < a.n_tot + a.m) {
+            const int k = ineq_pos[t - a.n_tot];
+            if (k >= 0) wt -= a.alpha * x[n + k];                                                        // wz -= alpha xs
+        }
+        w[t] = kktmul_entry(a, t, wt, x);
+    }
+}
+
+extern "C" int b2d_kkt_solve_pre(b2d_kkt* k, b2_bounds* b, const double* jac_d, const double* pr_diag_d, const double* diag_buffer_d,
+                                 const double* l_diag_d, const double* u_diag_d, double* buffer_d, double* pd_buffer_d, double* w_d,
+                                 void* stream) {
+    if (!k || !b || !w_d || !pd_buffer_d || (k->m && (!buffer_d || !jac_d)) || b->n_tot != (int64_t)k->n + k->ns) {
+        set_error("b2d_kkt_solve_pre: invalid argument"); return B2_ERR_INVALID;
+    }
+    cudaStream_t st = as_stream(stream);
+    const int64_t tot = b->n_tot + k->n_eq;
+    if (tot == 0) return B2_OK;
+    k_dcond_pre<<<grid_for(tot), 256, 0, st>>>(k->n, k->m, k->ns, k->n_eq, b->nlb, b->lbpos.p, b->ubpos.p, k->ind_ineq.p, k->ind_eq.p,
+                                              l_diag_d, u_diag_d, pr_diag_d, diag_buffer_d, buffer_d, pd_buffer_d, w_d);
+    if (k->m > 0 && k->n > 0)
+        k_gemv_t<<<(k->n + 7) / 8, 256, 0, st>>>(k->m, k->n, k->m, jac_d, buffer_d, pd_buffer_d, 1.0, 1.0);
+    B2_CUDA(cudaGetLastError());
+    return B2_OK;
+}
+
+extern "C" int b2d_kkt_solve_post(b2d_kkt* k, b2_bounds* b, const double* jac_d, const double* pr_diag_d, const double* diag_buffer_d,
+                                  const double* l_lower_d, const double* u_lower_d, const double* l_diag_d, const double* u_diag_d,
+                                  const double* buffer_d, const double* pd_buffer_d, double* w_d, void* stream) {
+    if (!k || !b || !w_d || !pd_buffer_d || b->n_tot != (int64_t)k->n + k->ns) { set_error("b2d_kkt_solve_post: invalid argument"); return B2_ERR_INVALID; }
+    cudaStream_t st = as_stream(stream);
+    const int64_t tot = b->n_tot + k->n_eq;
+    if (tot == 0) return B2_OK;
+    if (k->m > 0)
+        k_gemv_n<<<(k->m + GEMV_ROWS - 1) / GEMV_ROWS, 256, 0, st>>>(k->m, k->n, k->m, jac_d, pd_buffer_d, w_d + b->n_tot, 1.0, 0.0);    // dual(w) = jac * xx
+    k_dcond_post<<<grid_for(tot), 256, 0, st>>>(k->n, k->m, k->ns, k->n_eq, k->ind_ineq.p, k->ind_eq.p, pr_diag_d, diag_buffer_d, buffer_d,
+                                               pd_buffer_d, w_d);
+    B2_CUDA(cudaGetLastError());
+    return b2_finish_aug_solve(b, k->m, l_lower_d, u_lower_d, l_diag_d, u_diag_d, w_d, stream);
+}
+
+extern "C" int b2d_kkt_mul(b2d_kkt* k, b2_bounds* b, const double* hess_d, const double* jac_d, const double* reg_d,
+                           const double* du_diag_d, const double* l_lower_d, const double* u_lower_d, const double* l_diag_d,
+                           const double* u_diag_d, double alpha, double beta, const double* x_d, double* w_d, void* stream) {
+    if (!k || !b || !x_d || !w_d || b->n_tot != (int64_t)k->n + k->ns) { set_error("b2d_kkt_mul: invalid argument"); return B2_ERR_INVALID; }
+    cudaStream_t st = as_stream(stream);
+    const int n = k->n, m = k->m;
+    if (n > 0) k_symv_lower<<<(n + 7) / 8, 256, 0, st>>>(n, n, hess_d, x_d, w_d, alpha, beta);                       // _symv!('L', alpha, hess, xx, beta, wx)
+    if (m > 0) {
+        if (n > 0) k_gemv_t<<<(n + 7) / 8, 256, 0, st>>>(m, n, m, jac_d, x_d + b->n_tot, w_d, alpha, 1.0);           // wx += alpha jac' xy
+        k_gemv_n<<<(m + GEMV_ROWS - 1) / GEMV_ROWS, 256, 0, st>>>(m, n, m, jac_d, x_d, w_d + b->n_tot, alpha, beta);                  // wy = alpha jac xx + beta wy
+    }
+    KktMulArgs a = make_kktmul(b, m, reg_d, du_diag_d, l_lower_d, u_lower_d, l_diag_d, u_diag_d, alpha, beta);
+    const int64_t tot = a.n_tot + a.m + a.nlb + a.nub;
+    if (tot) k_dcond_mul_tail<<<grid_for(tot), 256, 0, st>>>(a, n, k->ineq_pos.p, k->ind_ineq.p, x_d, w_d);
     B2_CUDA(cudaGetLastError());
     return B2_OK;
 }

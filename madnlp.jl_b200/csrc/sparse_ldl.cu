@@ -793,8 +793,9 @@ int b2_inertia(b2_solver* s, int64_t* num_pos, int64_t* num_zero, int64_t* num_n
 int b2_inertia_parts(b2_solver* s, int64_t* local_neg, int64_t* local_zero, int64_t* top_neg, int64_t* top_zero, void* stream) {
     if (!s || s->symbolic_only || !s->factorized) { set_error("b2_inertia_parts: not factorized"); return B2_ERR_FACTORIZATION; }
     cudaStream_t st = as_stream(stream);
-    B2_CUDA(cudaMemcpyAsync(s->h_counters, s->d_counters.p, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    B2_CUDA(cudaMemcpyAsync(s->h_counters, s->d_counters.p, 8 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     B2_CUDA(cudaStreamSynchronize(st));
+    if (s->h_counters[4]) { set_error("b2: dependency wait timed out inside the single-launch schedule"); return B2_ERR_FACTORIZATION; }
     if (local_neg) *local_neg = s->h_counters[0];
     if (local_zero) *local_zero = s->h_counters[1];
     if (top_neg) *top_neg = s->h_counters[2];

@@ -411,6 +411,10 @@ class DenseCondensedKKTSystem(_KKTBase):
         self.ind_eq = ind_eq
         self._ind_ineq_d = torch.from_numpy(ind_ineq).to(_DEV)
         self._ind_eq_d = torch.from_numpy(ind_eq).to(_DEV)
+        h = C.c_void_p()
+        ii = np.ascontiguousarray(ind_ineq, dtype=np.int64)
+        check(lib.b2d_kkt_create(n, m, ns, ii.ctypes.data if ns else None, C.byref(h)))
+        self._dk = _Plan(h, lib.b2d_kkt_destroy)
         self.linear_solver = linear_solver(self.aug_com, opt_linear_solver)
 
     def num_variables(self):
@@ -454,48 +458,27 @@ class DenseCondensedKKTSystem(_KKTBase):
         check(fn(self.m, self.n, self.m, ptr(self.jac), ptr(x), ptr(y), float(alpha), float(beta), _sp(self.stream)))
 
     def solve_kkt(self, w: UnreducedKKTVector):
-        """src/IPM/factorization.jl:190-229."""
-        n, ns = self.n, self.ns
-        full = w.values
-        wx = full[:n]; ws = full[n:n + ns]
-        dual = w.dual()
-        Ss = self.pr_diag[n:n + ns]
-        self.reduce_rhs(w)
-        self.buffer.zero_()
-        wz = dual[self._ind_ineq_d]
-        self.buffer[self._ind_ineq_d] = self.diag_buffer * (wz + ws / Ss)
-        x = self.pd_buffer
-        x[:n] = wx
-        self._gemv(True, self.buffer, x, 1.0, 1.0)            # xx = jac' * buffer + wx
-        x[n:] = dual[self._ind_eq_d]
-        self.linear_solver.solve_linear_system(x)
-        wx.copy_(x[:n])
-        self._gemv(False, wx, dual, 1.0, 0.0)                  # dual(w) = jac * wx
-        dual[self._ind_eq_d] = x[n:]
-        dual[self._ind_ineq_d] = dual[self._ind_ineq_d] * self.diag_buffer
-        dual -= self.buffer
-        ws.copy_((ws + dual[self._ind_ineq_d]) / Ss)
-        self.finish_aug_solve(w)
+        """src/IPM/factorization.jl:190-229: own kernels around the dense solve (b2d_kkt_solve_pre / _post)."""
+        sp = _sp(self.stream)
+        check(lib.b2d_kkt_solve_pre(self._dk.h, self._bounds.h, ptr(self.jac), ptr(self.pr_diag), ptr(self.diag_buffer),
+                                    ptr(self.l_diag), ptr(self.u_diag), ptr(self.buffer), ptr(self.pd_buffer), ptr(w.values), sp))
+        self.linear_solver.solve_linear_system(self.pd_buffer)
+        check(lib.b2d_kkt_solve_post(self._dk.h, self._bounds.h, ptr(self.jac), ptr(self.pr_diag), ptr(self.diag_buffer),
+                                     ptr(self.l_lower), ptr(self.u_lower), ptr(self.l_diag), ptr(self.u_diag), ptr(self.buffer),
+                                     ptr(self.pd_buffer), ptr(w.values), sp))
         return w
 
     def mul(self, w, x, alpha=1.0, beta=0.0):
-        """src/IPM/factorization.jl:326-344 (AbstractDenseKKTSystem)."""
-        n = self.n
-        wp, xp = w.primal(), x.primal()
-        wx, ws = wp[:n], wp[n:]
-        xx, xs = xp[:n], xp[n:]
-        wy, xy = w.dual(), x.dual()
-        check(lib.b2d_symv_lower(n, n, ptr(self.hess), ptr(xx), ptr(wx), float(alpha), float(beta), _sp(self.stream)))   # _symv!('L', ...)
-        if self.m > 0:
-            self._gemv(True, xy, wx, alpha, 1.0)
-            self._gemv(False, xx, wy, alpha, beta)
-        if beta == 0.0:
-            ws.copy_(-alpha * xy[self._ind_ineq_d])
-        else:
-            ws.copy_(beta * ws - alpha * xy[self._ind_ineq_d])
-        wy[self._ind_ineq_d] -= alpha * xs
-        self._kktmul(w, x, alpha, beta)
+        """src/IPM/factorization.jl:303-324 (AbstractDenseKKTSystem): symv + 2 gemv + one fused tail kernel (b2d_kkt_mul)."""
+        check(lib.b2d_kkt_mul(self._dk.h, self._bounds.h, ptr(self.hess), ptr(self.jac), ptr(self.reg), ptr(self.du_diag),
+                              ptr(self.l_lower), ptr(self.u_lower), ptr(self.l_diag), ptr(self.u_diag), float(alpha), float(beta),
+                              ptr(x.values), ptr(w.values), _sp(self.stream)))
         return w
+
+    def jtprod(self, y, x):
+        """src/KKT/Dense/utils.jl:12-23: y[1:n] = jac' x ; y[n + k] = -x[ind_ineq[k]] (not on the per-iteration solve path)."""
+        self._gemv(True, x, y[: self.n], 1.0, 0.0)
+        y[self.n:] = -x[self._ind_ineq_d]
 
 
 def create_kkt_system(kkt_type, cb, linear_solver=None, opt_linear_solver=None):

@@ -35,6 +35,16 @@ def device_view(ptr, n):
 class DistributedSparseSolver:
     input_type = "csc"
 
+    def _on_stream(self):
+        """the b2_* kernels run on `self.stream`; torch.distributed orders its collectives against torch's CURRENT stream --
+        make the two the same for the duration of a call (a raw cudaStream_t cannot be made current: refuse it)"""
+        import contextlib
+        if self.stream is None:
+            return contextlib.nullcontext()
+        if not isinstance(self.stream, torch.cuda.Stream):
+            raise TypeError("DistributedSparseSolver needs a torch.cuda.Stream (or None = current stream)")
+        return torch.cuda.stream(self.stream)
+
     def __init__(self, csc, opt=None, rank=None, world=None, group=None, stream=None):
         capi.require_device()
         self.rank = dist.get_rank() if rank is None else rank
@@ -77,22 +87,24 @@ class DistributedSparseSolver:
         return True
 
     def factorize(self):
-        sp = capi.stream_ptr(self.stream)
-        check(lib.b2_factorize_local(self._h, sp))
-        if self._xf is not None and self.world > 1:
-            dist.all_reduce(self._xf, group=self.group)
-        check(lib.b2_factorize_top(self._h, sp))
+        with self._on_stream():
+            sp = capi.stream_ptr(self.stream)
+            check(lib.b2_factorize_local(self._h, sp))
+            if self._xf is not None and self.world > 1:
+                dist.all_reduce(self._xf, group=self.group)
+            check(lib.b2_factorize_top(self._h, sp))
         return self
 
     def solve_linear_system(self, x):
-        sp = capi.stream_ptr(self.stream)
-        check(lib.b2_solve_fwd_local(self._h, x.data_ptr(), sp))
-        if self._xv is not None and self.world > 1:
-            dist.all_reduce(self._xv, group=self.group)
-        check(lib.b2_solve_top(self._h, x.data_ptr(), sp))
-        check(lib.b2_solve_bwd_local(self._h, x.data_ptr(), sp))
-        if self.world > 1:
-            dist.all_reduce(x, group=self.group)
+        with self._on_stream():
+            sp = capi.stream_ptr(self.stream)
+            check(lib.b2_solve_fwd_local(self._h, x.data_ptr(), sp))
+            if self._xv is not None and self.world > 1:
+                dist.all_reduce(self._xv, group=self.group)
+            check(lib.b2_solve_top(self._h, x.data_ptr(), sp))
+            check(lib.b2_solve_bwd_local(self._h, x.data_ptr(), sp))
+            if self.world > 1:
+                dist.all_reduce(x, group=self.group)
         return x
 
     def is_inertia(self):
@@ -103,7 +115,8 @@ class DistributedSparseSolver:
         check(lib.b2_inertia_parts(self._h, C.byref(a), C.byref(b), C.byref(c), C.byref(d), capi.stream_ptr(self.stream)))
         loc = torch.tensor([a.value, b.value], dtype=torch.int64, device="cuda")
         if self.world > 1:
-            dist.all_reduce(loc, group=self.group)
+            with self._on_stream():
+                dist.all_reduce(loc, group=self.group)
         neg = int(loc[0].item()) + c.value
         zero = int(loc[1].item()) + d.value
         return (self.n - neg - zero, zero, neg)

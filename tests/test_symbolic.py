@@ -173,3 +173,44 @@ def test_random_patterns_factor_and_solve(n, density, n_neg, ordering, nemin, pa
     assert (rowval >= np.repeat(np.arange(n), np.diff(colptr))).all()          # lower triangle, sorted rows
     nz = _well_conditioned_values(colptr, rowval, n, rng, n_neg=n_neg)
     _check(n, colptr, rowval, nz, n_neg, tol=1e-8, ordering=ordering, nemin=nemin, n_parts=parts, part_rank=0)
+
+
+@pytest.mark.parametrize("ordering", [0, 1])
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_duals_sharing_a_primal_neighbour_get_distinct_partners(ordering, seed):
+    """Augmented KKT with a ZERO (2,2) block where two equality rows touch the SAME two variables: a fill-reducing
+    ordering eliminates the (degree-2) duals first; moving both to just after their common earliest neighbour u leaves the
+    rank-one Schur block -(a_i a_j)/d_u and the second dual pivot cancels exactly.  The ordering constraint therefore matches
+    every dual with a DISTINCT preceding primal neighbour -> inertia exactly (n_tot, 0, m) with 1 x 1 static pivots, as
+    Bunch-Kaufman (dsytrf) reports."""
+    rng = np.random.default_rng(seed)
+    n_tot, m = 8, 2
+    R = rng.standard_normal((n_tot, n_tot))
+    H = R @ R.T + n_tot * np.eye(n_tot)              # dense SPD block: every primal has a high degree
+    rows, cols, vals = [], [], []
+    for j in range(n_tot):
+        for i in range(j, n_tot):
+            rows.append(i); cols.append(j); vals.append(H[i, j])
+    for c in range(m):                               # both constraints couple variables 0 and 1 only
+        for j in (0, 1):
+            rows.append(n_tot + c); cols.append(j); vals.append(rng.uniform(0.5, 2.0) * (1.0 if (c + j) % 2 else -1.0))
+        rows.append(n_tot + c); cols.append(n_tot + c); vals.append(0.0)
+    N = n_tot + m
+    cp, rv, mp = o.coo_to_csc(np.array(rows), np.array(cols), N, N)
+    nz = np.zeros(len(rv)); o.transfer(nz, np.array(vals), mp)
+    truth = o.DenseLDLInertiaSolver(cp, rv, nz, N).factorize().inertia()
+    assert truth == (n_tot, 0, m)
+    S = Symbolic(N, cp, rv, ordering=ordering, kkt_n_primal=n_tot)
+    assert S.factorize(nz) == (n_tot, 0, m)
+    # structural statement of the matching: a system of distinct representatives among PRECEDING primal neighbours exists
+    iperm = np.empty(N, dtype=np.int64); iperm[S.perm] = np.arange(N)
+    full = o.tril_to_full(cp, rv, np.ones(len(rv)), N).toarray() != 0
+    used = set()
+    for v in sorted(range(n_tot, N), key=lambda q: iperm[q]):
+        cand = [u for u in range(n_tot) if full[v, u] and iperm[u] < iperm[v] and u not in used]
+        assert cand, "dual %d has no unused preceding primal neighbour" % v
+        used.add(min(cand, key=lambda u: iperm[u]))
+    b = rng.standard_normal(N)
+    x = S.solve(b)
+    xr = np.linalg.solve(o.tril_to_full(cp, rv, nz, N).toarray(), b)
+    assert np.abs(x - xr).max() / np.abs(xr).max() < 1e-9
