@@ -169,7 +169,7 @@ def _all_cores_worker(args_tuple):
     return dt
 
 
-def cpu_all_cores_throughput(name, steps=12):
+def cpu_all_cores_throughput(name, steps=6):
     """what ALL host cores can deliver on this workload: one independent IPM replay per core (the factorisation itself is
     sequential in the reference), aggregate steps/s.  Not a single-problem speed: a throughput ceiling for context."""
     import multiprocessing as mp

@@ -2,6 +2,7 @@
 // C-ABI declared in include/b200kkt.h; replaces the AbstractLinearSolver back-end role of CUDSSSolver
 // (lib/MadNLPGPU/ext/MadNLPGPUCUDAExt/cudss.jl:88-214) / Ma97Solver (lib/MadNLPHSL/src/ma97.jl:29-115).
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 #include <vector>
@@ -13,6 +14,7 @@
 #include "solve_kernels.cuh"
 #include "warp_kernels.cuh"
 #include "bigsolve_kernels.cuh"
+#include "densesolve_kernels.cuh"
 
 using namespace b2;
 
@@ -985,7 +987,7 @@ struct b2d_solver {
     int32_t N = 0, lda = 0;
     const double* A_d = nullptr;
     b2_options opt;
-    DevBuf<double> fact, dvec, linv, side;
+    DevBuf<double> fact, dvec, linv, side, flow;     // flow: [2][nblk*128] hand-off vectors of the single-launch solve
     DevBuf<int64_t> linv_off;
     DevBuf<FrontDesc> desc;
     DevBuf<int32_t> list, counters;
@@ -1012,7 +1014,7 @@ void enqueue_dense_factor(b2d_solver* s, cudaStream_t st) {
     a.desc = s->desc.p; a.child_idx = nullptr; a.rel = nullptr; a.amap_src = nullptr; a.amap_dst = nullptr;
     a.A = nullptr; a.L = s->fact.p; a.ws = nullptr; a.dvec = s->dvec.p; a.counters = s->counters.p; a.eps = s->opt.pivot_eps;
     const int N = s->N;
-    cudaMemsetAsync(s->counters.p, 0, 4 * sizeof(int32_t), st);
+    cudaMemsetAsync(s->counters.p, 0, 2 * sizeof(int32_t), st);     // [2] = sticky error flag of the dataflow solve
     k_copy_lower<<<dim3(std::max(1, std::min(8, (N + 255) / 256)), N), 256, 0, st>>>(N, s->lda, s->A_d, s->fact.p);
     for (int ob = 0; ob < N; ob += DB) launch_big_step(a, s->list.p, 1, ob, N, s->linv.p, s->linv_off.p, st, nullptr);
 }
@@ -1037,11 +1039,12 @@ int b2d_create(int32_t N, int32_t lda, const double* A_d, const b2_options* opt,
     int32_t zero = 0;
     int64_t zero64 = 0;
     if (s->side.alloc(N) != cudaSuccess || s->linv.alloc((size_t)((N + BS - 1) / BS) * BS * BS) != cudaSuccess || s->linv_off.upload(&zero64, 1) != cudaSuccess ||
-        s->fact.alloc((size_t)N * N) != cudaSuccess || s->dvec.alloc(N) != cudaSuccess || s->desc.upload(&d, 1) != cudaSuccess ||
+        s->fact.alloc((size_t)N * N) != cudaSuccess || s->dvec.alloc(N) != cudaSuccess ||
+        s->flow.alloc((size_t)2 * ((N + BS - 1) / BS) * BS) != cudaSuccess || s->desc.upload(&d, 1) != cudaSuccess ||
         s->list.upload(&zero, 1) != cudaSuccess || s->counters.alloc(4) != cudaSuccess ||
         cudaMallocHost((void**)&s->h_counters, 4 * sizeof(int32_t)) != cudaSuccess ||
         cudaStreamCreateWithFlags(&s->cap_stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaMemset(s->fact.p, 0, s->fact.bytes()) != cudaSuccess) {
+        cudaMemset(s->fact.p, 0, s->fact.bytes()) != cudaSuccess || cudaMemset(s->counters.p, 0, 4 * sizeof(int32_t)) != cudaSuccess) {
         delete s;
         return cuda_fail(cudaGetLastError(), "b2d_create allocation", __FILE__, __LINE__);
     }
@@ -1083,6 +1086,7 @@ int b2d_inertia_enqueue(b2d_solver* s, void* stream) {
 
 int b2d_inertia_fetch(b2d_solver* s, int64_t* num_pos, int64_t* num_zero, int64_t* num_neg) {
     if (!s || !s->factorized) { set_error("b2d_inertia: not factorized"); return B2_ERR_FACTORIZATION; }
+    if (s->h_counters[2]) { set_error("b2d: a hand-off wait timed out inside the single-launch solve"); return B2_ERR_SOLVE; }
     const int64_t neg = s->h_counters[0], zero = s->h_counters[1];
     if (num_neg) *num_neg = neg;
     if (num_zero) *num_zero = zero;
@@ -1103,11 +1107,24 @@ int b2d_solve(b2d_solver* s, double* x_d, int32_t nrhs, void* stream) {
     cudaStream_t st = as_stream(stream);
     const int N = s->N;
     const int nblk = (N + BS - 1) / BS;
+    static int flow_ok = -1;            // every CTA of the dataflow kernel must be resident: one per SM
+    if (flow_ok < 0) {
+        flow_ok = cudaFuncSetAttribute(k_dense_solve_flow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DS_SMEM) == cudaSuccess ? 1 : 0;
+        if (const char* e = getenv("B2_DENSE_SOLVE_FLOW")) flow_ok = flow_ok && atoi(e) != 0;
+    }
     for (int c = 0; c < nrhs; ++c) {
+        double* x = x_d + (size_t)c * N;
+        if (flow_ok && nblk <= sm_count()) {
+            // ONE launch: block row / block column k is owned by CTA k, hand-off through sentinel-initialised vectors
+            B2_CUDA(cudaMemsetAsync(s->flow.p, 0xFF, s->flow.bytes(), st));
+            k_dense_solve_flow<<<nblk, DS_NT, DS_SMEM, st>>>(N, s->fact.p, s->linv.p, s->dvec.p, x, s->flow.p, s->flow.p + (size_t)nblk * BS,
+                                                            s->counters.p + 2);
+            continue;
+        }
         BigSolveArgs bs;
         SolveArgs& a = bs.s;
         a.desc = s->desc.p; a.rows = nullptr; a.child_idx = nullptr; a.rel = nullptr; a.cbv_off = s->linv_off.p;   // single zero offset
-        a.L = s->fact.p; a.Lt = nullptr; a.dvec = s->dvec.p; a.xp = x_d + (size_t)c * N; a.cbv = nullptr;
+        a.L = s->fact.p; a.Lt = nullptr; a.dvec = s->dvec.p; a.xp = x; a.cbv = nullptr;
         bs.Linv = s->linv.p; bs.linv_off = s->linv_off.p; bs.side = s->side.p;
         k_bs_head<<<1, BS_NT, 0, st>>>(bs, s->list.p, 0, 0);
         for (int b = 0; b < nblk; ++b) {

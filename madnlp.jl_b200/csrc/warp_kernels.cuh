@@ -237,7 +237,8 @@ __device__ __forceinline__ void front_factor_team(const FactorArgs& a, const Chi
 #pragma unroll
         for (int j = 0; j < FMAX; ++j) if (j <= ir) CBo[(size_t)j * r + ir] = av[j];
     }
-    if (DEP) __threadfence();
+    // hand-off: the team barrier orders every thread's stores before thread 0's st.release.gpu (release is cumulative over the
+    // barrier's synchronises-with edge -- the CUTLASS semaphore pattern), so no team-wide __threadfence() is needed
     team_sync<NW>(team);
     if (DEP && tid == 0) flag_set(done + s);
     B2_STAMP(7);
@@ -385,7 +386,8 @@ __device__ __forceinline__ void front_fwd_team(const SolveArgs& a, const ChildRe
         }
     }
     if (tid < f) { if (tid < w) a.xp[d.col0 + tid] = y; else a.cbv[a.cbv_off[s] + tid - w] = y; }
-    if (DEP) __threadfence();
+    // hand-off: the team barrier orders every thread's stores before thread 0's st.release.gpu (release is cumulative over the
+    // barrier's synchronises-with edge -- the CUTLASS semaphore pattern), so no team-wide __threadfence() is needed
     team_sync<NW>(team);
     if (DEP && tid == 0) flag_set(done + s);
 }
@@ -473,7 +475,8 @@ __device__ __forceinline__ void front_bwd_team(const SolveArgs& a, int s, double
         }
     }
     if (tid < w) a.xp[d.col0 + tid] = t;
-    if (DEP) __threadfence();
+    // hand-off: the team barrier orders every thread's stores before thread 0's st.release.gpu (release is cumulative over the
+    // barrier's synchronises-with edge -- the CUTLASS semaphore pattern), so no team-wide __threadfence() is needed
     team_sync<NW>(team);
     if (DEP && tid == 0) flag_set(done + s);
 }

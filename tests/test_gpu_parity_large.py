@@ -124,10 +124,19 @@ def test_dense_condensed_full_size(n_eq):
     assert okc and okg
     dc = x.full(); dg = xg.values.cpu().numpy()
     assert np.abs(dg - dc).max() / np.abs(dc).max() <= 1e-8
-    # mul! alone (the DenseCondensed wrappers are own kernels, no torch ops): K * d == rhs on the unreduced system
-    yc = o.UnreducedKKTVector.for_kkt(kc); kc.mul(yc, x)
-    yg = K.UnreducedKKTVector.for_kkt(kg); kg.mul(yg, xg)
-    assert np.abs(yg.values.cpu().numpy() - yc.full()).max() <= 1e-9 * (np.abs(yc.full()).max() + 1.0)
+    # mul! and solve_kkt! alone on the SAME input (the DenseCondensed wrappers are own kernels, no torch ops); tolerance: a few
+    # ulps of the largest term of a row, |K| |x|  (summation order differs)
+    xin = np.random.default_rng(9).standard_normal(len(dc))
+    xc2 = o.UnreducedKKTVector.for_kkt(kc); xc2.full()[:] = xin
+    xg2 = K.UnreducedKKTVector.for_kkt(kg); xg2.values.copy_(_dev(xin))
+    yc = o.UnreducedKKTVector.for_kkt(kc); yc.full()[:] = 1.0; kc.mul(yc, xc2, -0.5, 2.0)
+    yg = K.UnreducedKKTVector.for_kkt(kg); yg.values.fill_(1.0); kg.mul(yg, xg2, -0.5, 2.0)
+    scale = (np.abs(qp.P).sum(axis=1).max() + np.abs(qp.A).sum(axis=0).max() + np.abs(qp.A).sum(axis=1).max()
+             + max(np.abs(it[k]).max() for k in ("reg", "l_diag", "u_diag", "l_lower", "u_lower")) + 2.0) * np.abs(xin).max()
+    assert np.abs(yg.values.cpu().numpy() - yc.full()).max() <= 1e-13 * scale
+    kc.solve_kkt(xc2); kg.solve_kkt(xg2)
+    sc = xc2.full()
+    assert np.abs(xg2.values.cpu().numpy() - sc).max() <= 1e-7 * np.abs(sc).max()     # unrefined single solve, kappa ~ 1e9
 
 
 def _product_perm(N, cp, rv, **opts):
