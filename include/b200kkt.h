@@ -173,6 +173,11 @@ int b2d_solve(b2d_solver* s, double* x_d, int32_t nrhs, void* stream);
 int b2_coo_to_csc(int32_t m, int32_t n, int64_t nnz_coo, const int32_t* I_h, const int32_t* J_h,
                   int32_t* colptr_h, int32_t* rowval_h, int64_t* map_h, int64_t* nnz_csc);
 
+/* The same construction with device sorts (lib/MadNLPGPU/src/KKT/gpu_sparse.jl:260-302): I_d, J_d, and all outputs are DEVICE arrays
+ * (rowval_d capacity nnz_coo); identical output to b2_coo_to_csc.  Synchronises `stream` once to return *nnz_csc. */
+int b2_coo_to_csc_device(int32_t m, int32_t n, int64_t nnz_coo, const int32_t* I_d, const int32_t* J_d,
+                         int32_t* colptr_d, int32_t* rowval_d, int64_t* map_d, int64_t* nnz_csc, void* stream);
+
 /* Device plan for  dst .= 0; dst[map[k]] += V[k]  (src/matrixtools.jl:79-88) as a race-free,
  * deterministic segmented gather: one thread per destination slot summing its sources in COO
  * order -- bit-identical to the reference's sequential CPU loop. */

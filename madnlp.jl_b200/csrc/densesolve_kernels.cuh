@@ -101,28 +101,33 @@ __global__ void __launch_bounds__(DS_NT, 1) k_dense_solve_flow(int N, const doub
         ybuf[(size_t)k * BS + r] = yk;                                        // publish y_k (consumers: the block rows below)
     }
     // ---------------- diagonal + backward
+    // s_k(j) -= sum_i L(cb + i, kb + j) x_c(i): a warp owns 4 columns j, its lanes stride the rows i (each load instruction reads
+    // 32 consecutive rows of one column: coalesced), column sums meet through shuffles; `sacc` lives in the threads tid < BS
     double s = (g == 0 && r < nb) ? yk / dvec[kb + r] : 0.0;
+    const int warp = tid >> 5, lane = tid & 31;
     for (int c = nblk - 1; c > k; --c) {
-        {                                                                     // L(c*BS + g*16 + q, kb + r): 16 contiguous rows
-            const int cb = c * BS, ncb = min(BS, N - cb);
-            const double* p = L + (size_t)(kb + min(r, nb - 1)) * N + cb + g * 16;
+        const int cb = c * BS, ncb = min(BS, N - cb);
 #pragma unroll
-            for (int q = 0; q < 16; ++q) v[q] = (r < nb && g * 16 + q < ncb) ? p[q] : 0.0;
+        for (int q = 0; q < 4; ++q) {
+            const int j = warp * 4 + q;
+            const double* p = L + (size_t)(kb + min(j, nb - 1)) * N + cb;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[q * 4 + u] = (j < nb && lane + 32 * u < ncb) ? p[lane + 32 * u] : 0.0;
         }
         const int b = c & 1;
         if (tid < BS) vec[b][tid] = ds_poll(xbuf + (size_t)c * BS + tid, err);
         __syncthreads();
-        double acc = 0.0;
 #pragma unroll
-        for (int q = 0; q < 16; ++q) acc = fma(v[q], vec[b][g * 16 + q], acc);
-        part[b][g][r] = acc;
-        __syncthreads();
-        if (g == 0) {
-            double sum = 0.0;
+        for (int q = 0; q < 4; ++q) {
+            double acc = 0.0;
 #pragma unroll
-            for (int u = 0; u < 8; ++u) sum += part[b][u][r];
-            s -= sum;
+            for (int u = 0; u < 4; ++u) acc = fma(v[q * 4 + u], vec[b][lane + 32 * u], acc);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (lane == 0) part[b][0][warp * 4 + q] = acc;
         }
+        __syncthreads();
+        if (g == 0) s -= part[b][0][r];
     }
     __syncthreads();
     if (g == 0) tk[r] = s;

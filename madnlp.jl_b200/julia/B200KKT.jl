@@ -17,6 +17,7 @@ import MadNLP: AbstractLinearSolver, AbstractOptions, MadNLPLogger, SymbolicExce
     SolveException, factorize!, solve_linear_system!, is_inertia, inertia, improve!, introduce, input_type,
     default_options, is_supported, is_async
 using CUDA, CUDA.CUSPARSE
+# (nothing here extends a method on types this module does not own without one of ITS types in the signature)
 
 const libb200kkt = get(ENV, "B200KKT_LIB", "libb200kkt.so")
 
@@ -106,33 +107,186 @@ is_supported(::Type{<:B200Solver}, ::Type{Float32}) = false
 is_async(::B200Solver) = true
 
 # ---------------------------------------------------------------------------------------------------------------------
-# Assembly overloads on CuVector storage: the same leaf functions MadNLPGPU overloads
-# (lib/MadNLPGPU/src/KKT/gpu_sparse.jl:308-382), now one ccall each.  `kkt.ext` holds the native plans created in
-# get_sparse_condensed_ext (one-time): ext.cond (b2_condensed_plan), ext.hess_plan / ext.jt_plan (b2_transfer_plan).
+# KKT-level overloads.  Dispatch is on OUR solver type in the `LS` parameter of the stock KKT structs
+#   SparseCondensedKKTSystem{T,VT,MT,QN,LS,...} (src/KKT/Sparse/condensed.jl:7)   with VT <: CuVector AND LS <: B200Solver
+#   DenseCondensedKKTSystem{T,VT,MT,QN,LS,VI}   (src/KKT/Dense/condensed.jl:10)   with VT <: CuVector AND LS <: B200DenseSolver
+# -- strictly more specific than MadNLPGPU's `VT <: AbstractGPUVector` methods (lib/MadNLPGPU/src/KKT/gpu_sparse.jl:308-382,
+# gpu_dense.jl:86-138), so loading both packages is neither ambiguous nor type piracy (a type this module owns is in every
+# signature).  The native plans live in the solver object (which this module owns), built lazily from the kkt's own maps at
+# the first call: MadNLP's `ext` slot (get_sparse_condensed_ext, gpu_sparse.jl:100-130) keeps whatever MadNLPGPU put there.
 # ---------------------------------------------------------------------------------------------------------------------
-function MadNLP.build_kkt!(kkt::MadNLP.SparseCondensedKKTSystem{T,VT}) where {T, VT <: CuVector{T}}
-    rc = ccall((:b2_condensed_assemble, libb200kkt), Cint,
+mutable struct CondensedPlans
+    cond::Ptr{Cvoid}        # b2_condensed_plan   (pattern of tril(H) U diag U tril(Jt Jt') + the dptr/hptr/jptr maps)
+    hess_plan::Ptr{Cvoid}   # b2_transfer_plan    hess_raw (COO) -> hess_com (CSC)
+    jt_plan::Ptr{Cvoid}     # b2_transfer_plan    jt_coo         -> jt_csc
+    hess_spmv::Ptr{Cvoid}   # b2_spmv_plan of hess_com
+    jt_spmv::Ptr{Cvoid}     # b2_spmv_plan of jt_csc
+    bounds::Ptr{Cvoid}      # b2_bounds (ind_lb / ind_ub and their inverse maps)
+end
+
+const _plans = IdDict{Any,CondensedPlans}()     # solver handle -> plans (freed with the solver)
+
+const B200CondensedKKT{T} = MadNLP.SparseCondensedKKTSystem{T,VT,MT,QN,LS} where {VT<:CuVector{T},MT,QN,LS<:B200Solver}
+
+function plans(kkt::B200CondensedKKT{T}) where T
+    get!(_plans, kkt.linear_solver) do
+        n = size(kkt.hess_com, 1); m = size(kkt.jt_csc, 2)
+        h0(v) = Array(v) .- one(eltype(v))                                   # host, 0-based
+        hcp, hrv = h0(kkt.hess_com.colPtr), h0(kkt.hess_com.rowVal)
+        jcp, jrv = h0(kkt.jt_csc.colPtr), h0(kkt.jt_csc.rowVal)
+        cond = Ref{Ptr{Cvoid}}(C_NULL); nnz_aug = Ref{Int64}(0)
+        check(ccall((:b2_condensed_symbolic, libb200kkt), Cint,
+            (Int32, Int32, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Ptr{Cvoid}}, Ptr{Int64}),
+            n, m, hcp, hrv, jcp, jrv, cond, nnz_aug), SymbolicException)
+        @assert nnz_aug[] == length(MadNLP.nzval(kkt.aug_com))               # same pattern as build_condensed_aug_symbolic
+        tplan(map_d) = begin
+            mp = Array(map_d) .- 1; h = Ref{Ptr{Cvoid}}(C_NULL)
+            check(ccall((:b2_transfer_plan_create, libb200kkt), Cint, (Int64, Int64, Ptr{Int64}, Ptr{Ptr{Cvoid}}),
+                length(mp), maximum(mp; init = -1) + 1, mp, h), SymbolicException); h[]
+        end
+        splan(nr, nc, cp, rv) = begin
+            h = Ref{Ptr{Cvoid}}(C_NULL)
+            check(ccall((:b2_spmv_plan_create, libb200kkt), Cint, (Int32, Int32, Ptr{Int32}, Ptr{Int32}, Ptr{Ptr{Cvoid}}), nr, nc, cp, rv, h), SymbolicException); h[]
+        end
+        lb = Array(kkt.ind_lb) .- 1; ub = Array(kkt.ind_ub) .- 1; b = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:b2_bounds_create, libb200kkt), Cint, (Int64, Int64, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Ptr{Cvoid}}),
+            length(kkt.pr_diag), length(lb), length(ub), lb, ub, b), SymbolicException)
+        CondensedPlans(cond[], tplan(kkt.hess_csc_map), tplan(kkt.jt_csc_map), splan(n, n, hcp, hrv), splan(n, m, jcp, jrv), b[])
+    end
+end
+
+function MadNLP.build_kkt!(kkt::B200CondensedKKT{T}) where T
+    p = plans(kkt)
+    check(ccall((:b2_condensed_assemble, libb200kkt), Cint,
         (Ptr{Cvoid}, CuPtr{T}, CuPtr{T}, CuPtr{T}, CuPtr{T}, CuPtr{T}, CuPtr{T}, Ptr{Cvoid}),
-        kkt.ext.cond, pointer(MadNLP.nzval(kkt.aug_com)), pointer(kkt.pr_diag), pointer(kkt.du_diag),
-        pointer(MadNLP.nzval(kkt.hess_com)), pointer(MadNLP.nzval(kkt.jt_csc)), pointer(kkt.diag_buffer), stream_ptr())
-    check(rc, FactorizationException)
+        p.cond, pointer(MadNLP.nzval(kkt.aug_com)), pointer(kkt.pr_diag), pointer(kkt.du_diag),
+        pointer(MadNLP.nzval(kkt.hess_com)), pointer(MadNLP.nzval(kkt.jt_csc)), pointer(kkt.diag_buffer), stream_ptr()), FactorizationException)
 end
 
-function MadNLP.compress_hessian!(kkt::MadNLP.SparseCondensedKKTSystem{T,VT}) where {T, VT <: CuVector{T}}
+function MadNLP.compress_hessian!(kkt::B200CondensedKKT{T}) where T
     check(ccall((:b2_transfer, libb200kkt), Cint, (Ptr{Cvoid}, CuPtr{T}, CuPtr{T}, Ptr{Cvoid}),
-        kkt.ext.hess_plan, pointer(MadNLP.nzval(kkt.hess_com)), pointer(kkt.hess_raw.V), stream_ptr()), FactorizationException)
+        plans(kkt).hess_plan, pointer(MadNLP.nzval(kkt.hess_com)), pointer(kkt.hess_raw.V), stream_ptr()), FactorizationException)
 end
 
-function MadNLP.compress_jacobian!(kkt::MadNLP.SparseCondensedKKTSystem{T,VT}) where {T, VT <: CuVector{T}}
+function MadNLP.compress_jacobian!(kkt::B200CondensedKKT{T}) where T
     check(ccall((:b2_transfer, libb200kkt), Cint, (Ptr{Cvoid}, CuPtr{T}, CuPtr{T}, Ptr{Cvoid}),
-        kkt.ext.jt_plan, pointer(MadNLP.nzval(kkt.jt_csc)), pointer(kkt.jt_coo.V), stream_ptr()), FactorizationException)
+        plans(kkt).jt_plan, pointer(MadNLP.nzval(kkt.jt_csc)), pointer(kkt.jt_coo.V), stream_ptr()), FactorizationException)
 end
 
-# transfer!(dest::CuSparseMatrixCSC, src::SparseMatrixCOO, plan) for SparseKKTSystem (accumulating, unlike
-# lib/MadNLPGPU/ext/MadNLPGPUCUDAExt/cuda_sparse.jl:6-12 which drops duplicates)
-function b200_transfer!(dest_nz::CuVector{T}, V::CuVector{T}, plan::Ptr{Cvoid}) where T
-    check(ccall((:b2_transfer, libb200kkt), Cint, (Ptr{Cvoid}, CuPtr{T}, CuPtr{T}, Ptr{Cvoid}),
-        plan, pointer(dest_nz), pointer(V), stream_ptr()), FactorizationException)
+# solve_kkt! (src/IPM/factorization.jl:143-167): pre -> b2_solve -> post
+function MadNLP.solve_kkt!(kkt::B200CondensedKKT{T}, w::MadNLP.AbstractKKTVector) where T
+    p = plans(kkt); n = size(kkt.hess_com, 1); m = size(kkt.jt_csc, 2); wv = MadNLP.full(w)
+    check(ccall((:b2_condensed_solve_pre, libb200kkt), Cint,
+        (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64, CuPtr{T}, CuPtr{T}, CuPtr{T}, CuPtr{T}, CuPtr{T}, CuPtr{T}, CuPtr{T}, Ptr{Cvoid}),
+        p.bounds, p.jt_spmv, n, m, pointer(MadNLP.nzval(kkt.jt_csc)), pointer(kkt.pr_diag), pointer(kkt.diag_buffer),
+        pointer(kkt.l_diag), pointer(kkt.u_diag), pointer(kkt.buffer), pointer(wv), stream_ptr()), SolveException)
+    solve_linear_system!(kkt.linear_solver, view(wv, 1:n))
+    check(ccall((:b2_condensed_solve_post, libb200kkt), Cint,
+        (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64, CuPtr{T}, CuPtr{T}, CuPtr{T}, CuPtr{T}, CuPtr{T}, CuPtr{T}, CuPtr{T}, CuPtr{T}, CuPtr{T}, Ptr{Cvoid}),
+        p.bounds, p.jt_spmv, n, m, pointer(MadNLP.nzval(kkt.jt_csc)), pointer(kkt.pr_diag), pointer(kkt.diag_buffer),
+        pointer(kkt.l_lower), pointer(kkt.u_lower), pointer(kkt.l_diag), pointer(kkt.u_diag), pointer(kkt.buffer), pointer(wv), stream_ptr()), SolveException)
+    return w
+end
+solve_linear_system!(M::B200Solver{T}, x::SubArray{T,1,<:CuVector{T}}) where T =
+    (check(ccall((:b2_solve, libb200kkt), Cint, (Ptr{Cvoid}, CuPtr{T}, Int32, Ptr{Cvoid}), M.handle, pointer(x), 1, stream_ptr()), SolveException); x)
+
+# mul!(w, kkt, x, alpha, beta) (src/IPM/factorization.jl:303-324) incl. _kktmul!: ONE kernel instead of 3 SpMV + broadcasts
+function MadNLP.mul!(w::MadNLP.AbstractKKTVector{T}, kkt::B200CondensedKKT{T}, x::MadNLP.AbstractKKTVector, alpha = one(T), beta = zero(T)) where T
+    p = plans(kkt); n = size(kkt.hess_com, 1); m = size(kkt.jt_csc, 2)
+    check(ccall((:b2_condensed_kkt_mul, libb200kkt), Cint,
+        (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64, CuPtr{T}, CuPtr{T}, CuPtr{T}, CuPtr{T}, CuPtr{T}, CuPtr{T}, CuPtr{T}, CuPtr{T},
+         Cdouble, Cdouble, CuPtr{T}, CuPtr{T}, Ptr{Cvoid}),
+        p.bounds, p.hess_spmv, p.jt_spmv, n, m, pointer(MadNLP.nzval(kkt.hess_com)), pointer(MadNLP.nzval(kkt.jt_csc)),
+        pointer(kkt.reg), pointer(kkt.du_diag), pointer(kkt.l_lower), pointer(kkt.u_lower), pointer(kkt.l_diag), pointer(kkt.u_diag),
+        alpha, beta, pointer(MadNLP.full(x)), pointer(MadNLP.full(w)), stream_ptr()), SolveException)
+    return w
+end
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Dense back-end: role of LapackCUDASolver (lib/MadNLPGPU/ext/MadNLPGPUCUDAExt/cusolver.jl:150-187), plus inertia
+# ---------------------------------------------------------------------------------------------------------------------
+mutable struct B200DenseSolver{T} <: AbstractLinearSolver{T}
+    handle::Ptr{Cvoid}
+    A::CuMatrix{T}                      # kept by reference (src/LinearSolvers/lapack.jl:40); lower triangle is read
+    kkt_plan::Ptr{Cvoid}                # b2d_kkt (index sets of the DenseCondensed wrappers), created on first use
+    bounds::Ptr{Cvoid}
+    opt::B200Options
+    logger::MadNLPLogger
+end
+function B200DenseSolver(A::CuMatrix{Float64}; opt = B200Options(), logger = MadNLPLogger())
+    N = size(A, 1); h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:b2d_create, libb200kkt), Cint, (Int32, Int32, CuPtr{Float64}, Ptr{CB2Options}, Ptr{Ptr{Cvoid}}),
+        N, stride(A, 2), pointer(A), Ref(CB2Options(opt)), h), SymbolicException)
+    M = B200DenseSolver{Float64}(h[], A, C_NULL, C_NULL, opt, logger)
+    finalizer(m -> ccall((:b2d_destroy, libb200kkt), Cint, (Ptr{Cvoid},), m.handle), M)
+    return M
+end
+factorize!(M::B200DenseSolver) = (check(ccall((:b2d_factorize, libb200kkt), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), M.handle, stream_ptr()), FactorizationException); M)
+solve_linear_system!(M::B200DenseSolver{T}, x::CuVector{T}) where T =
+    (check(ccall((:b2d_solve, libb200kkt), Cint, (Ptr{Cvoid}, CuPtr{T}, Int32, Ptr{Cvoid}), M.handle, pointer(x), 1, stream_ptr()), SolveException); x)
+is_inertia(::B200DenseSolver) = true
+function inertia(M::B200DenseSolver)
+    p = Ref{Int64}(0); z = Ref{Int64}(0); n = Ref{Int64}(0)
+    check(ccall((:b2d_inertia, libb200kkt), Cint, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Ptr{Cvoid}), M.handle, p, z, n, stream_ptr()), FactorizationException)
+    return (Int(p[]), Int(z[]), Int(n[]))
+end
+improve!(::B200DenseSolver) = false
+introduce(::B200DenseSolver) = "b200kkt dense LDL' (DMMA)"
+input_type(::Type{<:B200DenseSolver}) = :dense
+default_options(::Type{<:B200DenseSolver}) = B200Options()
+is_supported(::Type{<:B200DenseSolver}, ::Type{Float64}) = true
+is_async(::B200DenseSolver) = true
+
+const B200DenseKKT{T} = MadNLP.DenseCondensedKKTSystem{T,VT,MT,QN,LS} where {VT<:CuVector{T},MT,QN,LS<:B200DenseSolver}
+
+function dense_plans(kkt::B200DenseKKT{T}) where T
+    M = kkt.linear_solver
+    if M.kkt_plan == C_NULL
+        n = size(kkt.hess, 1); m = size(kkt.jac, 1); ii = Array(kkt.ind_ineq) .- 1; h = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:b2d_kkt_create, libb200kkt), Cint, (Int32, Int32, Int32, Ptr{Int64}, Ptr{Ptr{Cvoid}}), n, m, length(ii), ii, h), SymbolicException)
+        M.kkt_plan = h[]
+        lb = Array(kkt.ind_lb) .- 1; ub = Array(kkt.ind_ub) .- 1; b = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:b2_bounds_create, libb200kkt), Cint, (Int64, Int64, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Ptr{Cvoid}}),
+            length(kkt.pr_diag), length(lb), length(ub), lb, ub, b), SymbolicException)
+        M.bounds = b[]
+    end
+    return M.kkt_plan, M.bounds
+end
+
+# build_kkt!(::DenseCondensedKKTSystem) (src/KKT/Dense/condensed.jl:157-186): one fused DMMA SYRK + epilogue
+function MadNLP.build_kkt!(kkt::B200DenseKKT{T}) where T
+    n = size(kkt.hess, 1); m = size(kkt.jac, 1)
+    check(ccall((:b2d_condensed_assemble, libb200kkt), Cint,
+        (Int32, Int32, Int32, Int32, CuPtr{Int64}, CuPtr{Int64}, CuPtr{T}, CuPtr{T}, CuPtr{T}, CuPtr{T}, CuPtr{T}, CuPtr{T}, Ptr{Cvoid}),
+        n, m, kkt.n_ineq, kkt.n_eq, pointer(kkt.etc[:b200_ind_ineq0]), pointer(kkt.etc[:b200_ind_eq0]), pointer(kkt.hess), pointer(kkt.jac),
+        pointer(kkt.pr_diag), pointer(kkt.du_diag), pointer(kkt.diag_buffer), pointer(kkt.aug_com), stream_ptr()), FactorizationException)
+end
+# (kkt.etc is the Dict{Symbol,Any} scratch slot of the struct, Dense/condensed.jl:49: the 0-based device copies of ind_ineq / ind_eq
+#  are stored there once:  kkt.etc[:b200_ind_ineq0] = CuVector(kkt.ind_ineq .- 1) ...)
+
+# solve_kkt!(::DenseCondensedKKTSystem) (src/IPM/factorization.jl:190-229)
+function MadNLP.solve_kkt!(kkt::B200DenseKKT{T}, w::MadNLP.AbstractKKTVector) where T
+    kp, bp = dense_plans(kkt); wv = MadNLP.full(w)
+    check(ccall((:b2d_kkt_solve_pre, libb200kkt), Cint,
+        (Ptr{Cvoid}, Ptr{Cvoid}, CuPtr{T}, CuPtr{T}, CuPtr{T}, CuPtr{T}, CuPtr{T}, CuPtr{T}, CuPtr{T}, CuPtr{T}, Ptr{Cvoid}),
+        kp, bp, pointer(kkt.jac), pointer(kkt.pr_diag), pointer(kkt.diag_buffer), pointer(kkt.l_diag), pointer(kkt.u_diag),
+        pointer(kkt.buffer), pointer(kkt.pd_buffer), pointer(wv), stream_ptr()), SolveException)
+    solve_linear_system!(kkt.linear_solver, kkt.pd_buffer)
+    check(ccall((:b2d_kkt_solve_post, libb200kkt), Cint,
+        (Ptr{Cvoid}, Ptr{Cvoid}, CuPtr{T}, CuPtr{T}, CuPtr{T}, CuPtr{T}, CuPtr{T}, CuPtr{T}, CuPtr{T}, CuPtr{T}, CuPtr{T}, CuPtr{T}, Ptr{Cvoid}),
+        kp, bp, pointer(kkt.jac), pointer(kkt.pr_diag), pointer(kkt.diag_buffer), pointer(kkt.l_lower), pointer(kkt.u_lower),
+        pointer(kkt.l_diag), pointer(kkt.u_diag), pointer(kkt.buffer), pointer(kkt.pd_buffer), pointer(wv), stream_ptr()), SolveException)
+    return w
+end
+
+# mul!(w, ::AbstractDenseKKTSystem, x, alpha, beta) (src/IPM/factorization.jl:303-324)
+function MadNLP.mul!(w::MadNLP.AbstractKKTVector{T}, kkt::B200DenseKKT{T}, x::MadNLP.AbstractKKTVector, alpha = one(T), beta = zero(T)) where T
+    kp, bp = dense_plans(kkt)
+    check(ccall((:b2d_kkt_mul, libb200kkt), Cint,
+        (Ptr{Cvoid}, Ptr{Cvoid}, CuPtr{T}, CuPtr{T}, CuPtr{T}, CuPtr{T}, CuPtr{T}, CuPtr{T}, CuPtr{T}, CuPtr{T}, Cdouble, Cdouble, CuPtr{T}, CuPtr{T}, Ptr{Cvoid}),
+        kp, bp, pointer(kkt.hess), pointer(kkt.jac), pointer(kkt.reg), pointer(kkt.du_diag), pointer(kkt.l_lower), pointer(kkt.u_lower),
+        pointer(kkt.l_diag), pointer(kkt.u_diag), alpha, beta, pointer(MadNLP.full(x)), pointer(MadNLP.full(w)), stream_ptr()), SolveException)
+    return w
 end
 
 # ---------------------------------------------------------------------------------------------------------------------

@@ -1,0 +1,58 @@
+"""Device-side symbolic phase: b2_coo_to_csc_device (device sorts, like lib/MadNLPGPU/src/KKT/gpu_sparse.jl:260-302)
+must reproduce the host construction b2_coo_to_csc / the oracle's coo_to_csc (src/matrixtools.jl:55-95) EXACTLY: same colptr, rowval,
+COO->CSC map -- integer work, bit-exact bar."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import madnlp_oracle as o
+import madnlp_jl_b200 as pkg
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+
+def _device_coo_to_csc(I, J, m, n):
+    lib, check = pkg.capi.lib, pkg.capi.check
+    nnz = len(I)
+    Id = torch.from_numpy(np.ascontiguousarray(I, dtype=np.int32)).cuda()
+    Jd = torch.from_numpy(np.ascontiguousarray(J, dtype=np.int32)).cuda()
+    colptr = torch.full((n + 1,), -7, dtype=torch.int32, device="cuda")
+    rowval = torch.full((max(nnz, 1),), -7, dtype=torch.int32, device="cuda")
+    cmap = torch.full((max(nnz, 1),), -7, dtype=torch.int64, device="cuda")
+    ncsc = C.c_int64(-1)
+    check(lib.b2_coo_to_csc_device(m, n, nnz, Id.data_ptr() if nnz else None, Jd.data_ptr() if nnz else None, colptr.data_ptr(),
+                                   rowval.data_ptr(), cmap.data_ptr(), C.byref(ncsc), torch.cuda.current_stream().cuda_stream))
+    return colptr.cpu().numpy(), rowval.cpu().numpy()[:ncsc.value], cmap.cpu().numpy()[:nnz], ncsc.value
+
+
+@pytest.mark.parametrize("m,n,nnz,seed", [(1, 1, 0, 0), (5, 7, 1, 1), (301, 257, 5000, 2), (40000, 40000, 600000, 3)])
+def test_device_coo_to_csc_matches_host_and_oracle(m, n, nnz, seed):
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from madnlp_jl_b200 import kkt as K
+    rng = np.random.default_rng(seed)
+    I = rng.integers(0, m, nnz); J = rng.integers(0, n, nnz)
+    if nnz > 1000:                                  # duplicates, an empty column range, a full column
+        I[:400] = I[400:800]; J[:400] = J[400:800]
+        J[J == n // 2] = n // 2 + 1
+    cp_d, rv_d, mp_d, ncsc = _device_coo_to_csc(I, J, m, n)
+    cp_h, rv_h, mp_h = K.coo_to_csc(I, J, m, n)
+    assert ncsc == len(rv_h)
+    assert (cp_d == cp_h).all() and (rv_d == rv_h).all() and (mp_d == mp_h).all()
+    if nnz:
+        cp_o, rv_o, mp_o = o.coo_to_csc(I, J, m, n)
+        assert (cp_d == cp_o).all() and (rv_d == rv_o).all() and (mp_d == mp_o).all()
+
+
+def test_device_coo_to_csc_on_the_headline_kkt_pattern():
+    """the augmented COO of the OPF-10k SparseKKTSystem ([pr_diag | hess | jac | -1 | du_diag] positions, augmented.jl:77-107)"""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    W = pkg.workloads
+    model, st = W.acopf_case("case1354_pegase", relax_equality=False)
+    cb = o.Callback(st.nvar, st.ncon, st.jac_I, st.jac_J, st.hess_I, st.hess_J, st.ind_ineq, st.ind_lb, st.ind_ub)
+    kc = o.SparseKKTSystem(cb, o.UmfpackStandInSolver)
+    cp_d, rv_d, mp_d, ncsc = _device_coo_to_csc(kc.aug_I, kc.aug_J, kc.N, kc.N)
+    assert (cp_d == kc.aug_colptr).all() and (rv_d == kc.aug_rowval).all() and (mp_d == kc.aug_csc_map).all()
