@@ -215,6 +215,21 @@ int b2d_condensed_assemble(int32_t n, int32_t m, int32_t ns, int32_t n_eq,
                            const double* pr_diag_d, const double* du_diag_d,
                            double* diag_buffer_d, double* aug_d, void* stream);
 
+/* The same assembly with the J' D J contraction on the 5th-generation tensor cores: fp64 is cut into 8 signed 7-bit digits per entry
+ * (Ozaki scheme) and the 36 digit-pair products run as exact int8 GEMMs on tcgen05.mma.kind::i8 with TMA-staged operands
+ * (csrc/ozaki_kernels.cuh); the result agrees with the fp64 contraction to ~1e-14 of max|W| (parity bar 1e-13,
+ * tests/test_gpu_parity_large.py).  The plan owns the digit planes (8 * n_pad * ns_pad bytes), exponents, tile list and tensor maps.
+ * ns <= 16384.  b2d_ozaki_plan_status reports whether a (bounded) pipeline wait ever timed out. */
+typedef struct b2d_ozaki_plan b2d_ozaki_plan;
+int b2d_ozaki_plan_create(int32_t n, int32_t ns, b2d_ozaki_plan** out);
+int b2d_ozaki_plan_destroy(b2d_ozaki_plan* p);
+int b2d_condensed_assemble_ozaki(b2d_ozaki_plan* p, int32_t n, int32_t m, int32_t ns, int32_t n_eq,
+                                 const int64_t* ind_ineq_d, const int64_t* ind_eq_d,
+                                 const double* hess_d, const double* jac_d,
+                                 const double* pr_diag_d, const double* du_diag_d,
+                                 double* diag_buffer_d, double* aug_d, void* stream);
+int b2d_ozaki_plan_status(b2d_ozaki_plan* p, int32_t* timed_out, void* stream);
+
 /* dense mat-vecs on column-major device matrices for the DenseCondensedKKTSystem wrappers (jtprod!/mul!/solve_kkt!,
  * src/IPM/factorization.jl:190-229,326-344; the reference calls cuBLAS gemv/symv, lib/MadNLPGPU/.../cuda.jl:54-84):
  *   gemv_n: y = alpha*A*x + beta*y (A rows x cols, ld = lda)   gemv_t: y = alpha*A'*x + beta*y

@@ -117,6 +117,10 @@ PROTOTYPES = {
     "b2d_inertia_fetch": (C.c_int, [_p, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64)]),
     "b2d_solve": (C.c_int, [_p, _p, _i32, _p]),
     "b2_coo_to_csc_device": (C.c_int, [_i32, _i32, _i64, _p, _p, _p, _p, _p, C.POINTER(_i64), _p]),
+    "b2d_ozaki_plan_create": (C.c_int, [_i32, _i32, _PP]),
+    "b2d_ozaki_plan_destroy": (C.c_int, [_p]),
+    "b2d_condensed_assemble_ozaki": (C.c_int, [_p, _i32, _i32, _i32, _i32] + [_p] * 9),
+    "b2d_ozaki_plan_status": (C.c_int, [_p, C.POINTER(_i32), _p]),
     "b2d_kkt_create": (C.c_int, [_i32, _i32, _i32, _p, _PP]),
     "b2d_kkt_destroy": (C.c_int, [_p]),
     "b2d_kkt_solve_pre": (C.c_int, [_p] * 10 + [_p]),

@@ -131,10 +131,17 @@ __global__ void k_condensed(int64_t nslot, const int32_t* __restrict__ hsrc, con
         const int h = hsrc[i], dd = dsrc[i];
         if (h >= 0) acc = __dadd_rn(acc, Hnz[h]);
         if (dd >= 0) acc = __dadd_rn(acc, pr[dd]);
+        // triples in batches of 4: index records first, then the 12 values, then the adds in the reference's order
+        // (latency-bound gather: a slot holds 0-12 triples)
         const int a = tptr[i], b = tptr[i + 1];
-        for (int q = a; q < b; ++q) {
-            const int4 t = trip[q];
-            acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(D[t.x], Jt[t.y]), Jt[t.z]));
+        for (int q0 = a; q0 < b; q0 += 4) {
+            int4 t[4]; double dv[4], j1[4], j2[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) t[u] = (q0 + u < b) ? trip[q0 + u] : make_int4(-1, 0, 0, 0);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { const bool ok = t[u].x >= 0; dv[u] = ok ? D[t[u].x] : 0.0; j1[u] = ok ? Jt[t[u].y] : 0.0; j2[u] = ok ? Jt[t[u].z] : 0.0; }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) if (t[u].x >= 0) acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(dv[u], j1[u]), j2[u]));
         }
         nz[i] = acc;
     }
@@ -350,6 +357,25 @@ __global__ void k_dense_eq_rows(int n, int m, int n_eq, int N, const int64_t* __
     }
 }
 
+// the two cheap passes around the contraction: before_syrk -> diag_buffer D = Ss ./ (1 - Sd[ind_ineq] .* Ss); after -> equality rows
+int b2d_assemble_parts(int32_t n, int32_t m, int32_t ns, int32_t n_eq, const int64_t* ind_ineq_d, const int64_t* ind_eq_d,
+                       const double* jac_d, const double* pr_diag_d, const double* du_diag_d, double* diag_buffer_d, double* aug_d,
+                       bool before_syrk, cudaStream_t st) {
+    const int N = n + n_eq;
+    if (before_syrk) {
+        if (ns > 0) {
+            const int g = std::min((ns + 255) / 256, 8 * sm_count());
+            k_dense_diag_buffer<<<g, 256, 0, st>>>(ns, ind_ineq_d, pr_diag_d + n, du_diag_d, diag_buffer_d);
+        }
+    } else if (n_eq > 0) {
+        const int64_t total = (int64_t)n_eq * N;
+        const int g = (int)std::min<int64_t>((total + 255) / 256, 8 * sm_count());
+        k_dense_eq_rows<<<g, 256, 0, st>>>(n, m, n_eq, N, ind_eq_d, jac_d, du_diag_d, aug_d);
+    }
+    B2_CUDA(cudaGetLastError());
+    return B2_OK;
+}
+
 extern "C" int b2d_condensed_assemble(int32_t n, int32_t m, int32_t ns, int32_t n_eq, const int64_t* ind_ineq_d,
                                       const int64_t* ind_eq_d, const double* hess_d, const double* jac_d,
                                       const double* pr_diag_d, const double* du_diag_d, double* diag_buffer_d,
@@ -360,20 +386,13 @@ extern "C" int b2d_condensed_assemble(int32_t n, int32_t m, int32_t ns, int32_t 
     }
     cudaStream_t st = as_stream(stream);
     const int N = n + n_eq;
-    if (ns > 0) {
-        const int g = std::min((ns + 255) / 256, 8 * sm_count());
-        k_dense_diag_buffer<<<g, 256, 0, st>>>(ns, ind_ineq_d, pr_diag_d + n, du_diag_d, diag_buffer_d);
-    }
+    int rc = b2d_assemble_parts(n, m, ns, n_eq, ind_ineq_d, ind_eq_d, jac_d, pr_diag_d, du_diag_d, diag_buffer_d, aug_d, true, st);
+    if (rc != B2_OK) return rc;
     dim3 grid((n + DT_M - 1) / DT_M, (n + DT_N - 1) / DT_N);
     const size_t syrk_smem = (size_t)(2 * DT_K * (DT_M + 4) + 2 * DT_K * (DT_N + 4)) * sizeof(double);
     static bool attr_set = false;
     if (!attr_set) { B2_CUDA(cudaFuncSetAttribute(k_dense_syrk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)syrk_smem)); attr_set = true; }
     k_dense_syrk<<<grid, 256, syrk_smem, st>>>(n, m, ns, N, ind_ineq_d, hess_d, jac_d, pr_diag_d, diag_buffer_d, aug_d);
-    if (n_eq > 0) {
-        const int64_t total = (int64_t)n_eq * N;
-        const int g = (int)std::min<int64_t>((total + 255) / 256, 8 * sm_count());
-        k_dense_eq_rows<<<g, 256, 0, st>>>(n, m, n_eq, N, ind_eq_d, jac_d, du_diag_d, aug_d);
-    }
     B2_CUDA(cudaGetLastError());
-    return B2_OK;
+    return b2d_assemble_parts(n, m, ns, n_eq, ind_ineq_d, ind_eq_d, jac_d, pr_diag_d, du_diag_d, diag_buffer_d, aug_d, false, st);
 }

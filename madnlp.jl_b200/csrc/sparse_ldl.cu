@@ -161,9 +161,11 @@ int64_t enqueue_factor(b2_solver* s, int ph, cudaStream_t st) {
     if (P.dep_ngroup && (s->opt.dep_schedule & 1)) {
         DepSched ds;
         ds.grp_type = sched + P.dep_type_off; ds.grp_ptr = sched + P.dep_ptr_off; ds.tasks = sched + P.dep_tasks_off; ds.ngroup = P.dep_ngroup;
+        // (the group ticket in slot 3*nsuper re-arms itself: the CTA that takes the last group resets it)
         cudaMemsetAsync(s->d_flags.p, 0, (size_t)s->S.nsuper * sizeof(int32_t), st);
         const size_t sm = sizeof(double) * std::max<size_t>((size_t)FW_WARPS * TeamSmem<1>::doubles(P.dep_maxf1), (size_t)TeamSmem<2>::doubles(P.dep_maxf2));
-        k_factor_dep<<<P.dep_ngroup, 128, sm, st>>>(a, s->d_childrec.p, ds, P.dep_maxf1, P.dep_maxf2, s->d_flags.p, s->d_counters.p + 4);
+        k_factor_dep<<<P.dep_ngroup, 128, sm, st>>>(a, s->d_childrec.p, ds, P.dep_maxf1, P.dep_maxf2, s->d_flags.p, s->d_counters.p + 4,
+                                                    s->d_flags.p + (size_t)3 * s->S.nsuper);
         return 2;
     }
     if (P.fused.n_cta) warp_launch(P.fused);
@@ -230,10 +232,11 @@ int64_t enqueue_solve(b2_solver* s, int ph, bool forward, cudaStream_t st) {
         DepSched ds;
         ds.grp_type = sched + P.dep_type_off; ds.grp_ptr = sched + P.dep_ptr_off; ds.tasks = sched + P.dep_tasks_off; ds.ngroup = P.dep_ngroup;
         int* flags = s->d_flags.p + (size_t)(forward ? 1 : 2) * s->S.nsuper;
+        int* ticket = s->d_flags.p + (size_t)3 * s->S.nsuper;
         cudaMemsetAsync(flags, 0, (size_t)s->S.nsuper * sizeof(int32_t), st);
         const size_t smd = sizeof(double) * std::max<size_t>((size_t)4 * SolveSmem<1>::doubles, (size_t)SolveSmem<2>::doubles);
-        if (forward) k_fwd_dep<<<P.dep_ngroup, 128, smd, st>>>(a, s->d_childrec.p, ds, flags, s->d_counters.p + 4);
-        else k_bwd_dep<<<P.dep_ngroup, 128, smd, st>>>(a, ds, s->d_parent.p, flags, s->d_counters.p + 4);
+        if (forward) k_fwd_dep<<<P.dep_ngroup, 128, smd, st>>>(a, s->d_childrec.p, ds, flags, s->d_counters.p + 4, ticket);
+        else k_bwd_dep<<<P.dep_ngroup, 128, smd, st>>>(a, ds, s->d_parent.p, flags, s->d_counters.p + 4, ticket);
         return 2;
     }
     if (forward && P.fused.n_cta) warp_launch(P.fused);

@@ -525,10 +525,25 @@ struct DepSched {
     int ngroup;
 };
 
+// Forward progress: a CTA only ever waits for groups that come EARLIER in the topological order.  Groups are therefore claimed
+// through an atomic ticket instead of blockIdx.x: whichever CTA the hardware starts first takes the earliest unclaimed group, so a
+// running CTA never waits for work that no running (or finished) CTA owns -- independent of the block dispatch order, which the
+// programming model does not specify (the bounded spin in flag_wait stays as a second line of defence).
+__device__ __forceinline__ int claim_group(int* ticket, int ngroup) {
+    __shared__ int g_sh;
+    if (threadIdx.x == 0) {
+        const int t = atomicAdd(ticket, 1);
+        if (t == ngroup - 1) atomicExch(ticket, 0);     // last claim of this launch: re-arm the counter for the next one
+        g_sh = t;
+    }
+    __syncthreads();
+    return g_sh;
+}
+
 __global__ void __launch_bounds__(128) k_factor_dep(FactorArgs a, const ChildRec* childrec, DepSched ds, int maxf1, int maxf2,
-                                                    int* done, int* err) {
+                                                    int* done, int* err, int* ticket) {
     extern __shared__ __align__(16) double sm[];
-    const int g = blockIdx.x;
+    const int g = claim_group(ticket, ds.ngroup);
     const int type = ds.grp_type[g], t0 = ds.grp_ptr[g], n = ds.grp_ptr[g + 1] - t0;
     int nneg = 0, npert = 0;
     if (type == 1) {
@@ -543,10 +558,10 @@ __global__ void __launch_bounds__(128) k_factor_dep(FactorArgs a, const ChildRec
     }
 }
 
-__global__ void __launch_bounds__(128) k_fwd_dep(SolveArgs a, const ChildRec* childrec, DepSched ds, int* done, int* err) {
+__global__ void __launch_bounds__(128) k_fwd_dep(SolveArgs a, const ChildRec* childrec, DepSched ds, int* done, int* err, int* ticket) {
     extern __shared__ __align__(16) double smd[];       // max(4 one-warp slices, 1 two-warp slice)
     double (*sm)[SolveSmem<1>::doubles] = (double (*)[SolveSmem<1>::doubles])smd;
-    const int g = blockIdx.x;
+    const int g = claim_group(ticket, ds.ngroup);
     const int type = ds.grp_type[g], t0 = ds.grp_ptr[g], n = ds.grp_ptr[g + 1] - t0;
     if (type == 1) {
         const int team = threadIdx.x >> 5, tid = threadIdx.x & 31;
@@ -557,10 +572,10 @@ __global__ void __launch_bounds__(128) k_fwd_dep(SolveArgs a, const ChildRec* ch
     }
 }
 
-__global__ void __launch_bounds__(128) k_bwd_dep(SolveArgs a, DepSched ds, const int32_t* parent, int* done, int* err) {
+__global__ void __launch_bounds__(128) k_bwd_dep(SolveArgs a, DepSched ds, const int32_t* parent, int* done, int* err, int* ticket) {
     extern __shared__ __align__(16) double smd[];
     double (*sm)[SolveSmem<1>::doubles] = (double (*)[SolveSmem<1>::doubles])smd;
-    const int g = ds.ngroup - 1 - blockIdx.x;            // reverse topological order
+    const int g = ds.ngroup - 1 - claim_group(ticket, ds.ngroup);   // reverse topological order
     const int type = ds.grp_type[g], t0 = ds.grp_ptr[g], n = ds.grp_ptr[g + 1] - t0;
     if (type == 1) {
         const int team = threadIdx.x >> 5, tid = threadIdx.x & 31;

@@ -415,6 +415,16 @@ class DenseCondensedKKTSystem(_KKTBase):
         ii = np.ascontiguousarray(ind_ineq, dtype=np.int64)
         check(lib.b2d_kkt_create(n, m, ns, ii.ctypes.data if ns else None, C.byref(h)))
         self._dk = _Plan(h, lib.b2d_kkt_destroy)
+        # J' D J on the 5th-generation tensor cores (tcgen05 int8 digits + TMA, csrc/ozaki_kernels.cuh) when the contraction is big
+        # enough to pay for the digit split; B2_OZAKI=0/1 forces the DMMA kernel / the tensor-core kernel
+        import os
+        want = os.environ.get("B2_OZAKI")
+        use = (n >= 512 and 256 <= ns <= 16384) if want is None else (want != "0" and 0 < ns <= 16384)
+        self._ozaki = None
+        if use:
+            hz = C.c_void_p()
+            check(lib.b2d_ozaki_plan_create(n, ns, C.byref(hz)))
+            self._ozaki = _Plan(hz, lib.b2d_ozaki_plan_destroy)
         self.linear_solver = linear_solver(self.aug_com, opt_linear_solver)
 
     def num_variables(self):
@@ -443,10 +453,24 @@ class DenseCondensedKKTSystem(_KKTBase):
         pass
 
     def build_kkt(self):
-        """Dense/condensed.jl:157-186 as diag-buffer + one DMMA SYRK with fused scaling/epilogue + equality rows."""
+        """Dense/condensed.jl:157-186 as diag-buffer + ONE contraction kernel with fused scaling/epilogue + equality rows; the
+        contraction runs on tcgen05 (int8 Ozaki digits, TMA) when self._ozaki is set, else on the fp64 DMMA path."""
+        if self._ozaki is not None:
+            check(lib.b2d_condensed_assemble_ozaki(self._ozaki.h, self.n, self.m, self.ns, self.n_eq, ptr(self._ind_ineq_d), ptr(self._ind_eq_d),
+                                                   ptr(self.hess), ptr(self.jac), ptr(self.pr_diag), ptr(self.du_diag),
+                                                   ptr(self.diag_buffer), ptr(self.aug_com), _sp(self.stream)))
+            return
         check(lib.b2d_condensed_assemble(self.n, self.m, self.ns, self.n_eq, ptr(self._ind_ineq_d), ptr(self._ind_eq_d),
                                          ptr(self.hess), ptr(self.jac), ptr(self.pr_diag), ptr(self.du_diag),
                                          ptr(self.diag_buffer), ptr(self.aug_com), _sp(self.stream)))
+
+    def tensor_core_status(self):
+        """True if the tcgen05 assembly is active and none of its (bounded) pipeline waits ever timed out"""
+        if self._ozaki is None:
+            return None
+        t = C.c_int32(0)
+        check(lib.b2d_ozaki_plan_status(self._ozaki.h, C.byref(t), _sp(self.stream)))
+        return t.value == 0
 
     def is_inertia_correct(self, num_pos, num_zero, num_neg):
         """Dense/condensed.jl:189-191."""

@@ -52,7 +52,15 @@ def _worker(rank, world, port, q, one_device=False):
             M = B200SparseSolver(csc)
             M.factorize()
             xs = M.solve_linear_system(torch.from_numpy(b).cuda()).cpu().numpy()
-            out.append((case, inertia, M.inertia(), float(np.abs(x - xs).max() / np.abs(xs).max()), D.stats()["sep_rows"], D.exchange_bytes))
+            # ... and the ORACLE: LDL^T (src/LinearSolvers/ldl.jl restated) inertia, refined reference solution
+            L = o.LDLSolver(k.aug_colptr, k.aug_rowval, k.aug_nz, k.n).factorize()
+            Kf = o.tril_to_full(k.aug_colptr, k.aug_rowval, k.aug_nz, k.n).tocsr()
+            xo = L.solve(b.copy())
+            for _ in range(2):
+                xo += L.solve(b - Kf @ xo)
+            res = float(np.abs(Kf @ x - b).max() / (abs(Kf).max() * np.abs(x).max() + np.abs(b).max()))
+            out.append((case, inertia, M.inertia(), float(np.abs(x - xs).max() / np.abs(xs).max()), D.stats()["sep_rows"], D.exchange_bytes,
+                        tuple(L.inertia()), res))
         q.put((rank, out))
     finally:
         dist.destroy_process_group()
@@ -76,7 +84,9 @@ def test_two_rank_sharded_factorization_matches_single_gpu(mode):
     assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
     for _ in range(2):
         rank, out = q.get(timeout=5)
-        for case, inertia, inertia1, err, sep, exb in out:
+        for case, inertia, inertia1, err, sep, exb, inertia_oracle, res in out:
             assert inertia == inertia1, (case, inertia, inertia1)
+            assert tuple(inertia) == inertia_oracle, (case, inertia, inertia_oracle)      # the sharded factorisation vs the LDL^T oracle
             assert err < 1e-9, (case, err)
+            assert res < 1e-12, (case, res)                                                # backward-stable single solve of the sharded path
             assert sep > 0 and exb["factor"] > 0

@@ -506,3 +506,30 @@ def test_ipm_reductions_match_the_reference_formulas(n_tot, m, seed):
         check(lib.b2_get_alpha_max(h, P("x"), P("xl"), P("xu"), P("dx"), tau, O(0), st))
         assert np.isnan(float(out[0])) == np.isnan(o.get_alpha_max(x, xl, xu, np.where(np.arange(n_tot) == 3, np.nan, dx), tau))
     lib.b2_bounds_destroy(h)
+
+
+@pytest.mark.parametrize("n,m,n_eq", [(640, 300, 0), (515, 333, 40), (1024, 512, 0)])
+def test_dense_assembly_on_tensor_cores_matches_oracle(n, m, n_eq, monkeypatch):
+    """A8 with the contraction on tcgen05.mma.kind::i8 (Ozaki digits, csrc/ozaki_kernels.cuh): ragged sizes (n, ns not multiples of the
+    128 / 64 tile and K-block sizes: zero padding), equality rows, D spanning 18 decades.  Bar: 1e-13 of max|K| against the oracle's
+    fp64 assembly (Dense/condensed.jl:157-186), and agreement with the DMMA kernel to the same bar."""
+    _need_gpu()
+    from madnlp_jl_b200 import kkt as K
+    qp = W.dense_qp(n=n, m=m, n_eq=n_eq, seed=7)
+    it = W.dense_qp_iterate(qp, mu=1e-5, seed=8)
+    cb = o.Callback(qp.n, qp.m, [], [], [], [], qp.ind_ineq, qp.ind_lb, qp.ind_ub)
+    kc = o.DenseCondensedKKTSystem(cb); kc.initialize(); kc.hess[:] = qp.P; kc.jac[:] = qp.A
+    out = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("B2_OZAKI", flag)
+        kg = K.DenseCondensedKKTSystem(cb); kg.initialize(); kg.set_dense(hess_np=qp.P, jac_np=qp.A)
+        for name in ("reg", "du_diag", "l_diag", "u_diag", "l_lower", "u_lower"):
+            getattr(kc, name)[:] = it[name]
+            getattr(kg, name).copy_(_dev(it[name]))
+        kg.set_aug_diagonal_(); kg.build_kkt()
+        out[flag] = np.tril(kg.aug_com.cpu().numpy().T)
+        assert kg.tensor_core_status() is (True if flag == "1" else None)
+    o.set_aug_diagonal_(kc); kc.build_kkt()
+    ref = np.tril(kc.aug_com); scale = np.abs(kc.aug_com).max()
+    assert np.abs(out["1"] - ref).max() / scale <= 1e-13
+    assert np.abs(out["0"] - ref).max() / scale <= 1e-13

@@ -91,10 +91,11 @@ def test_headline_first_factorisation_inertia_matches_ldl_oracle_when_indefinite
     assert tuple(kg.linear_solver.inertia()) == tuple(ref)
 
 
-@pytest.mark.parametrize("n_eq", [0, 256])
-def test_dense_condensed_full_size(n_eq):
-    """configs[1] at n = 4096, m = 2048."""
+@pytest.mark.parametrize("n_eq,ozaki", [(0, "1"), (256, "1"), (0, "0")])
+def test_dense_condensed_full_size(n_eq, ozaki, monkeypatch):
+    """configs[1] at n = 4096, m = 2048; `ozaki` = J' D J on tcgen05 (int8 digits + TMA) / on the fp64 DMMA path."""
     _need_gpu()
+    monkeypatch.setenv("B2_OZAKI", ozaki)
     from madnlp_jl_b200 import kkt as K
     from madnlp_jl_b200.richardson import RichardsonIterator
     qp = W.dense_qp(n=4096, m=2048, n_eq=n_eq, seed=1)
@@ -111,6 +112,7 @@ def test_dense_condensed_full_size(n_eq):
     kg.set_aug_diagonal_(); kg.build_kkt()
     aug = kg.aug_com.cpu().numpy().T
     assert np.abs(np.tril(aug) - np.tril(kc.aug_com)).max() / np.abs(kc.aug_com).max() <= 1e-13
+    assert kg.tensor_core_status() is (True if ozaki == "1" else None)
     kc.linear_solver.factorize(); kg.linear_solver.factorize()
     assert tuple(kg.linear_solver.inertia()) == tuple(kc.linear_solver.inertia()) == (qp.n, 0, n_eq)
     # step direction through solve_kkt! + mul! + Richardson on both sides
