@@ -112,6 +112,11 @@ __device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_
         "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n}\n"
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(IDESC), "r"(accumulate) : "memory");
 }
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}\n" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -169,33 +174,41 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_ozaki_syrk(const __grid_constan
             tma_load_3d(sa, &mapA, &full_bar[st], kb * BKB, bm * BM, 0);      // box (64 B of K, 128 rows, 8 digits)
             tma_load_3d(sb, &mapB, &full_bar[st], kb * BKB, bn * BN, 0);      // box (64 B of K,  64 rows, 8 digits)
         }
-    } else if (warp == 5 && lane == 0) {
-        // ---------------- MMA issuer
-        uint32_t started = 0;                           // bit d: accumulator d has been written once
+    } else if (warp == 5) {
+        // ---------------- MMA issuer: the WHOLE warp runs the (warp-uniform) loop so that descriptors and predicates live in uniform
+        // registers; one elected lane issues.  The 72 MMAs of a K block are straight-line code: their operand descriptors differ from
+        // the stage's base descriptors by compile-time constants (digit tile offset + 32-byte K step), the accumulator by d * 64
+        // columns -- a single thread cannot afford ~100 cycles of address arithmetic per 32-cycle MMA (measured: v1 of this kernel).
+        const bool leader = elect_one();
         bool ok = true;
         for (int kb = 0; kb < nkb && ok; ++kb) {
             const int st = kb % STAGES;
             ok = mbar_wait(&full_bar[st], (kb / STAGES) & 1, err);
             if (!ok) break;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t sa = smem_u32(smem + (size_t)st * STAGE_BYTES);
-            const uint32_t sb = sa + S * A_TILE;
-#pragma unroll 1
-            for (int t = 0; t < S; ++t) {
-#pragma unroll 1
-                for (int s = 0; s + t < S; ++s) {
-                    const int d = s + t;
-                    const uint64_t ad = umma_desc_k_sw64(sa + s * A_TILE), bd = umma_desc_k_sw64(sb + t * B_TILE);
+            if (leader) {
+                const uint32_t sa = smem_u32(smem + (size_t)st * STAGE_BYTES);
+                const uint64_t ad0 = umma_desc_k_sw64(sa), bd0 = umma_desc_k_sw64(sa + S * A_TILE);
+                const uint32_t acc_any = kb > 0 ? 1u : 0u;
 #pragma unroll
-                    for (int k2 = 0; k2 < BKB / 32; ++k2) {             // UMMA_K = 32 bytes: advance the start address inside the swizzle row
-                        umma_i8(tmem_base + d * BN, ad + (uint64_t)(k2 * 2), bd + (uint64_t)(k2 * 2), (started >> d) & 1u);
-                        started |= 1u << d;
+                for (int t = 0; t < S; ++t) {
+#pragma unroll
+                    for (int s = 0; s < S - t; ++s) {
+#pragma unroll
+                        for (int k2 = 0; k2 < BKB / 32; ++k2) {
+                            // first write of accumulator d = s + t: K block 0, t == 0, k2 == 0 (t is the outer loop, so every d is first met at t = 0)
+                            const uint32_t acc = (t > 0 || k2 > 0) ? 1u : acc_any;
+                            umma_i8(tmem_base + (uint32_t)((s + t) * BN), ad0 + (uint64_t)((s * A_TILE + k2 * 32) >> 4),
+                                    bd0 + (uint64_t)((t * B_TILE + k2 * 32) >> 4), acc);
+                        }
                     }
                 }
+                umma_commit(&empty_bar[st]);            // the stage may be refilled once these MMAs have read it
             }
-            umma_commit(&empty_bar[st]);                // the stage may be refilled once these MMAs have read it
+            __syncwarp();
         }
-        umma_commit(&accum_bar);                         // all accumulators final
+        if (leader) umma_commit(&accum_bar);             // all accumulators final
+        __syncwarp();
     } else if (warp < 4) {
         // ---------------- epilogue: warp w owns TMEM lanes 32w .. 32w+31 = tile rows
         if (mbar_wait(&accum_bar, 0, err)) {
