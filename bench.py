@@ -387,7 +387,7 @@ def run_b200(args, rank, world, local_rank):
         }
         if secondary is not None:
             line["secondary"] = secondary
-        if world == 1:
+        if world == 1 and args.cpu_sample_steps > 0:
             line["cpu_baseline"] = cpu_baseline_sample(args, st, its)
         print(json.dumps(line), flush=True)
     if world > 1:

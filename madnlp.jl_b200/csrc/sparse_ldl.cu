@@ -214,10 +214,14 @@ int64_t enqueue_solve(b2_solver* s, int ph, bool forward, cudaStream_t st) {
         cfg.attrs = pattr; cfg.numAttrs = pdl ? 1 : 0;
         return cfg;
     };
-    auto warp_launch = [&](const WarpLaunch& L) {
+    auto warp_launch = [&](const WarpLaunch& L, bool fused = false) {
         const ChildRec* cr = s->d_childrec.p;
         const WarpSched wsched = warp_sched(s, L);
-        if (L.nw == 1) {
+        if (L.nw == 1 && fused) {     // bottom subtrees: more one-warp teams per CTA, fewer sequential rounds per stage
+            cudaLaunchConfig_t cfg = cfg_of(L.n_cta, SOLVE_FUSED_TEAMS * 32, (size_t)SOLVE_FUSED_TEAMS * SolveSmem<1>::doubles * sizeof(double));
+            if (forward) cudaLaunchKernelEx(&cfg, k_fwd_warp2<1, SOLVE_FUSED_TEAMS>, a, cr, wsched);
+            else cudaLaunchKernelEx(&cfg, k_bwd_warp2<1, SOLVE_FUSED_TEAMS>, a, wsched);
+        } else if (L.nw == 1) {
             cudaLaunchConfig_t cfg = cfg_of(L.n_cta, FW_WARPS * 32, (size_t)FW_WARPS * SolveSmem<1>::doubles * sizeof(double));
             if (forward) cudaLaunchKernelEx(&cfg, k_fwd_warp2<1>, a, cr, wsched);
             else cudaLaunchKernelEx(&cfg, k_bwd_warp2<1>, a, wsched);
@@ -239,7 +243,7 @@ int64_t enqueue_solve(b2_solver* s, int ph, bool forward, cudaStream_t st) {
         else k_bwd_dep<<<P.dep_ngroup, 128, smd, st>>>(a, ds, s->d_parent.p, flags, s->d_counters.p + 4, ticket);
         return 2;
     }
-    if (forward && P.fused.n_cta) warp_launch(P.fused);
+    if (forward && P.fused.n_cta) warp_launch(P.fused, true);
     if (!forward && P.topfused.n_cta) warp_launch(P.topfused);
     const int nlev = (int)P.lev.size();
     for (int q = 0; q < nlev; ++q) {
@@ -273,7 +277,7 @@ int64_t enqueue_solve(b2_solver* s, int ph, bool forward, cudaStream_t st) {
         }
     }
     if (forward && P.topfused.n_cta) warp_launch(P.topfused);
-    if (!forward && P.fused.n_cta) warp_launch(P.fused);
+    if (!forward && P.fused.n_cta) warp_launch(P.fused, true);
     return nl;
 }
 
@@ -284,6 +288,8 @@ int set_smem_attrs() {
     B2_CUDA(cudaFuncSetAttribute(k_factor_dep, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     B2_CUDA(cudaFuncSetAttribute(k_fwd_warp2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     B2_CUDA(cudaFuncSetAttribute(k_bwd_warp2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    B2_CUDA(cudaFuncSetAttribute((k_fwd_warp2<1, SOLVE_FUSED_TEAMS>), cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    B2_CUDA(cudaFuncSetAttribute((k_bwd_warp2<1, SOLVE_FUSED_TEAMS>), cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     B2_CUDA(cudaFuncSetAttribute(k_fwd_warp2<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     B2_CUDA(cudaFuncSetAttribute(k_bwd_warp2<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     B2_CUDA(cudaFuncSetAttribute(k_fwd_dep, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
@@ -713,7 +719,7 @@ int b2_options_default(b2_options* opt) {
     opt->pivot_eps = 1e-13;
     opt->use_cuda_graph = 1;
     opt->small_front_max = 160;
-    opt->fuse_max_fronts = 16;
+    opt->fuse_max_fronts = 8;      // measured optimum on OPF-10k (profiles/r02_sweep.txt)
     opt->dep_schedule = 1;
     opt->n_parts = 1;
     opt->part_rank = 0;

@@ -481,11 +481,14 @@ __device__ __forceinline__ void front_bwd_team(const SolveArgs& a, int s, double
     if (DEP && tid == 0) flag_set(done + s);
 }
 
-template <int NW>
-__global__ void __launch_bounds__(TeamsPerCta<NW>::value * NW * 32) k_fwd_warp2(SolveArgs a, const ChildRec* childrec, WarpSched ws) {
+// NTEAM teams per CTA.  Measured on OPF-10k (profiles/r02_sweep.txt): sweeping the fused bottom subtrees with 8 one-warp teams per
+// CTA instead of 4 is SLOWER (0.139 -> 0.164 ms per solve: fewer resident CTAs, wider barriers), while smaller subtrees
+// (fuse_max_fronts 16 -> 8) are faster (0.150 -> 0.139 ms) -- so the fused launches keep TeamsPerCta teams.
+constexpr int SOLVE_FUSED_TEAMS = 4;
+template <int NW, int NTEAM = TeamsPerCta<NW>::value>
+__global__ void __launch_bounds__(NTEAM * NW * 32) k_fwd_warp2(SolveArgs a, const ChildRec* childrec, WarpSched ws) {
     extern __shared__ __align__(16) double smd[];
     double (*sm)[SolveSmem<NW>::doubles] = (double (*)[SolveSmem<NW>::doubles])smd;
-    constexpr int NTEAM = TeamsPerCta<NW>::value;
     const int team = threadIdx.x / (32 * NW), tid = threadIdx.x % (32 * NW);
     pdl_trigger();
     const int s0 = ws.cta_ptr[blockIdx.x], s1 = ws.cta_ptr[blockIdx.x + 1];
@@ -497,11 +500,10 @@ __global__ void __launch_bounds__(TeamsPerCta<NW>::value * NW * 32) k_fwd_warp2(
     pdl_wait();                                         // (idle teams too: this grid's completion must imply its predecessor's)
 }
 
-template <int NW>
-__global__ void __launch_bounds__(TeamsPerCta<NW>::value * NW * 32) k_bwd_warp2(SolveArgs a, WarpSched ws) {
+template <int NW, int NTEAM = TeamsPerCta<NW>::value>
+__global__ void __launch_bounds__(NTEAM * NW * 32) k_bwd_warp2(SolveArgs a, WarpSched ws) {
     extern __shared__ __align__(16) double smd[];
     double (*sm)[SolveSmem<NW>::doubles] = (double (*)[SolveSmem<NW>::doubles])smd;
-    constexpr int NTEAM = TeamsPerCta<NW>::value;
     const int team = threadIdx.x / (32 * NW), tid = threadIdx.x % (32 * NW);
     pdl_trigger();
     const int s0 = ws.cta_ptr[blockIdx.x], s1 = ws.cta_ptr[blockIdx.x + 1];

@@ -30,7 +30,7 @@ Base.@kwdef mutable struct B200Options <: AbstractOptions
     b200_use_cuda_graph::Int32 = 1
     b200_small_front_max::Int32 = 160
     b200_kkt_n_primal::Int32 = 0        # set by the KKT overloads below for SparseKKTSystem
-    b200_fuse_max_fronts::Int32 = 16
+    b200_fuse_max_fronts::Int32 = 8
     b200_dep_schedule::Int32 = 1
 end
 
