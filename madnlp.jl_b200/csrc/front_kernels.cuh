@@ -254,17 +254,17 @@ __device__ __forceinline__ void cp_async_commit_group() { asm volatile("cp.async
 template <int N>
 __device__ __forceinline__ void cp_async_wait_group_n() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-__global__ void __launch_bounds__(256, 2) k_big_update_pipe(FactorArgs a, const int32_t* __restrict__ list, int kb0, int kmax, int jlo_rel,
-                                                            int jhi_rel, int clip_jlo) {
-    const FrontDesc d = a.desc[list[blockIdx.z]];
+// one 128 x 64 tile (bx, by) of the update; `gu_sm` is the CTA's dynamic shared memory (GU_SMEM bytes).  Returns without work for
+// tiles above the diagonal / outside the column range.  All threads of the CTA must call it together.
+__device__ __forceinline__ void big_update_tile(const FactorArgs& a, const FrontDesc& d, int kb0, int kmax, int jlo_rel, int jhi_rel, int clip_jlo,
+                                                int bx, int by, double* gu_sm) {
     if (kb0 >= d.w) return;
     const int f = d.f;
     const int kcount = min(kmax, d.w - kb0);
     const int jlo = kb0 + (clip_jlo ? min(jlo_rel, kcount) : jlo_rel);
     const int jhi = min(f, kb0 + jhi_rel);
-    const int i0 = jlo + blockIdx.x * GU_M, j0 = jlo + blockIdx.y * GU_N;
+    const int i0 = jlo + bx * GU_M, j0 = jlo + by * GU_N;
     if (j0 > i0 + GU_M - 1 || i0 >= f || j0 >= jhi) return;          // tile above the diagonal / outside the front
-    extern __shared__ __align__(16) double gu_sm[];
     double* As = gu_sm;                                               // [stage][k][GU_LDA]
     double* Bs = gu_sm + GU_STAGES * GU_K * GU_LDA;                   // [stage][k][GU_LDB]
     double* dneg = Bs + GU_STAGES * GU_K * GU_LDB;                    // -d_k, k < kcount (<= 128)
@@ -366,6 +366,36 @@ __global__ void __launch_bounds__(256, 2) k_big_update_pipe(FactorArgs a, const 
                 if (j < jhi && i < f && i >= j) colp[cc][i] = t[cc][rr] + Cs[jj * GU_LDC + lane + 32 * rr];
             }
         }
+    }
+}
+
+
+__global__ void __launch_bounds__(256, 2) k_big_update_pipe(FactorArgs a, const int32_t* __restrict__ list, int kb0, int kmax, int jlo_rel,
+                                                            int jhi_rel, int clip_jlo) {
+    extern __shared__ __align__(16) double gu_sm[];
+    const FrontDesc d = a.desc[list[blockIdx.z]];
+    big_update_tile(a, d, kb0, kmax, jlo_rel, jhi_rel, clip_jlo, blockIdx.x, blockIdx.y, gu_sm);
+}
+
+// The same update as a PERSISTENT kernel with a dynamic tile queue, for the look-ahead schedule of the dense factorisation:
+// CTAs that land on the first `n_reserved` SMs exit at once, so those SMs stay free for the next panel's diagonal-block kernel
+// (one CTA that needs a whole SM) while this kernel works through the trailing update on all the others.  Tiles are handed out
+// by an atomic counter (`*tile_counter`, zeroed by the host before the launch), so it does not matter which CTAs left.
+__device__ __forceinline__ unsigned smid() { unsigned r; asm volatile("mov.u32 %0, %%smid;" : "=r"(r)); return r; }
+__global__ void __launch_bounds__(256, 2) k_big_update_dyn(FactorArgs a, const int32_t* __restrict__ list, int kb0, int kmax, int jlo_rel,
+                                                           int jhi_rel, int clip_jlo, int nbx, int nby, int* tile_counter, int n_reserved) {
+    extern __shared__ __align__(16) double gu_sm[];
+    __shared__ int t_sh;
+    if ((int)smid() < n_reserved) return;
+    const FrontDesc d = a.desc[list[0]];
+    const int ntile = nbx * nby;
+    for (;;) {
+        __syncthreads();                                 // (the previous tile's epilogue has finished with shared memory)
+        if (threadIdx.x == 0) t_sh = atomicAdd(tile_counter, 1);
+        __syncthreads();
+        const int t = t_sh;
+        if (t >= ntile) return;
+        big_update_tile(a, d, kb0, kmax, jlo_rel, jhi_rel, clip_jlo, t % nbx, t / nbx, gu_sm);
     }
 }
 

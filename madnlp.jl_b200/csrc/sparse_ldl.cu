@@ -997,6 +997,9 @@ struct b2d_solver {
     const double* A_d = nullptr;
     b2_options opt;
     DevBuf<double> fact, dvec, linv, side, flow;     // flow: [2][nblk*128] hand-off vectors of the single-launch solve
+    DevBuf<int32_t> tilecnt;                         // look-ahead schedule: one dynamic-tile counter per panel step
+    cudaStream_t aux_stream = nullptr;               // second branch of the look-ahead schedule (trailing updates)
+    std::vector<cudaEvent_t> ev_chain, ev_bulk;
     DevBuf<int64_t> linv_off;
     DevBuf<FrontDesc> desc;
     DevBuf<int32_t> list, counters;
@@ -1006,6 +1009,9 @@ struct b2d_solver {
     bool factorized = false;
     ~b2d_solver() {
         if (g_factor) cudaGraphExecDestroy(g_factor);
+        for (auto e : ev_chain) cudaEventDestroy(e);
+        for (auto e : ev_bulk) cudaEventDestroy(e);
+        if (aux_stream) cudaStreamDestroy(aux_stream);
         if (cap_stream) cudaStreamDestroy(cap_stream);
         if (h_counters) cudaFreeHost(h_counters);
     }
@@ -1018,7 +1024,55 @@ __global__ void k_copy_lower(int N, int lda, const double* __restrict__ A, doubl
         F[(size_t)j * N + i] = A[(size_t)j * lda + i];
 }
 
+// Look-ahead schedule of the dense LDL^T (two stream branches; captured into ONE graph by b2d_factorize):
+//   chain  S1:  D(k) diag block   T(k) rows below   C(k) update of block column k+1 only        D(k+1) ...
+//   bulk   S2:                                      R(k) update of the columns >= k+2 (persistent, dynamic tiles, leaves one SM free)
+// R(k) waits for C(k) (event), C(k+1) waits for R(k): the 60 us single-CTA diagonal-block kernel of panel k+1 (and as much of its
+// trsm as finds room) runs WHILE the trailing update of panel k occupies the other SMs, instead of after it.
+void enqueue_dense_factor_lookahead(b2d_solver* s, cudaStream_t S1) {
+    FactorArgs a;
+    a.desc = s->desc.p; a.child_idx = nullptr; a.rel = nullptr; a.amap_src = nullptr; a.amap_dst = nullptr;
+    a.A = nullptr; a.L = s->fact.p; a.ws = nullptr; a.dvec = s->dvec.p; a.counters = s->counters.p; a.eps = s->opt.pivot_eps;
+    const int N = s->N, nb = (N + DB - 1) / DB, nsm = sm_count();
+    cudaStream_t S2 = s->aux_stream;
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(k_big_diag128, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Diag128Smem));
+        cudaFuncSetAttribute(k_big_trsm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GU_SMEM);
+        cudaFuncSetAttribute(k_big_update_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GU_SMEM);
+        cudaFuncSetAttribute(k_big_update_dyn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GU_SMEM);
+        attr = true;
+    }
+    cudaMemsetAsync(s->counters.p, 0, 2 * sizeof(int32_t), S1);
+    cudaMemsetAsync(s->tilecnt.p, 0, s->tilecnt.bytes(), S1);
+    k_copy_lower<<<dim3(std::max(1, std::min(8, (N + 255) / 256)), N), 256, 0, S1>>>(N, s->lda, s->A_d, s->fact.p);
+    int last_bulk = -1;
+    for (int k = 0; k < nb; ++k) {
+        const int ob = k * DB;
+        k_big_diag128<<<1, 256, sizeof(Diag128Smem), S1>>>(a, s->list.p, ob, s->linv.p, s->linv_off.p);
+        const int rem = N - ob - 1;
+        if (rem <= 0 || ob + DB >= N) continue;
+        k_big_trsm<<<dim3((rem + TR_ROWS - 1) / TR_ROWS, 1), 256, GU_SMEM, S1>>>(a, s->list.p, ob, s->linv.p, s->linv_off.p);
+        if (last_bulk >= 0) cudaStreamWaitEvent(S1, s->ev_bulk[last_bulk], 0);       // R(k-1) also wrote block column k+1
+        const int rem1 = N - (ob + DB);                                                // rows/cols from the next block on
+        k_big_update_pipe<<<dim3((rem1 + GU_M - 1) / GU_M, (DB + GU_N - 1) / GU_N, 1), 256, GU_SMEM, S1>>>(a, s->list.p, ob, DB, DB, 2 * DB, 1);
+        const int rem2 = N - (ob + 2 * DB);
+        if (rem2 > 0) {
+            cudaEventRecord(s->ev_chain[k], S1);
+            cudaStreamWaitEvent(S2, s->ev_chain[k], 0);
+            const int nbx = (rem2 + GU_M - 1) / GU_M, nby = (rem2 + GU_N - 1) / GU_N;
+            k_big_update_dyn<<<2 * nsm, 256, GU_SMEM, S2>>>(a, s->list.p, ob, DB, 2 * DB, 1 << 30, 0, nbx, nby, s->tilecnt.p + k, 1);
+            cudaEventRecord(s->ev_bulk[k], S2);
+            last_bulk = k;
+        }
+    }
+    if (last_bulk >= 0) cudaStreamWaitEvent(S1, s->ev_bulk[last_bulk], 0);           // join
+}
+
 void enqueue_dense_factor(b2d_solver* s, cudaStream_t st) {
+    static int lookahead = -1;
+    if (lookahead < 0) { const char* e = getenv("B2_DENSE_LOOKAHEAD"); lookahead = e ? (atoi(e) != 0) : 1; }
+    if (lookahead && s->aux_stream && s->N > 4 * DB) { enqueue_dense_factor_lookahead(s, st); return; }
     FactorArgs a;
     a.desc = s->desc.p; a.child_idx = nullptr; a.rel = nullptr; a.amap_src = nullptr; a.amap_dst = nullptr;
     a.A = nullptr; a.L = s->fact.p; a.ws = nullptr; a.dvec = s->dvec.p; a.counters = s->counters.p; a.eps = s->opt.pivot_eps;
@@ -1053,11 +1107,21 @@ int b2d_create(int32_t N, int32_t lda, const double* A_d, const b2_options* opt,
         s->list.upload(&zero, 1) != cudaSuccess || s->counters.alloc(4) != cudaSuccess ||
         cudaMallocHost((void**)&s->h_counters, 4 * sizeof(int32_t)) != cudaSuccess ||
         cudaStreamCreateWithFlags(&s->cap_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&s->aux_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        s->tilecnt.alloc((size_t)((N + DB - 1) / DB)) != cudaSuccess ||
         cudaMemset(s->fact.p, 0, s->fact.bytes()) != cudaSuccess || cudaMemset(s->counters.p, 0, 4 * sizeof(int32_t)) != cudaSuccess) {
         delete s;
         return cuda_fail(cudaGetLastError(), "b2d_create allocation", __FILE__, __LINE__);
     }
     if (set_smem_attrs() != B2_OK) { delete s; return B2_ERR_CUDA; }
+    {
+        const int nb = (N + DB - 1) / DB;
+        s->ev_chain.resize(nb); s->ev_bulk.resize(nb);
+        for (int k = 0; k < nb; ++k) {
+            if (cudaEventCreateWithFlags(&s->ev_chain[k], cudaEventDisableTiming) != cudaSuccess ||
+                cudaEventCreateWithFlags(&s->ev_bulk[k], cudaEventDisableTiming) != cudaSuccess) { delete s; return cuda_fail(cudaGetLastError(), "b2d_create events", __FILE__, __LINE__); }
+        }
+    }
     *out = s;
     return B2_OK;
 }

@@ -21,12 +21,14 @@ kkt = K.create_kkt_system(K.SparseCondensedKKTSystem, cb, None, pkg.capi.default
 la = IPMLinearAlgebra(kkt)
 devit = [{k: torch.from_numpy(np.ascontiguousarray(getattr(it, k))).cuda() for k in bench.FIELDS} for it in its]
 flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device="cuda")
-for i in range(8):
+for i in range(14):
     la.load_iterate(devit[i % len(devit)]); assert la.step(mu=its[i % len(its)].mu)
 ev = lambda: torch.cuda.Event(enable_timing=True)
 rows = []
 itx = la.iterator
 for i in range(24):
+    if i % len(devit) == bench.NONCONVEX_AT:
+        continue                      # the nonconvex iterate takes the regularisation branch: not a plain step
     it = devit[i % len(devit)]
     flush.fill_(1.0); torch.cuda.synchronize()
     e = [ev() for _ in range(8)]; h = []
