@@ -34,7 +34,8 @@ struct Diag128Smem {
     double ubuf[2][DB];                   // pivot column (unscaled), double-buffered
     double xbuf[2][DB];                   // row k of the inverse
     double dd[DB];
-    unsigned long long bar[4];            // [0..1] phase F, [2..3] phase I
+    double tb[32 * 33];                   // phase I: one 32 x 32 product of the blocked inversion (column-major, ld 33)
+    unsigned long long bar[4];            // [0..1] phase F (2..3 unused)
 };
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
@@ -165,64 +166,87 @@ __global__ void __launch_bounds__(256, 1) k_big_diag128(FactorArgs a, const int3
         a.dvec[d.col0 + kb + tid] = sm.dd[tid];
     }
     DPROF();
-    // ---- phase I: X = L11^{-1} by the same elementary operations applied to the identity:
-    //      for k: X(i, :) -= l(i,k) * X(k, :), i > k  (row k is final by then and non-zero only in columns <= k)
+    // ---- phase I: X = L11^{-1}, BLOCKED (4 x 4 blocks of 32), in place in sm.Lc (L11 has been written back to global memory):
+    //      (1) the four unit-lower diagonal blocks are inverted by one warp each -- lane j runs the forward substitution of column j
+    //          in registers, every l(i,k) is a shared-memory broadcast;
+    //      (2) X_ij = -X_ii * (sum_{k=j}^{i-1} L_ik X_kj) for i > j, block row by block row and j ascending (so that L_ij may be
+    //          overwritten by X_ij), each 32^3 product on the fp64 tensor pipe (8 warps x 2 tiles of m8n8k4 DMMA).
+    //      The round-1 version applied the 127 elementary row operations one by one (one mbarrier hand-off each, ~340 clk per step,
+    //      22 us of the 60 us this kernel sits on the factorisation's critical path); this is ~16 dependent steps.
+    {
+        const int warp = tid >> 5, lane = tid & 31;
+        double* Lc = sm.Lc;
+        if (warp < 4) {
+            const int o = 32 * warp;
+            double x[32];
 #pragma unroll
-    for (int ia = 0; ia < 8; ++ia)
+            for (int i = 0; i < 32; ++i) x[i] = (i == lane) ? 1.0 : 0.0;
 #pragma unroll
-        for (int ib = 0; ib < 8; ++ib) A[ia][ib] = (ty + 16 * ia == tx + 16 * ib) ? 1.0 : 0.0;
-    if (ty == 0) {
+            for (int i = 1; i < 32; ++i) {
+                double acc = 0.0;
 #pragma unroll
-        for (int ib = 0; ib < 8; ++ib) sm.xbuf[0][tx + 16 * ib] = A[0][ib];
-    }
-    mbar_arrive(&sm.bar[2]);
-#pragma unroll
-    for (int kq = 0; kq < 8; ++kq) {
-        for (int kk = 0; kk < 16; ++kk) {
-            const int k = 16 * kq + kk;
-            if (k + 1 >= nb) break;                                // the last column has nothing below it
-            const double* xb = sm.xbuf[k & 1];
-            mbar_wait(&sm.bar[2 + (k & 1)], (k >> 1) & 1);
-            const double* lc = sm.Lc + k * DB + ty;
-            double li[8], xr[8];
-#pragma unroll
-            for (int ia = 0; ia < 8; ++ia) li[ia] = (ia >= kq) ? -lc[16 * ia] : 0.0;
-#pragma unroll
-            for (int ib = 0; ib < 8; ++ib) xr[ib] = (ib <= kq) ? xb[tx + 16 * ib] : 0.0;
-            const bool have_next = k + 2 < nb;
-            const bool own_next = ty == ((kk + 1) & 15);
-            if (have_next && !own_next) mbar_arrive(&sm.bar[2 + ((k + 1) & 1)]);
-            // the two candidate next rows first (a-index kq, or kq+1 when kk == 15)
-#pragma unroll
-            for (int ia = kq; ia < min(kq + 2, 8); ++ia)
-#pragma unroll
-                for (int ib = 0; ib < 8; ++ib)
-                    if (ib <= kq) A[ia][ib] = fma(li[ia], xr[ib], A[ia][ib]);
-            if (have_next && own_next) {
-                double* xn = sm.xbuf[(k + 1) & 1];
-#pragma unroll
-                for (int ib = 0; ib < 8; ++ib) xn[tx + 16 * ib] = (kk == 15) ? A[min(kq + 1, 7)][ib] : A[kq][ib];
-                mbar_arrive(&sm.bar[2 + ((k + 1) & 1)]);
+                for (int k = 0; k < i; ++k) acc = fma(Lc[(o + k) * DB + o + i], x[k], acc);      // x[k] = 0 for k < lane: harmless
+                x[i] = (i > lane) ? -acc : x[i];
             }
+            __syncwarp();
 #pragma unroll
-            for (int ia = kq + 2; ia < 8; ++ia)
+            for (int i = 0; i < 32; ++i) Lc[(o + lane) * DB + o + i] = (i >= lane) ? x[i] : 0.0; // column `lane` of X_bb incl. the unit diagonal
+        }
+        __syncthreads();
+        const int g = lane >> 2, q = lane & 3;
+        const int tr = warp & 3, tc0 = (warp >> 2) * 2;          // this warp's two 8 x 8 output tiles: tile row tr, tile columns tc0, tc0 + 1
+        for (int bi = 1; bi < 4; ++bi) {
+            for (int bj = 0; bj < bi; ++bj) {
+                double c[2][2];
+                // stage 1: T = sum_{k = bj}^{bi-1} L(bi, k) X(k, bj)
+                c[0][0] = c[0][1] = c[1][0] = c[1][1] = 0.0;
+                for (int bk = bj; bk < bi; ++bk) {
 #pragma unroll
-                for (int ib = 0; ib < 8; ++ib)
-                    if (ib <= kq) A[ia][ib] = fma(li[ia], xr[ib], A[ia][ib]);
+                    for (int k0 = 0; k0 < 32; k0 += 4) {
+                        const double af = Lc[(32 * bk + k0 + q) * DB + 32 * bi + 8 * tr + g];            // L(bi,bk)(row 8tr+g, k0+q)
+#pragma unroll
+                        for (int y = 0; y < 2; ++y) {
+                            const double bf = Lc[(32 * bj + 8 * (tc0 + y) + g) * DB + 32 * bk + k0 + q];  // X(bk,bj)(k0+q, col)
+                            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                                         : "+d"(c[y][0]), "+d"(c[y][1]) : "d"(af), "d"(bf));
+                        }
+                    }
+                }
+#pragma unroll
+                for (int y = 0; y < 2; ++y)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) sm.tb[(8 * (tc0 + y) + 2 * q + e) * 33 + 8 * tr + g] = c[y][e];
+                __syncthreads();
+                // stage 2: X(bi, bj) = -X(bi, bi) * T      (overwrites L(bi, bj): no later product needs it)
+                c[0][0] = c[0][1] = c[1][0] = c[1][1] = 0.0;
+#pragma unroll
+                for (int k0 = 0; k0 < 32; k0 += 4) {
+                    const double af = Lc[(32 * bi + k0 + q) * DB + 32 * bi + 8 * tr + g];                 // X(bi,bi)(row, k0+q)
+#pragma unroll
+                    for (int y = 0; y < 2; ++y) {
+                        const double bf = sm.tb[(8 * (tc0 + y) + g) * 33 + k0 + q];                       // T(k0+q, col)
+                        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                                     : "+d"(c[y][0]), "+d"(c[y][1]) : "d"(af), "d"(bf));
+                    }
+                }
+                __syncthreads();                                   // every warp has read L(bi, bj) (stage 1) and T (stage 2)
+#pragma unroll
+                for (int y = 0; y < 2; ++y)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) Lc[(32 * bj + 8 * (tc0 + y) + 2 * q + e) * DB + 32 * bi + 8 * tr + g] = -c[y][e];
+                __syncthreads();
+            }
         }
     }
     DPROF();
     // ---- store the inverse, column-major with ld DB, zero outside the nb x nb unit-lower block
     double* out = Linv + linv_off[s] + (size_t)(kb / DB) * DB * DB;
-#pragma unroll
-    for (int ib = 0; ib < 8; ++ib)
-#pragma unroll
-        for (int ia = 0; ia < 8; ++ia) {
-            const int i = ty + 16 * ia, j = tx + 16 * ib;
-            double v = 0.0;
-            if (i < nb && j < nb) v = (i > j) ? A[ia][ib] : (i == j ? 1.0 : 0.0);
-            out[(size_t)j * DB + i] = v;
-        }
+    for (int e = tid; e < DB * DB; e += 256) {
+        const int i = e & (DB - 1), j = e >> 7;
+        double v = 0.0;
+        if (i < nb && j < nb && i >= j) v = (i == j) ? 1.0 : sm.Lc[j * DB + i];
+        out[(size_t)j * DB + i] = v;
+    }
 #ifdef B2_DIAG_PROF
     DPROF();
     if (tid == 0 && blockIdx.x == 0 && (kb == 0 || kb == 1280))

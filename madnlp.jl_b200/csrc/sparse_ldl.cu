@@ -1035,6 +1035,8 @@ void enqueue_dense_factor_lookahead(b2d_solver* s, cudaStream_t S1) {
     a.A = nullptr; a.L = s->fact.p; a.ws = nullptr; a.dvec = s->dvec.p; a.counters = s->counters.p; a.eps = s->opt.pivot_eps;
     const int N = s->N, nb = (N + DB - 1) / DB, nsm = sm_count();
     cudaStream_t S2 = s->aux_stream;
+    static int n_reserved = -1;        // SMs the trailing update leaves to the chain (diagonal block: 1 CTA; trsm / column update: many)
+    if (n_reserved < 0) { const char* e = getenv("B2_DENSE_RESERVED_SMS"); n_reserved = e ? std::max(1, atoi(e)) : 1; }
     static bool attr = false;
     if (!attr) {
         cudaFuncSetAttribute(k_big_diag128, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Diag128Smem));
@@ -1061,7 +1063,7 @@ void enqueue_dense_factor_lookahead(b2d_solver* s, cudaStream_t S1) {
             cudaEventRecord(s->ev_chain[k], S1);
             cudaStreamWaitEvent(S2, s->ev_chain[k], 0);
             const int nbx = (rem2 + GU_M - 1) / GU_M, nby = (rem2 + GU_N - 1) / GU_N;
-            k_big_update_dyn<<<2 * nsm, 256, GU_SMEM, S2>>>(a, s->list.p, ob, DB, 2 * DB, 1 << 30, 0, nbx, nby, s->tilecnt.p + k, 1);
+            k_big_update_dyn<<<2 * nsm, 256, GU_SMEM, S2>>>(a, s->list.p, ob, DB, 2 * DB, 1 << 30, 0, nbx, nby, s->tilecnt.p + k, n_reserved);
             cudaEventRecord(s->ev_bulk[k], S2);
             last_bulk = k;
         }
