@@ -28,13 +28,15 @@ constexpr int DB = 128;                   // outer block (== BS of the solve ker
 // Pivot-to-pivot synchronisation is an mbarrier per buffer instead of __syncthreads: the 16 threads that own the NEXT
 // pivot column update it first, publish it and arrive; everybody else arrives as soon as the current column has been
 // read, so the rest of the rank-1 update overlaps the owners' critical path (wait -> rcp -> column -> publish).
-constexpr int DB_LDS = DB + 1;            // padded stage (transposed reads of the symmetric fill are conflict-free)
+constexpr int DB_LDS = DB + 4;            // leading dimension of the block in shared memory: 132 = 4 (mod 16) doubles, so that the DMMA
+                                          // fragment loads of the blocked inversion (8 rows x 4 k, or 4 k x 8 columns) take the minimum of
+                                          // two wavefronts; the transposed reads of the symmetric fill stay cheap
 struct Diag128Smem {
-    double Lc[DB * DB_LDS];               // stage[j*DB_LDS + i] on entry; then Lc[k*DB + i] = l(i,k) for i > k, 0 for i <= k
+    double Lc[DB * DB_LDS];               // stage[j*DB_LDS + i] on entry; then Lc[k*DB_LDS + i] = l(i,k) for i > k, 0 for i <= k
     double ubuf[2][DB];                   // pivot column (unscaled), double-buffered
     double xbuf[2][DB];                   // row k of the inverse
     double dd[DB];
-    double tb[32 * 33];                   // phase I: one 32 x 32 product of the blocked inversion (column-major, ld 33)
+    double tb[32 * 36];                   // phase I: one 32 x 32 product of the blocked inversion (column-major, ld 36)
     unsigned long long bar[4];            // [0..1] phase F (2..3 unused)
 };
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
@@ -138,7 +140,7 @@ __global__ void __launch_bounds__(256, 1) k_big_diag128(FactorArgs a, const int3
                 mbar_arrive(&sm.bar[(k + 1) & 1]);
             }
             if (tx == kk) {
-                double* lc = sm.Lc + k * DB + ty;
+                double* lc = sm.Lc + k * DB_LDS + ty;
 #pragma unroll
                 for (int ia = 0; ia < 8; ++ia) lc[16 * ia] = (ty + 16 * ia > k) ? -li[ia] : 0.0;
                 if (ty == kk) sm.dd[k] = dk;
@@ -159,7 +161,7 @@ __global__ void __launch_bounds__(256, 1) k_big_diag128(FactorArgs a, const int3
     // ---- write back L11 (strict lower, unit diagonal implied) and D
     for (int e = tid; e < DB * DB; e += 256) {
         const int i = e & (DB - 1), j = e >> 7;
-        if (i < nb && j < i) Lp[(size_t)(kb + j) * f + kb + i] = sm.Lc[j * DB + i];
+        if (i < nb && j < i) Lp[(size_t)(kb + j) * f + kb + i] = sm.Lc[j * DB_LDS + i];
     }
     if (tid < nb) {
         Lp[(size_t)(kb + tid) * f + kb + tid] = sm.dd[tid];
@@ -185,12 +187,12 @@ __global__ void __launch_bounds__(256, 1) k_big_diag128(FactorArgs a, const int3
             for (int i = 1; i < 32; ++i) {
                 double acc = 0.0;
 #pragma unroll
-                for (int k = 0; k < i; ++k) acc = fma(Lc[(o + k) * DB + o + i], x[k], acc);      // x[k] = 0 for k < lane: harmless
+                for (int k = 0; k < i; ++k) acc = fma(Lc[(o + k) * DB_LDS + o + i], x[k], acc);      // x[k] = 0 for k < lane: harmless
                 x[i] = (i > lane) ? -acc : x[i];
             }
             __syncwarp();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) Lc[(o + lane) * DB + o + i] = (i >= lane) ? x[i] : 0.0; // column `lane` of X_bb incl. the unit diagonal
+            for (int i = 0; i < 32; ++i) Lc[(o + lane) * DB_LDS + o + i] = (i >= lane) ? x[i] : 0.0; // column `lane` of X_bb incl. the unit diagonal
         }
         __syncthreads();
         const int g = lane >> 2, q = lane & 3;
@@ -203,10 +205,10 @@ __global__ void __launch_bounds__(256, 1) k_big_diag128(FactorArgs a, const int3
                 for (int bk = bj; bk < bi; ++bk) {
 #pragma unroll
                     for (int k0 = 0; k0 < 32; k0 += 4) {
-                        const double af = Lc[(32 * bk + k0 + q) * DB + 32 * bi + 8 * tr + g];            // L(bi,bk)(row 8tr+g, k0+q)
+                        const double af = Lc[(32 * bk + k0 + q) * DB_LDS + 32 * bi + 8 * tr + g];            // L(bi,bk)(row 8tr+g, k0+q)
 #pragma unroll
                         for (int y = 0; y < 2; ++y) {
-                            const double bf = Lc[(32 * bj + 8 * (tc0 + y) + g) * DB + 32 * bk + k0 + q];  // X(bk,bj)(k0+q, col)
+                            const double bf = Lc[(32 * bj + 8 * (tc0 + y) + g) * DB_LDS + 32 * bk + k0 + q];  // X(bk,bj)(k0+q, col)
                             asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                                          : "+d"(c[y][0]), "+d"(c[y][1]) : "d"(af), "d"(bf));
                         }
@@ -215,16 +217,16 @@ __global__ void __launch_bounds__(256, 1) k_big_diag128(FactorArgs a, const int3
 #pragma unroll
                 for (int y = 0; y < 2; ++y)
 #pragma unroll
-                    for (int e = 0; e < 2; ++e) sm.tb[(8 * (tc0 + y) + 2 * q + e) * 33 + 8 * tr + g] = c[y][e];
+                    for (int e = 0; e < 2; ++e) sm.tb[(8 * (tc0 + y) + 2 * q + e) * 36 + 8 * tr + g] = c[y][e];
                 __syncthreads();
                 // stage 2: X(bi, bj) = -X(bi, bi) * T      (overwrites L(bi, bj): no later product needs it)
                 c[0][0] = c[0][1] = c[1][0] = c[1][1] = 0.0;
 #pragma unroll
                 for (int k0 = 0; k0 < 32; k0 += 4) {
-                    const double af = Lc[(32 * bi + k0 + q) * DB + 32 * bi + 8 * tr + g];                 // X(bi,bi)(row, k0+q)
+                    const double af = Lc[(32 * bi + k0 + q) * DB_LDS + 32 * bi + 8 * tr + g];                 // X(bi,bi)(row, k0+q)
 #pragma unroll
                     for (int y = 0; y < 2; ++y) {
-                        const double bf = sm.tb[(8 * (tc0 + y) + g) * 33 + k0 + q];                       // T(k0+q, col)
+                        const double bf = sm.tb[(8 * (tc0 + y) + g) * 36 + k0 + q];                       // T(k0+q, col)
                         asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                                      : "+d"(c[y][0]), "+d"(c[y][1]) : "d"(af), "d"(bf));
                     }
@@ -233,7 +235,7 @@ __global__ void __launch_bounds__(256, 1) k_big_diag128(FactorArgs a, const int3
 #pragma unroll
                 for (int y = 0; y < 2; ++y)
 #pragma unroll
-                    for (int e = 0; e < 2; ++e) Lc[(32 * bj + 8 * (tc0 + y) + 2 * q + e) * DB + 32 * bi + 8 * tr + g] = -c[y][e];
+                    for (int e = 0; e < 2; ++e) Lc[(32 * bj + 8 * (tc0 + y) + 2 * q + e) * DB_LDS + 32 * bi + 8 * tr + g] = -c[y][e];
                 __syncthreads();
             }
         }
@@ -244,7 +246,7 @@ __global__ void __launch_bounds__(256, 1) k_big_diag128(FactorArgs a, const int3
     for (int e = tid; e < DB * DB; e += 256) {
         const int i = e & (DB - 1), j = e >> 7;
         double v = 0.0;
-        if (i < nb && j < nb && i >= j) v = (i == j) ? 1.0 : sm.Lc[j * DB + i];
+        if (i < nb && j < nb && i >= j) v = (i == j) ? 1.0 : sm.Lc[j * DB_LDS + i];
         out[(size_t)j * DB + i] = v;
     }
 #ifdef B2_DIAG_PROF
