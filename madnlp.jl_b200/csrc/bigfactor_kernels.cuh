@@ -94,12 +94,13 @@ __global__ void __launch_bounds__(256, 1) k_big_diag128(FactorArgs a, const int3
 #pragma unroll
         for (int ib = 0; ib < 8; ++ib) {
             const int i = ty + 16 * ia, j = tx + 16 * ib;
-            A[ia][ib] = stage[min(i, j) * DB_LDS + max(i, j)];
+            A[ia][ib] = (ia >= ib) ? stage[min(i, j) * DB_LDS + max(i, j)] : 0.0;    // block-lower part only (see phase F)
         }
     __syncthreads();
     int nneg = 0, npert = 0;
     DPROF();
-    // ---- phase F: unblocked right-looking LDL^T
+    // ---- phase F: unblocked right-looking LDL^T.  Only the register blocks on or below the block diagonal (ia >= ib: 36 of the 64)
+    //      are kept up to date -- the diagonal blocks stay fully symmetric, so every pivot column is still read out of one b-index.
     if (tx == 0) {
 #pragma unroll
         for (int ia = 0; ia < 8; ++ia) sm.ubuf[0][ty + 16 * ia] = A[ia][0];
@@ -132,7 +133,7 @@ __global__ void __launch_bounds__(256, 1) k_big_diag128(FactorArgs a, const int3
             for (int ib = kq; ib < min(kq + 2, 8); ++ib)
 #pragma unroll
                 for (int ia = 0; ia < 8; ++ia)
-                    if (ia >= kq) A[ia][ib] = fma(li[ia], uc[ib], A[ia][ib]);
+                    if (ia >= kq && ia >= ib) A[ia][ib] = fma(li[ia], uc[ib], A[ia][ib]);
             if (have_next && own_next) {
                 double* un = sm.ubuf[(k + 1) & 1];
 #pragma unroll
@@ -149,7 +150,7 @@ __global__ void __launch_bounds__(256, 1) k_big_diag128(FactorArgs a, const int3
             for (int ib = kq + 2; ib < 8; ++ib)
 #pragma unroll
                 for (int ia = 0; ia < 8; ++ia)
-                    if (ia >= kq) A[ia][ib] = fma(li[ia], uc[ib], A[ia][ib]);
+                    if (ia >= kq && ia >= ib) A[ia][ib] = fma(li[ia], uc[ib], A[ia][ib]);
         }
     }
     if (tid == 0) {
