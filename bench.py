@@ -330,6 +330,7 @@ def run_b200(args, rank, world, local_rank):
     fac_ms = time_phase(kkt.linear_solver.factorize)
     sol_ms = time_phase(lambda: kkt.linear_solver.solve_linear_system(xsol))
     clocks = sampler.stop() if sampler else None
+    stats = kkt.linear_solver.stats()          # (launch counts are known once the sweeps have been issued)
 
     secondary = None
     if not args.no_secondary:

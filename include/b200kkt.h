@@ -194,6 +194,12 @@ int b2_condensed_symbolic(int32_t n, int32_t m,
                           const int32_t* H_colptr_h, const int32_t* H_rowval_h,
                           const int32_t* Jt_colptr_h, const int32_t* Jt_rowval_h,
                           b2_condensed_plan** out, int64_t* nnz_aug);
+/* the same construction with device sorts (condensed.jl:251 on the GPU, lib/MadNLPGPU/src/KKT/gpu_sparse.jl:100-130): patterns are
+ * DEVICE arrays; the resulting plan is identical to b2_condensed_symbolic's.  Synchronises `stream`. */
+int b2_condensed_symbolic_device(int32_t n, int32_t m,
+                                 const int32_t* H_colptr_d, const int32_t* H_rowval_d,
+                                 const int32_t* Jt_colptr_d, const int32_t* Jt_rowval_d,
+                                 b2_condensed_plan** out, int64_t* nnz_aug, void* stream);
 int b2_condensed_pattern(b2_condensed_plan* p, int32_t* colptr_h, int32_t* rowval_h);
 int b2_condensed_plan_sizes(b2_condensed_plan* p, int64_t* n_dptr, int64_t* n_hptr, int64_t* n_jptr);
 int b2_condensed_plan_destroy(b2_condensed_plan* p);

@@ -116,6 +116,7 @@ PROTOTYPES = {
     "b2d_inertia_enqueue": (C.c_int, [_p, _p]),
     "b2d_inertia_fetch": (C.c_int, [_p, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64)]),
     "b2d_solve": (C.c_int, [_p, _p, _i32, _p]),
+    "b2_condensed_symbolic_device": (C.c_int, [_i32, _i32, _p, _p, _p, _p, _PP, C.POINTER(_i64), _p]),
     "b2_coo_to_csc_device": (C.c_int, [_i32, _i32, _i64, _p, _p, _p, _p, _p, C.POINTER(_i64), _p]),
     "b2d_ozaki_plan_create": (C.c_int, [_i32, _i32, _PP]),
     "b2d_ozaki_plan_destroy": (C.c_int, [_p]),

@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "condensed_plan.cuh"
 
 using namespace b2;
 
@@ -107,14 +108,6 @@ extern "C" int b2_transfer(b2_transfer_plan* p, double* dst_nz_d, const double* 
 // ---------------------------------------------------------------------------------------------------------
 // sparse condensed KKT:  aug = tril(H) + diag(pr_diag[1:n]) + tril(Jt * D * Jt')
 // ---------------------------------------------------------------------------------------------------------
-struct b2_condensed_plan {
-    int32_t n = 0, m = 0;
-    int64_t nnz_aug = 0, n_dptr = 0, n_hptr = 0, n_jptr = 0;
-    std::vector<int32_t> colptr, rowval;
-    DevBuf<int32_t> hsrc, dsrc, tptr;   // per slot: H.nz index or -1, pr_diag index or -1, triple range
-    DevBuf<int4> trip;                  // (col, k, l, 0): D[col]*Jt.nz[k]*Jt.nz[l]
-};
-
 __global__ void k_diag_buffer(int64_t m, const double* __restrict__ Ss, const double* __restrict__ Sd, double* __restrict__ D) {
     pdl_sync();
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x)

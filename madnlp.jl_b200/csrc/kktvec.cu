@@ -607,20 +607,63 @@ __global__ void __launch_bounds__(256) k_gemv_t(int rows, int cols, int lda, con
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if (lane == 0) y[j] = alpha * acc + scl2(beta, y[j]);
 }
-// symmetric product from the lower triangle: y_j = alpha*( sum_{i>=j} A(i,j) x_i + sum_{i<j} A(j,i) x_i ) + beta*y_j.
-// One warp per column j: the column part streams coalesced; the row part (A(j,i), i<j) is a strided read of row j.
-__global__ void __launch_bounds__(256) k_symv_lower(int n, int lda, const double* __restrict__ A, const double* __restrict__ x,
-                                                    double* __restrict__ y, double alpha, double beta) {
+// symmetric product from the lower triangle: y_j = alpha*( sum_{i>=j} A(i,j) x_i + sum_{i<j} A(j,i) x_i ) + beta*y_j, in TWO
+// coalesced passes over the lower triangle (the one-pass version read row j of the triangle with a stride of lda doubles):
+//   pass 1 (k_symv_lower_cols): one warp per column j, lanes stride the rows i >= j           -> y_j  = alpha * t_j + beta * y_j
+//   pass 2 (k_symv_lower_rows): a CTA owns 32 rows, its 8 warps take interleaved column groups -> y_i += alpha * sum_{j<i} A(i,j) x_j
+__global__ void __launch_bounds__(256) k_symv_lower_cols(int n, int lda, const double* __restrict__ A, const double* __restrict__ x,
+                                                         double* __restrict__ y, double alpha, double beta) {
     const int lane = threadIdx.x & 31;
     const int j = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (j >= n) return;
     const double* col = A + (size_t)j * lda;
     double acc = 0.0;
-    for (int i = j + lane; i < n; i += 32) acc = fma(col[i], x[i], acc);
-    for (int i = lane; i < j; i += 32) acc = fma(A[(size_t)i * lda + j], x[i], acc);
+    int i = j + lane;
+    for (; i + 7 * 32 < n; i += 8 * 32) {
+        double v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = col[i + 32 * u];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc = fma(v[u], x[i + 32 * u], acc);
+    }
+    for (; i < n; i += 32) acc = fma(col[i], x[i], acc);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if (lane == 0) y[j] = alpha * acc + scl2(beta, y[j]);
+}
+__global__ void __launch_bounds__(256) k_symv_lower_rows(int n, int lda, const double* __restrict__ A, const double* __restrict__ x,
+                                                         double* __restrict__ y, double alpha) {
+    __shared__ double part[8][GEMV_ROWS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int r0 = blockIdx.x * GEMV_ROWS, i = r0 + lane;
+    const bool ok = i < n;
+    const double* base = A + (ok ? i : 0);
+    const int jend = min(n, r0 + GEMV_ROWS);                 // columns j < i <= r0 + 31
+    double acc = 0.0;
+    for (int j = warp * 8; j < jend; j += 64) {
+        double v[8], xv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int jj = j + u;
+            const bool use = ok && jj < i;                   // strictly below the diagonal
+            v[u] = use ? base[(size_t)jj * lda] : 0.0;
+            xv[u] = use ? x[jj] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc = fma(v[u], xv[u], acc);
+    }
+    part[warp][lane] = acc;
+    __syncthreads();
+    if (warp == 0 && ok) {
+        double tot = 0.0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) tot += part[q][lane];
+        y[i] += alpha * tot;
+    }
+}
+static inline void launch_symv_lower(int n, int lda, const double* A, const double* x, double* y, double alpha, double beta, cudaStream_t st) {
+    k_symv_lower_cols<<<(n + 7) / 8, 256, 0, st>>>(n, lda, A, x, y, alpha, beta);
+    k_symv_lower_rows<<<(n + GEMV_ROWS - 1) / GEMV_ROWS, 256, 0, st>>>(n, lda, A, x, y, alpha);
 }
 
 extern "C" int b2d_gemv_n(int32_t rows, int32_t cols, int32_t lda, const double* A_d, const double* x_d, double* y_d, double alpha,
@@ -643,7 +686,7 @@ extern "C" int b2d_symv_lower(int32_t n, int32_t lda, const double* A_d, const d
                               void* stream) {
     if (n < 0 || lda < n || (n && (!A_d || !x_d || !y_d))) { set_error("b2d_symv_lower: invalid argument"); return B2_ERR_INVALID; }
     if (n == 0) return B2_OK;
-    k_symv_lower<<<(n + 7) / 8, 256, 0, as_stream(stream)>>>(n, lda, A_d, x_d, y_d, alpha, beta);
+    launch_symv_lower(n, lda, A_d, x_d, y_d, alpha, beta, as_stream(stream));
     B2_CUDA(cudaGetLastError());
     return B2_OK;
 }
@@ -779,7 +822,7 @@ extern "C" int b2d_kkt_mul(b2d_kkt* k, b2_bounds* b, const double* hess_d, const
     if (!k || !b || !x_d || !w_d || b->n_tot != (int64_t)k->n + k->ns) { set_error("b2d_kkt_mul: invalid argument"); return B2_ERR_INVALID; }
     cudaStream_t st = as_stream(stream);
     const int n = k->n, m = k->m;
-    if (n > 0) k_symv_lower<<<(n + 7) / 8, 256, 0, st>>>(n, n, hess_d, x_d, w_d, alpha, beta);                       // _symv!('L', alpha, hess, xx, beta, wx)
+    if (n > 0) launch_symv_lower(n, n, hess_d, x_d, w_d, alpha, beta, st);                                           // _symv!('L', alpha, hess, xx, beta, wx)
     if (m > 0) {
         if (n > 0) k_gemv_t<<<(n + 7) / 8, 256, 0, st>>>(m, n, m, jac_d, x_d + b->n_tot, w_d, alpha, 1.0);           // wx += alpha jac' xy
         k_gemv_n<<<(m + GEMV_ROWS - 1) / GEMV_ROWS, 256, 0, st>>>(m, n, m, jac_d, x_d, w_d + b->n_tot, alpha, beta);                  // wy = alpha jac xx + beta wy

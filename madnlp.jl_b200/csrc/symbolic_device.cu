@@ -87,3 +87,153 @@ extern "C" int b2_coo_to_csc_device(int32_t m, int32_t n, int64_t nnz_coo, const
     if (nnz_csc) *nnz_csc = h_last;
     return B2_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// build_condensed_aug_symbolic on the device (src/KKT/Sparse/condensed.jl:201-301; the reference's GPU path sorts the same key list
+// on the device, lib/MadNLPGPU/src/KKT/gpu_sparse.jl:100-130 + condensed.jl:251): enumerate diag | hess | Jt column pairs in the
+// reference's order, STABLE radix sort by (col, row), unique -> slots; the per-slot source lists keep the enumeration order, so the
+// plan -- and therefore every bit of the assembled matrix -- equals the host construction's (tests/test_gpu_symbolic.py).
+// ---------------------------------------------------------------------------------------------------------------------
+#include "condensed_plan.cuh"
+
+namespace {
+__global__ void k_pair_counts(int m, const int32_t* __restrict__ Jc, int32_t* __restrict__ cnt) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
+        const int c = Jc[i + 1] - Jc[i];
+        cnt[i] = c * (c + 1) / 2;
+    }
+}
+__global__ void k_fill_diag_hess(int n, const int32_t* __restrict__ Hc, const int32_t* __restrict__ Hr, int64_t* __restrict__ key,
+                                 int32_t* __restrict__ idx, int* __restrict__ bad) {
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+        key[j] = (int64_t)j * n + j; idx[j] = j;
+        for (int p = Hc[j]; p < Hc[j + 1]; ++p) {
+            const int r = Hr[p];
+            if (r < j || r >= n) atomicExch(bad, 1);
+            key[n + p] = (int64_t)j * n + r; idx[n + p] = n + p;
+        }
+    }
+}
+__global__ void k_fill_pairs(int n, int m, int64_t base, const int32_t* __restrict__ Jc, const int32_t* __restrict__ Jr,
+                             const int32_t* __restrict__ poff, int64_t* __restrict__ key, int32_t* __restrict__ idx, int4* __restrict__ rec,
+                             int* __restrict__ bad) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
+        int q = poff[i];
+        for (int j = Jc[i]; j < Jc[i + 1]; ++j)
+            for (int k = j; k < Jc[i + 1]; ++k, ++q) {
+                const int c1 = Jr[j], c2 = Jr[k];                       // (col, row) of the entry; rows of a Jt column are ascending
+                if (c2 < c1 || c2 >= n || c1 < 0) atomicExch(bad, 1);
+                key[base + q] = (int64_t)c1 * n + c2; idx[base + q] = (int32_t)(base + q);
+                rec[q] = make_int4(i, j, k, 0);
+            }
+    }
+}
+// per sorted position: slot bookkeeping; marks triple entries
+__global__ void k_cond_emit(int64_t tot, int n, int64_t n_hess_end, const int64_t* __restrict__ key, const int32_t* __restrict__ idx,
+                            const int32_t* __restrict__ head, const int32_t* __restrict__ scan, int32_t* __restrict__ rowval,
+                            int32_t* __restrict__ colcnt, int32_t* __restrict__ hsrc, int32_t* __restrict__ dsrc, int32_t* __restrict__ is_trip,
+                            int* __restrict__ bad) {
+    for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < tot; s += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t slot = scan[s] - 1, t = idx[s];
+        if (head[s]) { rowval[slot] = (int32_t)(key[s] % n); atomicAdd(colcnt + (int32_t)(key[s] / n) + 1, 1); }
+        int trip = 0;
+        if (t < n) dsrc[slot] = t;
+        else if (t < n_hess_end) { if (atomicExch(hsrc + slot, t - n) != -1) atomicExch(bad, 2); }      // duplicate entry in H
+        else trip = 1;
+        is_trip[s] = trip;
+    }
+}
+__global__ void k_cond_trip(int64_t tot, int64_t base, const int32_t* __restrict__ idx, const int32_t* __restrict__ head, const int32_t* __restrict__ scan,
+                            const int32_t* __restrict__ is_trip, const int32_t* __restrict__ texcl, const int4* __restrict__ rec,
+                            int32_t* __restrict__ tptr, int4* __restrict__ trip) {
+    for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < tot; s += (int64_t)gridDim.x * blockDim.x) {
+        if (head[s]) tptr[scan[s] - 1] = texcl[s];
+        if (is_trip[s]) trip[texcl[s]] = rec[idx[s] - base];
+    }
+}
+}  // namespace
+
+extern "C" int b2_condensed_symbolic_device(int32_t n, int32_t m, const int32_t* H_colptr_d, const int32_t* H_rowval_d,
+                                            const int32_t* Jt_colptr_d, const int32_t* Jt_rowval_d, b2_condensed_plan** out,
+                                            int64_t* nnz_aug, void* stream) {
+    if (!out || n <= 0 || m < 0 || !H_colptr_d || !Jt_colptr_d) { set_error("b2_condensed_symbolic_device: invalid argument"); return B2_ERR_INVALID; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); set_error("b2_condensed_symbolic_device: no CUDA device"); return B2_ERR_NO_DEVICE; }
+    cudaStream_t st = as_stream(stream);
+    const int grid_m = std::max(1, std::min((m + 255) / 256, 8 * sm_count())), grid_n = std::max(1, std::min((n + 255) / 256, 8 * sm_count()));
+    DevBuf<int32_t> cnt, poff, bad;
+    if (cnt.alloc(m + 1) != cudaSuccess || poff.alloc(m + 1) != cudaSuccess || bad.alloc(1) != cudaSuccess)
+        return cuda_fail(cudaGetLastError(), "condensed symbolic alloc", __FILE__, __LINE__);
+    B2_CUDA(cudaMemsetAsync(bad.p, 0, sizeof(int32_t), st));
+    B2_CUDA(cudaMemsetAsync(cnt.p, 0, (size_t)(m + 1) * sizeof(int32_t), st));
+    if (m > 0) k_pair_counts<<<grid_m, 256, 0, st>>>(m, Jt_colptr_d, cnt.p);
+    size_t tb = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, cnt.p, poff.p, m + 1, st);
+    DevBuf<unsigned char> tmp0;
+    if (tmp0.alloc(std::max<size_t>(tb, 16)) != cudaSuccess) return cuda_fail(cudaGetLastError(), "condensed symbolic temp", __FILE__, __LINE__);
+    B2_CUDA(cub::DeviceScan::ExclusiveSum(tmp0.p, tb, cnt.p, poff.p, m + 1, st));
+    int32_t nnzH = 0, nj = 0;
+    B2_CUDA(cudaMemcpyAsync(&nnzH, H_colptr_d + n, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    B2_CUDA(cudaMemcpyAsync(&nj, poff.p + m, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    B2_CUDA(cudaStreamSynchronize(st));
+    const int64_t base = (int64_t)n + nnzH, tot = base + nj;
+    if (tot > INT32_MAX) { set_error("b2_condensed_symbolic_device: too many entries"); return B2_ERR_INVALID; }
+    DevBuf<int64_t> key, key2;
+    DevBuf<int32_t> idx, idx2, head, scan, is_trip, texcl, colcnt, rowval;
+    DevBuf<int4> rec;
+    auto* p = new b2_condensed_plan();
+    p->n = n; p->m = m;
+    const int grid_t = (int)std::max<int64_t>(1, std::min<int64_t>((tot + 255) / 256, 8 * sm_count()));
+    if (key.alloc(tot) != cudaSuccess || key2.alloc(tot) != cudaSuccess || idx.alloc(tot) != cudaSuccess || idx2.alloc(tot) != cudaSuccess ||
+        head.alloc(tot) != cudaSuccess || scan.alloc(tot) != cudaSuccess || is_trip.alloc(tot) != cudaSuccess || texcl.alloc(tot) != cudaSuccess ||
+        colcnt.alloc(n + 1) != cudaSuccess || rowval.alloc(tot) != cudaSuccess || rec.alloc(std::max(nj, 1)) != cudaSuccess) {
+        delete p;
+        return cuda_fail(cudaGetLastError(), "condensed symbolic alloc", __FILE__, __LINE__);
+    }
+    k_fill_diag_hess<<<grid_n, 256, 0, st>>>(n, H_colptr_d, H_rowval_d, key.p, idx.p, bad.p);
+    if (m > 0 && nj > 0) k_fill_pairs<<<grid_m, 256, 0, st>>>(n, m, base, Jt_colptr_d, Jt_rowval_d, poff.p, key.p, idx.p, rec.p, bad.p);
+    int end_bit = 1;
+    while (end_bit < 63 && ((int64_t)1 << end_bit) <= (int64_t)n * n) ++end_bit;
+    size_t t1 = 0, t2 = 0, t3 = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, t1, key.p, key2.p, idx.p, idx2.p, (int)tot, 0, end_bit, st);
+    cub::DeviceScan::InclusiveSum(nullptr, t2, head.p, scan.p, (int)tot, st);
+    cub::DeviceScan::InclusiveSum(nullptr, t3, colcnt.p, colcnt.p, n + 1, st);
+    DevBuf<unsigned char> tmp;
+    if (tmp.alloc(std::max(std::max(t1, t2), std::max(t3, (size_t)16))) != cudaSuccess) { delete p; return cuda_fail(cudaGetLastError(), "condensed symbolic temp", __FILE__, __LINE__); }
+    size_t tsz = tmp.bytes();
+    B2_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tsz, key.p, key2.p, idx.p, idx2.p, (int)tot, 0, end_bit, st));
+    k_heads<<<grid_t, 256, 0, st>>>(tot, key2.p, head.p);
+    tsz = tmp.bytes();
+    B2_CUDA(cub::DeviceScan::InclusiveSum(tmp.p, tsz, head.p, scan.p, (int)tot, st));
+    int32_t nslot = 0;
+    B2_CUDA(cudaMemcpyAsync(&nslot, scan.p + (tot - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    B2_CUDA(cudaStreamSynchronize(st));
+    if (p->hsrc.alloc(nslot) != cudaSuccess || p->dsrc.alloc(nslot) != cudaSuccess || p->tptr.alloc((size_t)nslot + 1) != cudaSuccess ||
+        p->trip.alloc(std::max(nj, 1)) != cudaSuccess) { delete p; return cuda_fail(cudaGetLastError(), "condensed plan alloc", __FILE__, __LINE__); }
+    B2_CUDA(cudaMemsetAsync(p->hsrc.p, 0xFF, (size_t)nslot * sizeof(int32_t), st));
+    B2_CUDA(cudaMemsetAsync(p->dsrc.p, 0xFF, (size_t)nslot * sizeof(int32_t), st));
+    B2_CUDA(cudaMemsetAsync(colcnt.p, 0, (size_t)(n + 1) * sizeof(int32_t), st));
+    B2_CUDA(cudaMemsetAsync(p->trip.p, 0, sizeof(int4), st));
+    k_cond_emit<<<grid_t, 256, 0, st>>>(tot, n, base, key2.p, idx2.p, head.p, scan.p, rowval.p, colcnt.p, p->hsrc.p, p->dsrc.p, is_trip.p, bad.p);
+    tsz = tmp.bytes();
+    B2_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tsz, is_trip.p, texcl.p, (int)tot, st));
+    k_cond_trip<<<grid_t, 256, 0, st>>>(tot, base, idx2.p, head.p, scan.p, is_trip.p, texcl.p, rec.p, p->tptr.p, p->trip.p);
+    B2_CUDA(cudaMemcpyAsync(p->tptr.p + nslot, &nj, sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    tsz = tmp.bytes();
+    B2_CUDA(cub::DeviceScan::InclusiveSum(tmp.p, tsz, colcnt.p, colcnt.p, n + 1, st));
+    p->colptr.resize(n + 1); p->rowval.resize(nslot);
+    int32_t h_bad = 0;
+    B2_CUDA(cudaMemcpyAsync(p->colptr.data(), colcnt.p, (size_t)(n + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    B2_CUDA(cudaMemcpyAsync(p->rowval.data(), rowval.p, (size_t)nslot * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    B2_CUDA(cudaMemcpyAsync(&h_bad, bad.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    B2_CUDA(cudaStreamSynchronize(st));
+    if (h_bad) {
+        delete p;
+        set_error(h_bad == 2 ? "b2_condensed_symbolic_device: duplicate entry in H" : "b2_condensed_symbolic_device: entry above the diagonal (H must be lower, Jt rows sorted)");
+        return B2_ERR_INVALID;
+    }
+    p->nnz_aug = nslot; p->n_dptr = n; p->n_hptr = nnzH; p->n_jptr = nj;
+    *out = p;
+    if (nnz_aug) *nnz_aug = nslot;
+    return B2_OK;
+}

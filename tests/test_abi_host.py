@@ -168,3 +168,28 @@ def test_coo_to_csc_random(m, n, nnz, seed):
     capi.check(lib.b2_coo_to_csc(m, n, nnz, I32.ctypes.data if nnz else None, J32.ctypes.data if nnz else None,
                                  cp.ctypes.data, rv.ctypes.data, mp.ctypes.data, C.byref(k)))
     assert k.value == len(rv0) and (cp == cp0).all() and (rv[:k.value] == rv0).all() and (mp[:nnz] == mp0).all()
+
+
+def test_reference_arm_runs_without_the_product_library():
+    """bench.py --impl reference: one JSON line with the contract's keys, the requested --steps/--warmup, the same `config` dict the
+    B200 arm prints, and NO import of the product package (whose __init__ loads libb200kkt.so) -- VERDICT r1 'fix the import so
+    the record is clean'."""
+    import json, os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import sys, json; sys.argv = ['bench.py', '--impl', 'reference', '--steps', '3', '--warmup', '1', '--workload', 'case300_synth'];"
+            "import bench; bench.main();"
+            "bad = [m for m in sys.modules if m.startswith('madnlp_jl_b200') or m.startswith('madnlp.jl_b200')];"
+            "print(json.dumps({'loaded_product_modules': bad}))")
+    out = subprocess.run([sys.executable, "-c", code], cwd=root, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    line, probe = json.loads(lines[0]), json.loads(lines[-1])
+    assert probe["loaded_product_modules"] == []
+    assert line["impl"] == "reference" and line["steps"] == 3 and line["warmup"] == 1 and line["metric"] == "ipm_iters_per_sec"
+    for key in ("value", "unit", "n_gpus", "ms_per_step", "higher_is_better", "scaling", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in line, key
+    assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
+    import bench
+    class A: workload = "case300_synth"; no_flush = False
+    class S: nvar = line["config"]["n"]; ncon = line["config"]["m"]
+    assert line["config"] == bench.config_of(A, S, 1)
