@@ -83,9 +83,11 @@ struct AlphaMax {
     const double *x, *xl, *xu, *dx; double tau;
     __device__ double term(int64_t i) const {
         const double d = dx[i];
-        const double a = d < 0.0 ? (-x[i] + xl[i]) * tau / d : dinf();
-        const double c = d > 0.0 ? (-x[i] + xu[i]) * tau / d : dinf();
-        return comb<R_MIN>(a, c);
+        // one of the two reference terms is +Inf for every sign of d, so only the taken one is evaluated: ONE fp64
+        // division per element, and only the bound on the side d points to is read
+        if (d == 0.0 || d != d) return dinf();
+        const double bnd = d < 0.0 ? xl[i] : xu[i];
+        return (-x[i] + bnd) * tau / d;
     }
     __device__ double finish(double r) const { return r; }
 };

@@ -52,6 +52,28 @@ def coo_to_csc(I, J, m, n):
     return colptr, rowval[:ncsc.value].copy(), cmap[:nnz].copy()
 
 
+def coo_to_csc_device(I, J, m, n):
+    """The same construction with device sorts (lib/MadNLPGPU/src/KKT/gpu_sparse.jl:260-302) via b2_coo_to_csc_device; returns host
+    copies of (colptr, rowval, map) -- identical to coo_to_csc's (tests/test_gpu_symbolic.py)."""
+    nnz = len(I)
+    Id = torch.from_numpy(np.ascontiguousarray(I, dtype=np.int32)).to(_DEV)
+    Jd = torch.from_numpy(np.ascontiguousarray(J, dtype=np.int32)).to(_DEV)
+    colptr = torch.zeros(n + 1, dtype=torch.int32, device=_DEV)
+    rowval = torch.zeros(max(nnz, 1), dtype=torch.int32, device=_DEV)
+    cmap = torch.zeros(max(nnz, 1), dtype=torch.int64, device=_DEV)
+    ncsc = C.c_int64(0)
+    check(lib.b2_coo_to_csc_device(m, n, nnz, ptr(Id) if nnz else None, ptr(Jd) if nnz else None, ptr(colptr), ptr(rowval), ptr(cmap),
+                                   C.byref(ncsc), _sp()))
+    return colptr.cpu().numpy(), rowval.cpu().numpy()[:ncsc.value].copy(), cmap.cpu().numpy()[:nnz].copy()
+
+
+def _symbolic_on_device():
+    """B2_DEVICE_SYMBOLIC=1: build the COO->CSC maps and the condensed pattern/maps with device sorts, like the
+    reference's GPU path; default: the host constructions (identical results)."""
+    import os
+    return os.environ.get("B2_DEVICE_SYMBOLIC") == "1"
+
+
 class _Plan:
     """owns a native plan handle and frees it"""
 
@@ -297,6 +319,8 @@ class SparseCondensedKKTSystem(_KKTBase):
         self._init_common(cb, n + ns, m)
         self.buffer = _dz(m); self.buffer2 = _dz(m); self.diag_buffer = _dz(m)
         self.hess = _dz(len(hI)); self.jac = _dz(len(jI))
+        dev_sym = _symbolic_on_device()
+        coo_to_csc = coo_to_csc_device if dev_sym else globals()["coo_to_csc"]
         cp, rv, mp = coo_to_csc(jJ, jI, n, m)                        # jt_coo: I = jac_J, J = jac_I (condensed.jl:105-110)
         self.jt_csc = DeviceCSC(n, m, cp, rv, _dz(len(rv)))
         self._jt_plan = _transfer_plan(mp, len(rv))
@@ -306,8 +330,13 @@ class SparseCondensedKKTSystem(_KKTBase):
         self._hess_plan = _transfer_plan(hmp, len(hrv))
         self._hess_spmv = _spmv_plan(n, n, hcp, hrv)
         h = C.c_void_p(); nnz_aug = C.c_int64(0)
-        check(lib.b2_condensed_symbolic(n, m, hcp.ctypes.data, hrv.ctypes.data if len(hrv) else None, cp.ctypes.data,
-                                        rv.ctypes.data if len(rv) else None, C.byref(h), C.byref(nnz_aug)))
+        if dev_sym:
+            d32 = lambda a: torch.from_numpy(np.ascontiguousarray(a if len(a) else np.zeros(1), dtype=np.int32)).to(_DEV)
+            pats = [d32(hcp), d32(hrv), d32(cp), d32(rv)]
+            check(lib.b2_condensed_symbolic_device(n, m, ptr(pats[0]), ptr(pats[1]), ptr(pats[2]), ptr(pats[3]), C.byref(h), C.byref(nnz_aug), _sp()))
+        else:
+            check(lib.b2_condensed_symbolic(n, m, hcp.ctypes.data, hrv.ctypes.data if len(hrv) else None, cp.ctypes.data,
+                                            rv.ctypes.data if len(rv) else None, C.byref(h), C.byref(nnz_aug)))
         self._cond = _Plan(h, lib.b2_condensed_plan_destroy)
         acp = np.zeros(n + 1, dtype=np.int32); arv = np.zeros(nnz_aug.value, dtype=np.int32)
         check(lib.b2_condensed_pattern(h, acp.ctypes.data, arv.ctypes.data))

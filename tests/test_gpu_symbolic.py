@@ -106,3 +106,25 @@ def test_device_condensed_symbolic_equals_host_plan(case):
         assert torch.equal(out, ref)
     finally:
         lib.b2_condensed_plan_destroy(h)
+
+
+def test_kkt_system_built_with_device_symbolic_is_identical(monkeypatch):
+    """the host mirror with B2_DEVICE_SYMBOLIC=1 (all sorts on the device, like MadNLPGPU) == the default host constructions"""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from madnlp_jl_b200 import kkt as K
+    W = pkg.workloads
+    model, st = W.acopf_case("case300_synth")
+    cb = o.Callback(st.nvar, st.ncon, st.jac_I, st.jac_J, st.hess_I, st.hess_J, st.ind_ineq, st.ind_lb, st.ind_ub)
+    it = W.ipm_iterates(model, st, 1, seed=4)[0]
+    outs = []
+    for flag in ("0", "1"):
+        monkeypatch.setenv("B2_DEVICE_SYMBOLIC", flag)
+        kg = K.SparseCondensedKKTSystem(cb); kg.initialize()
+        for k, v in ((kg.get_jacobian(), it.jac), (kg.get_hessian(), it.hess), (kg.reg, it.reg + 1e-8), (kg.du_diag, it.du_diag - 1e-7),
+                     (kg.l_diag, it.l_diag), (kg.u_diag, it.u_diag), (kg.l_lower, it.l_lower), (kg.u_lower, it.u_lower)):
+            k.copy_(torch.from_numpy(np.ascontiguousarray(v)).cuda())
+        kg.compress_jacobian(); kg.compress_hessian(); kg.set_aug_diagonal_(); kg.build_kkt()
+        outs.append((kg.aug_com.colptr.copy(), kg.aug_com.rowval.copy(), kg.aug_com.nzval.cpu().numpy(), kg.jt_csc.nzval.cpu().numpy()))
+    for a, b in zip(outs[0], outs[1]):
+        assert (a == b).all()
