@@ -57,8 +57,23 @@ __device__ __forceinline__ void team_sync(int team) {
     else asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "r"(NW * 32) : "memory");
 }
 
+// Split team barrier of the pivot loop (front_factor_team): every warp ARRIVES on its own named barrier and WAITS on its
+// partner's, ids alternating with the pivot parity -- bar.arrive + bar.sync by disjoint warps, 64 threads per barrier.  A warp
+// can only arrive for pivot k+2 after its partner has left the wait of pivot k, so two ids per warp are enough.
+// ids: 1..2 = team_sync; 3 + team*4 + warp*2 + parity (<= 10 of the 16 hardware barriers).
+template <int NW>
+__device__ __forceinline__ void team_arrive(int team, int warp, int parity) {
+    static_assert(NW <= 2, "split barrier is written for one- and two-warp teams");
+    if (NW == 2) asm volatile("bar.arrive %0, 64;" ::"r"(3 + team * 4 + warp * 2 + parity) : "memory");
+}
+template <int NW>
+__device__ __forceinline__ void team_wait(int team, int warp, int parity) {
+    if (NW == 1) __syncwarp();
+    else asm volatile("bar.sync %0, 64;" ::"r"(3 + team * 4 + (warp ^ 1) * 2 + parity) : "memory");
+}
+
 // shared-memory slice of one team:
-//   F[maxf*maxf] assembly area, later the finished panel | colbuf[2][2*FMAX] | rel[MAXC][FMAX] ints | recs[MAXC] |
+//   F[maxf*maxf] assembly area, later the finished panel | colbuf[4][FMAX+4] | rel[MAXC][FMAX] ints | recs[MAXC] |
 //   stage[STAGE] children's update blocks landed by cp.async
 constexpr int MAXC = 8;                                // children staged per round
 template <int NW>
@@ -67,7 +82,7 @@ struct TeamSmem {
     static constexpr int STAGE = (NW == 1) ? 1024 : 4096;   // doubles; one child always fits (rc^2 <= (FMAX-1)^2)
     static __host__ __device__ int fsize(int maxf) { return (maxf * maxf + 1) & ~1; }   // keeps `stage` 16-byte aligned
     static __host__ __device__ int doubles(int maxf) {
-        return fsize(maxf) + 4 * FMAX + (MAXC * FMAX) / 2 + MAXC * 4 + STAGE;
+        return fsize(maxf) + 4 * (FMAX + 4) + (MAXC * FMAX) / 2 + MAXC * 4 + STAGE;
     }
 };
 
@@ -99,14 +114,76 @@ __device__ __forceinline__ void flag_set(int* flag) {
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
+// One pivot of front_factor_team's software-pipelined loop, for a window of NB live 8-column blocks: the latency chain of pivot k
+// (d_k -> reciprocal (approx + 2 Newton steps) -> l_k -> column k+1 -> publish -> arrive) and the pending row update of pivot k-1,
+// as one branch-free block.  The publish is a predicated st.shared + bar.arrive in ONE asm without a memory clobber, so that most
+// of the pending update (which reads the OTHER column buffers) follows the arrive and overlaps the partner warp's barrier latency.
+// The empty volatile asm statements (B2_TIE) keep NVVM from sinking the whole chain below the update; ptxas then issues the six tied
+// FMA pairs under the latency of the d_k load and runs the chain contiguously.  (Measured, profiles/r02_pivot_loop.txt: forcing a
+// finer interleave with real data dependencies -- one LOP3 per link -- costs more issue slots than the latency it hides.)
+struct PivotCtx { const double* cb; const double* pb; double* nb; double* Fk; double eps; int tid, k, f, team; };
+#define B2_TIE(c, x, y) asm volatile("" : "+d"(c), "+d"(x), "+d"(y))
+template <int NW, int P>
+__device__ __forceinline__ void pending_pair(double (&av)[32 * NW + 1], double lp, const double2* up) {
+    const double2 u = up[P];
+    av[2 * P - 1] = fma(-lp, u.x, av[2 * P]);
+    av[2 * P] = fma(-lp, u.y, av[2 * P + 1]);
+}
+template <int NW, int P0, int P1>
+struct PendingRange {
+    static __device__ __forceinline__ void run(double (&av)[32 * NW + 1], double lp, const double2* up) {
+        if constexpr (P0 < P1) { pending_pair<NW, P0>(av, lp, up); PendingRange<NW, P0 + 1, P1>::run(av, lp, up); }
+    }
+};
+template <int NW, int NB>
+__device__ __forceinline__ void pivot_iter(double (&av)[32 * NW + 1], double& lp, const PivotCtx& c, int& nneg, int& npert) {
+    constexpr int NP = 4 * NB;                          // pending pairs 1 .. NP-1 (pair 0 is column k+1, handled with the chain)
+    double dk = c.cb[1];
+    const double u0 = c.cb[2];
+    const double2* up = reinterpret_cast<const double2*>(c.pb + 2);
+    const bool tiny = !(fabs(dk) >= c.eps), neg = dk < 0.0;
+    dk = tiny ? (neg ? -c.eps : c.eps) : dk;
+    npert += (c.tid == 0 && tiny) ? 1 : 0;
+    nneg += (c.tid == 0 && !tiny && neg) ? 1 : 0;
+    double a1 = fma(-lp, up[0].y, av[1]);               // column k+1 with pivot k-1 applied
+    double r, e;
+    asm volatile("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(dk));
+    if constexpr (NP > 1) { pending_pair<NW, 1>(av, lp, up); B2_TIE(r, av[1], av[2]); }
+    e = fma(-dk, r, 1.0);
+    if constexpr (NP > 2) { pending_pair<NW, 2>(av, lp, up); B2_TIE(e, av[3], av[4]); }
+    r = fma(r, e, r);
+    if constexpr (NP > 3) { pending_pair<NW, 3>(av, lp, up); B2_TIE(r, av[5], av[6]); }
+    e = fma(-dk, r, 1.0);
+    if constexpr (NP > 4) { pending_pair<NW, 4>(av, lp, up); B2_TIE(e, av[7], av[8]); }
+    r = fma(r, e, r);
+    if constexpr (NP > 5) { pending_pair<NW, 5>(av, lp, up); B2_TIE(r, av[9], av[10]); }
+    double l = av[0] * r;
+    if constexpr (NP > 6) { pending_pair<NW, 6>(av, lp, up); B2_TIE(l, av[11], av[12]); }
+    // column k+1 with pivot k applied -- the value the next pivot waits for (junk, unused, when k+1 = f)
+    double nx = fma(-l, u0, a1);
+    double* dst = c.nb + (c.tid - c.k);                // row tid of column k+1 at nb[tid - (k+1) + 1]
+    if (NW == 1) {
+        if (c.tid > c.k) *dst = nx;
+    } else {
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.gt.s32 p, %2, %3;\n\t@p st.shared.f64 [%0], %1;\n\tbar.arrive %4, 64;\n\t}"
+                     ::"r"((unsigned)__cvta_generic_to_shared(dst)), "d"(nx), "r"(c.tid), "r"(c.k),
+                       "r"(3 + c.team * 4 + (c.tid >> 5) * 2 + ((c.k + 1) & 1)));
+    }
+    if (c.tid < c.f) c.Fk[c.tid] = (c.tid == c.k) ? dk : l;   // finished column k of the panel (rows < k: scratch)
+    av[0] = nx;
+    PendingRange<NW, 7, NP>::run(av, lp, up);
+    lp = l;
+}
+
 template <int NW, bool DEP = false>
 __device__ __forceinline__ void front_factor_team(const FactorArgs& a, const ChildRec* childrec, int s, double* sm_team,
                                                   int tid, int team, int maxf, int& nneg, int& npert, long long* prof = nullptr,
                                                   int* done = nullptr, int* err = nullptr) {
     constexpr int FMAX = 32 * NW, TEAM = 32 * NW, STAGE = TeamSmem<NW>::STAGE;
     double* F = sm_team;
-    double* colbuf = F + TeamSmem<NW>::fsize(maxf);    // [2][2*FMAX]
-    int* relst = (int*)(colbuf + 4 * FMAX);            // [MAXC][FMAX]
+    constexpr int CBS = FMAX + 4;                      // four pivot-column buffers
+    double* colbuf = F + TeamSmem<NW>::fsize(maxf);    // [4][CBS]
+    int* relst = (int*)(colbuf + 4 * CBS);             // [MAXC][FMAX]
     ChildRec* recs = (ChildRec*)(relst + MAXC * FMAX); // [MAXC]
     double* stage = (double*)(recs + MAXC);            // [STAGE]
     B2_STAMP(0);
@@ -114,7 +191,7 @@ __device__ __forceinline__ void front_factor_team(const FactorArgs& a, const Chi
     const int f = d.f, w = d.w, r = f - w;
     B2_STAMP(1);
     for (int i = tid; i < f * f; i += TEAM) F[i] = 0.0;
-    for (int i = tid; i < 4 * FMAX; i += TEAM) colbuf[i] = 0.0;
+    for (int i = tid; i < 4 * CBS; i += TEAM) colbuf[i] = 0.0;
     team_sync<NW>(team);
     B2_STAMP(2);
     {   // original matrix entries: panel layout pos + col*f == assembly-area layout
@@ -191,28 +268,54 @@ __device__ __forceinline__ void front_factor_team(const FactorArgs& a, const Chi
 #pragma unroll
     for (int j = 0; j < FMAX; ++j) av[j] = (j < f && tid < f) ? F[tid + j * f] : 0.0;
     av[FMAX] = 0.0;
-    // pivot k: the (unscaled) pivot column is published WINDOW-RELATIVE -- cb[1] = d_k, cb[2 + j] = u(k+1+j) -- so that the
-    // register window av[j] <-> column k+1+j lines up with 16-byte pairs whatever the parity of k: one LDS.128 feeds two
-    // FMAs (shared-memory issue, not the FP64 pipe, bounds a lone warp: tools/microbench/fp64_pipes.cu)
+    // Pivot loop, software-pipelined by one pivot.  The pivot column is published WINDOW-RELATIVE in one of four buffers --
+    // cb[1] = d_k, cb[2 + j] = u(k+1+j) -- so that the register window lines up with 16-byte pairs whatever the parity of k: one
+    // LDS.128 feeds two FMAs (shared-memory issue, not the FP64 pipe, bounds a lone warp: tools/microbench/fp64_pipes.cu).
+    // A pivot has a latency chain (barrier -> d_k -> reciprocal -> l_k -> the one FMA that makes column k+1 -> publish) and a
+    // throughput part (the other f-k-2 FMAs of the row).  Iteration k runs the chain of pivot k TOGETHER with the throughput
+    // part of pivot k-1 (`pending`: multiplier lp, buffer pb), as straight-line code per number of live 8-column blocks so that
+    // ptxas interleaves the two; the team barrier is split (arrive after the publish, wait at the top of the next iteration).
+    // Every element still receives the pivots' updates in ascending order, one fma each: bit-identical to the plain loop.
+    //   top of iteration k:  av[0] = column k (final), av[j] = column k+j with pivot k-1's update pending (j >= 1)
+    //   four buffers: a warp past wait(k) reads (k-1)%4 and k%4 and writes (k+1)%4; its partner, at most one pivot ahead (it has
+    //   this warp's arrive(k+1) but not arrive(k+2)), writes (k+2)%4.
+    colbuf[tid + 1] = av[0];                           // column 0
+    team_arrive<NW>(team, tid >> 5, 0);
+    double lp = 0.0;                                   // multiplier of the pending pivot (none yet: the pass only shifts)
+    int kb = 0, pbi = 3;
     for (int k = 0; k < w; ++k) {
-        double* cb = colbuf + (k & 1) * 2 * FMAX;
-        if (tid >= k) cb[tid - k + 1] = av[0];
-        team_sync<NW>(team);
-        double dk = cb[1];
-        if (!(fabs(dk) >= a.eps)) { dk = (dk < 0.0) ? -a.eps : a.eps; if (tid == 0) ++npert; }
-        else if (dk < 0.0 && tid == 0) ++nneg;
-        const double dinv = fast_rcp(dk);
-        const double l = av[0] * dinv;
-        if (tid < f) F[tid + k * f] = (tid == k) ? dk : l;    // finished column k of the panel (rows < k: scratch)
-        const double2* ub = reinterpret_cast<const double2*>(cb + 2);
+        const double* cb = colbuf + kb * CBS;
+        const double* pb = colbuf + pbi * CBS;
+        pbi = kb;
+        kb = (kb + 1) & 3;
+        double* nb = colbuf + kb * CBS;
+        double* Fk = F + k * f;
+        const int nblk = (f - k + 7) >> 3;              // live 8-column blocks of the window (team-uniform, >= 1)
+        team_wait<NW>(team, tid >> 5, k & 1);
+        PivotCtx c{cb, pb, nb, Fk, a.eps, tid, k, f, team};
+        switch (nblk) {
+            case 1: pivot_iter<NW, 1>(av, lp, c, nneg, npert); break;
+            case 2: pivot_iter<NW, 2>(av, lp, c, nneg, npert); break;
+            case 3: pivot_iter<NW, 3>(av, lp, c, nneg, npert); break;
+            case 4: pivot_iter<NW, 4>(av, lp, c, nneg, npert); break;
+            case 5: pivot_iter<NW, (NW > 1 ? 5 : 4)>(av, lp, c, nneg, npert); break;
+            case 6: pivot_iter<NW, (NW > 1 ? 6 : 4)>(av, lp, c, nneg, npert); break;
+            case 7: pivot_iter<NW, (NW > 1 ? 7 : 4)>(av, lp, c, nneg, npert); break;
+            default: pivot_iter<NW, (NW > 1 ? 8 : 4)>(av, lp, c, nneg, npert); break;
+        }
+    }
+    team_wait<NW>(team, tid >> 5, w & 1);              // pairs with the last iteration's (unconditional) arrive
+    {   // the last pivot's pending update (no shift): av[j] = column w+j, j >= 1; av[0] = column w is final
+        const double2* up = reinterpret_cast<const double2*>(colbuf + pbi * CBS + 2);
+        av[1] = fma(-lp, up[0].y, av[1]);
 #pragma unroll
         for (int j0 = 0; j0 < FMAX; j0 += 8) {
-            if (k + 1 + j0 < f) {                       // team-uniform
+            if (w + j0 < f) {
 #pragma unroll
-                for (int j = j0; j < j0 + 8; j += 2) {
-                    const double2 u = ub[j >> 1];
-                    av[j] = fma(-l, u.x, av[j + 1]);
-                    av[j + 1] = fma(-l, u.y, av[j + 2]);
+                for (int j = (j0 ? j0 : 2); j < j0 + 8; j += 2) {
+                    const double2 u = up[j >> 1];
+                    av[j] = fma(-lp, u.x, av[j]);
+                    av[j + 1] = fma(-lp, u.y, av[j + 1]);
                 }
             }
         }
