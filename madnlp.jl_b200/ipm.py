@@ -186,3 +186,77 @@ class IPMLinearAlgebra:
             self.del_w_last = del_w
         self.last_inertia = inertia
         return True
+
+class HostIteratePipeline:
+    """Double-buffered host<->device staging around `IPMLinearAlgebra.step` (the role of SparseWrapperModel's pinned buffers,
+    lib/MadNLPGPU/src/wrappers.jl:173-196, made asynchronous): while step i computes, a copy stream moves the callback outputs of
+    iterate i+1 from PINNED host memory into the idle one of two device staging sets, and a second copy stream returns step i-1's
+    direction to pinned host memory (the two DMA directions run concurrently).  `load()` then moves the staged iterate into the KKT
+    buffers with ONE device-to-device launch (`b2_copy_many`).  Every byte still crosses PCIe once per step; only the waiting is
+    hidden.  Events order all buffer reuse, so the caller never synchronises for the copies (`drain()` at the end of a run)."""
+
+    def __init__(self, la, fields):
+        k = la.kkt
+        self.la = la
+        self.fields = tuple(fields)
+        self._dst = dict(jac=k.get_jacobian(), hess=k.get_hessian(), reg=k.reg, du_diag=k.du_diag, l_diag=k.l_diag,
+                         u_diag=k.u_diag, l_lower=k.l_lower, u_lower=k.u_lower, rhs=la.p.values)
+        dev = la.d.values.device
+        self.stage = [{f: torch.empty_like(self._dst[f]) for f in self.fields} for _ in range(2)]
+        self.d_stage = [torch.empty_like(la.d.values) for _ in range(2)]
+        self.d_host = [torch.zeros(la.d.values.numel(), dtype=torch.float64).pin_memory() for _ in range(2)]
+        self.h2d = torch.cuda.Stream(device=dev)
+        self.d2h = torch.cuda.Stream(device=dev)
+        self.ev_staged = [torch.cuda.Event() for _ in range(2)]      # H2D of the slot complete
+        self.ev_consumed = [torch.cuda.Event() for _ in range(2)]    # the D2D out of the slot complete (slot may be refilled)
+        self.ev_d_ready = [torch.cuda.Event() for _ in range(2)]     # d copied into d_stage[slot]
+        self.ev_d_out = [torch.cuda.Event() for _ in range(2)]       # d_stage[slot] is in host memory (slot may be rewritten)
+        self.h2d_bytes = sum(self._dst[f].numel() * 8 for f in self.fields)
+        self.d2h_bytes = la.d.values.numel() * 8
+        self._n_pref = 0
+        self._n_out = 0
+
+    def prefetch(self, host_iterate):
+        """queue the H2D of one iterate (pinned host tensors) into the next staging slot; returns the slot"""
+        slot = self._n_pref & 1
+        if self._n_pref >= 2:
+            self.h2d.wait_event(self.ev_consumed[slot])
+        with torch.cuda.stream(self.h2d):
+            for f in self.fields:
+                self.stage[slot][f].copy_(host_iterate[f], non_blocking=True)
+            self.ev_staged[slot].record(self.h2d)
+        self._n_pref += 1
+        return slot
+
+    def load(self, slot):
+        """compute stream: wait for the slot, move it into the KKT buffers (one launch)"""
+        main = torch.cuda.current_stream()
+        main.wait_event(self.ev_staged[slot])
+        self.la.load_iterate(self.stage[slot])
+        self.ev_consumed[slot].record(main)
+
+    def push_result(self):
+        """queue the D2H of the step direction `d` behind the step just issued; returns the index of the pinned host buffer"""
+        import ctypes as C
+        from .capi import lib, check, stream_ptr
+        slot = self._n_out & 1
+        main = torch.cuda.current_stream()
+        if self._n_out >= 2:
+            main.wait_event(self.ev_d_out[slot])
+        d = self.la.d.values
+        src = (C.c_void_p * 1)(d.data_ptr()); dst = (C.c_void_p * 1)(self.d_stage[slot].data_ptr()); ns = (C.c_int64 * 1)(d.numel())
+        check(lib.b2_copy_many(1, src, dst, ns, stream_ptr(getattr(self.la.kkt, "stream", None))))
+        self.ev_d_ready[slot].record(main)
+        self.d2h.wait_event(self.ev_d_ready[slot])
+        with torch.cuda.stream(self.d2h):
+            self.d_host[slot].copy_(self.d_stage[slot], non_blocking=True)
+            self.ev_d_out[slot].record(self.d2h)
+        self._n_out += 1
+        return slot
+
+    def drain(self):
+        """compute stream waits for every queued result copy (call before the closing event of a timed region)"""
+        main = torch.cuda.current_stream()
+        for slot in range(min(2, self._n_out)):
+            main.wait_event(self.ev_d_out[slot])
+

@@ -340,6 +340,45 @@ def test_ipm_replay_regularises_like_the_reference():
         assert kg.is_inertia_correct(*la.last_inertia)
 
 
+def test_host_pipeline_returns_the_same_directions_as_serial_steps():
+    """ipm.HostIteratePipeline (double-buffered H2D of iterate i+1 / D2H of direction i-1 on copy streams, the asynchronous
+    form of SparseWrapperModel's pinned staging, lib/MadNLPGPU/src/wrappers.jl:173-196): the directions that arrive in the pinned
+    host buffers must be BIT-identical to the ones of copy -> step -> copy, for every iterate and across slot reuse."""
+    _need_gpu()
+    from madnlp_jl_b200 import kkt as K
+    from madnlp_jl_b200.ipm import IPMLinearAlgebra, HostIteratePipeline
+    fields = ("jac", "hess", "reg", "du_diag", "l_diag", "u_diag", "l_lower", "u_lower", "rhs")
+    model, st = W.acopf_case("case300_synth")
+    its = W.ipm_iterates(model, st, 5, seed=4)
+    host = [{k: torch.from_numpy(np.ascontiguousarray(getattr(it, k))).pin_memory() for k in fields} for it in its]
+    kg = K.SparseCondensedKKTSystem(_cb(st))
+    kg.initialize()
+    la = IPMLinearAlgebra(kg)
+    serial = []
+    for rep in range(2):                                  # second pass: captured graphs replay
+        for i, it in enumerate(its):
+            la.load_iterate_host(host, i)
+            assert la.step(mu=it.mu)
+            if rep:
+                serial.append(la.d.values.cpu().numpy().copy())
+    pipe = HostIteratePipeline(la, fields)
+    assert pipe.h2d_bytes == sum(v.numel() * 8 for v in host[0].values()) and pipe.d2h_bytes == la.d.values.numel() * 8
+    got = []
+    slot = pipe.prefetch(host[0])
+    for i, it in enumerate(its):
+        nxt = pipe.prefetch(host[i + 1]) if i + 1 < len(its) else None
+        pipe.load(slot)
+        assert la.step(mu=it.mu)
+        hs = pipe.push_result()
+        pipe.ev_d_out[hs].synchronize()
+        got.append(pipe.d_host[hs].numpy().copy())
+        slot = nxt
+    pipe.drain()
+    torch.cuda.synchronize()
+    for a, b in zip(got, serial):
+        assert np.array_equal(a, b)
+
+
 def test_golden_fixture_on_device():
     """The committed HS15 fixture (tests/golden/hs15_kkt.json): factor + solve the stored condensed and augmented
     matrices through the C ABI and reproduce the stored solve_kkt vector / inertia."""
