@@ -377,6 +377,14 @@ __global__ void __launch_bounds__(256, 2) k_big_update_pipe(FactorArgs a, const 
     big_update_tile(a, d, kb0, kmax, jlo_rel, jhi_rel, clip_jlo, blockIdx.x, blockIdx.y, gu_sm);
 }
 
+// the same tiles from row block `bx0` on (side branch of the dense look-ahead schedule: the first row block is done by k_near_syrk)
+__global__ void __launch_bounds__(256, 2) k_big_update_rows(FactorArgs a, const int32_t* __restrict__ list, int kb0, int kmax, int jlo_rel,
+                                                            int jhi_rel, int clip_jlo, int bx0) {
+    extern __shared__ __align__(16) double gu_sm[];
+    const FrontDesc d = a.desc[list[blockIdx.z]];
+    big_update_tile(a, d, kb0, kmax, jlo_rel, jhi_rel, clip_jlo, blockIdx.x + bx0, blockIdx.y, gu_sm);
+}
+
 // The same update as a PERSISTENT kernel with a dynamic tile queue, for the look-ahead schedule of the dense factorisation:
 // CTAs that land on the first `n_reserved` SMs exit at once, so those SMs stay free for the next panel's diagonal-block kernel
 // (one CTA that needs a whole SM) while this kernel works through the trailing update on all the others.  Tiles are handed out

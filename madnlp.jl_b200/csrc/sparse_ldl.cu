@@ -97,11 +97,11 @@ void launch_big_step(const FactorArgs& a, const int32_t* lb, int nfronts, int ob
         cudaFuncSetAttribute(k_big_update_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GU_SMEM);
         attr = true;
     }
-    k_big_diag128<<<nfronts, 256, sizeof(Diag128Smem), st>>>(a, lb, ob, Linv, linv_off);
+    k_big_diag128<<<nfronts, 256, sizeof(Diag128Smem), st>>>(a, lb, ob, Linv, linv_off, 1);
     if (nl) ++*nl;
     const int rem = maxf - ob - 1;                  // rows below the first pivot of the block (upper bound over the fronts)
     if (rem <= 0) return;
-    k_big_trsm<<<dim3((rem + TR_ROWS - 1) / TR_ROWS, nfronts), 256, GU_SMEM, st>>>(a, lb, ob, Linv, linv_off);
+    k_big_trsm<<<dim3((rem + TR_ROWS - 1) / TR_ROWS, nfronts), 256, GU_SMEM, st>>>(a, lb, ob, Linv, linv_off, 0);
     k_big_update_pipe<<<dim3((rem + GU_M - 1) / GU_M, (rem + GU_N - 1) / GU_N, nfronts), 256, GU_SMEM, st>>>(a, lb, ob, DB, DB, 1 << 30, 1);
     if (nl) *nl += 2;
 }
@@ -999,7 +999,8 @@ struct b2d_solver {
     DevBuf<double> fact, dvec, linv, side, flow;     // flow: [2][nblk*128] hand-off vectors of the single-launch solve
     DevBuf<int32_t> tilecnt;                         // look-ahead schedule: one dynamic-tile counter per panel step
     cudaStream_t aux_stream = nullptr;               // second branch of the look-ahead schedule (trailing updates)
-    std::vector<cudaEvent_t> ev_chain, ev_bulk;
+    cudaStream_t side_stream = nullptr;              // third branch: rest of the panel (trsm + next block column) beside the next diagonal block
+    std::vector<cudaEvent_t> ev_chain, ev_bulk, ev_diag, ev_near, ev_side;
     DevBuf<int64_t> linv_off;
     DevBuf<FrontDesc> desc;
     DevBuf<int32_t> list, counters;
@@ -1011,7 +1012,11 @@ struct b2d_solver {
         if (g_factor) cudaGraphExecDestroy(g_factor);
         for (auto e : ev_chain) cudaEventDestroy(e);
         for (auto e : ev_bulk) cudaEventDestroy(e);
+        for (auto e : ev_diag) cudaEventDestroy(e);
+        for (auto e : ev_near) cudaEventDestroy(e);
+        for (auto e : ev_side) cudaEventDestroy(e);
         if (aux_stream) cudaStreamDestroy(aux_stream);
+        if (side_stream) cudaStreamDestroy(side_stream);
         if (cap_stream) cudaStreamDestroy(cap_stream);
         if (h_counters) cudaFreeHost(h_counters);
     }
@@ -1024,41 +1029,97 @@ __global__ void k_copy_lower(int N, int lda, const double* __restrict__ A, doubl
         F[(size_t)j * N + i] = A[(size_t)j * lda + i];
 }
 
-// Look-ahead schedule of the dense LDL^T (two stream branches; captured into ONE graph by b2d_factorize):
-//   chain  S1:  D(k) diag block   T(k) rows below   C(k) update of block column k+1 only        D(k+1) ...
-//   bulk   S2:                                      R(k) update of the columns >= k+2 (persistent, dynamic tiles, leaves one SM free)
-// R(k) waits for C(k) (event), C(k+1) waits for R(k): the 60 us single-CTA diagonal-block kernel of panel k+1 (and as much of its
-// trsm as finds room) runs WHILE the trailing update of panel k occupies the other SMs, instead of after it.
+// Look-ahead schedule of the dense LDL^T (three stream branches; captured into ONE graph by b2d_factorize).  Per block column k:
+//   chain S1:  D(k) diagonal block -> N1(k) the 128 x 128 block of L below it (k_near_trsm) -> N2(k) update of the NEXT diagonal block
+//              (k_near_syrk) -> D(k+1) ...                         -- the only kernels on the critical path, each a few SMs wide
+//   side  S3:  T(k) trsm of the rows from block k+2 on (after D(k)) -> C(k) rest of block column k+1 (after N1(k), R(k-1))
+//   bulk  S2:  R(k) update of the columns >= k+2 (after C(k); persistent, dynamic tiles, leaves the reserved SMs to the chain)
+// N1(k+1) waits for C(k), N2(k) and C(k) wait for R(k-1).  While the trailing update is long (first panels) the chain waits for it;
+// once it is short the period is D + N1 + N2 instead of D + whole-panel trsm + whole-column update (round 2 before: 42 + 12 + 8 us).
+// B2_DENSE_NEAR=0 restores that two-branch schedule (T and C on the chain).
 void enqueue_dense_factor_lookahead(b2d_solver* s, cudaStream_t S1) {
     FactorArgs a;
     a.desc = s->desc.p; a.child_idx = nullptr; a.rel = nullptr; a.amap_src = nullptr; a.amap_dst = nullptr;
     a.A = nullptr; a.L = s->fact.p; a.ws = nullptr; a.dvec = s->dvec.p; a.counters = s->counters.p; a.eps = s->opt.pivot_eps;
     const int N = s->N, nb = (N + DB - 1) / DB, nsm = sm_count();
-    cudaStream_t S2 = s->aux_stream;
-    static int n_reserved = -1;        // SMs the trailing update leaves to the chain (diagonal block: 1 CTA; trsm / column update: many)
-    if (n_reserved < 0) { const char* e = getenv("B2_DENSE_RESERVED_SMS"); n_reserved = e ? std::max(1, atoi(e)) : 1; }
+    cudaStream_t S2 = s->aux_stream, S3 = s->side_stream;
+    static int n_reserved = -1;        // SMs the trailing update leaves to the chain (diagonal block: 1 CTA; near-diagonal kernels: 16 / 10 small CTAs)
+    // B2_DENSE_INV_SIDE=1: the diagonal-block kernel stops after writing L11 / D back; the near-diagonal trsm substitutes against L11
+    // (k_near_trsv) and the inverse (needed by the whole-panel trsm and by the solves) is formed by k_big_inv128 on the side branch
+    static int inv_side = -1;
+    if (inv_side < 0) { const char* e = getenv("B2_DENSE_INV_SIDE"); inv_side = e ? (atoi(e) != 0) : 0; }
+    if (n_reserved < 0) { const char* e = getenv("B2_DENSE_RESERVED_SMS"); n_reserved = e ? std::max(1, atoi(e)) : (inv_side ? 2 : 1); }
+    static int use_near = -1;
+    if (use_near < 0) { const char* e = getenv("B2_DENSE_NEAR"); use_near = e ? (atoi(e) != 0) : 1; }
+    // chain kernels launched programmatically dependent on their stream predecessor (launch latency of D / N1 / N2 overlaps the
+    // predecessor's run; each of them starts with pdl_sync())
+    static int chain_pdl = -1;
+    if (chain_pdl < 0) { const char* e = getenv("B2_DENSE_PDL"); chain_pdl = e ? (atoi(e) != 0) : 0; }
+    auto launch_chain = [&](auto kern, dim3 grid, size_t smem, auto... args) {
+        if (chain_pdl) launch_pdl(kern, grid, dim3(256), smem, S1, args...);
+        else kern<<<grid, 256, smem, S1>>>(args...);
+    };
     static bool attr = false;
     if (!attr) {
         cudaFuncSetAttribute(k_big_diag128, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Diag128Smem));
         cudaFuncSetAttribute(k_big_trsm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GU_SMEM);
         cudaFuncSetAttribute(k_big_update_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GU_SMEM);
+        cudaFuncSetAttribute(k_big_update_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GU_SMEM);
         cudaFuncSetAttribute(k_big_update_dyn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GU_SMEM);
+        cudaFuncSetAttribute(k_near_trsm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NT_SMEM);
+        cudaFuncSetAttribute(k_near_syrk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NS_SMEM);
+        cudaFuncSetAttribute(k_near_trsv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NV_SMEM);
+        cudaFuncSetAttribute(k_big_inv128, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Diag128Smem));
         attr = true;
     }
     cudaMemsetAsync(s->counters.p, 0, 2 * sizeof(int32_t), S1);
     cudaMemsetAsync(s->tilecnt.p, 0, s->tilecnt.bytes(), S1);
     k_copy_lower<<<dim3(std::max(1, std::min(8, (N + 255) / 256)), N), 256, 0, S1>>>(N, s->lda, s->A_d, s->fact.p);
-    int last_bulk = -1;
+    int last_bulk = -1, last_side = -1;
     for (int k = 0; k < nb; ++k) {
         const int ob = k * DB;
-        k_big_diag128<<<1, 256, sizeof(Diag128Smem), S1>>>(a, s->list.p, ob, s->linv.p, s->linv_off.p);
         const int rem = N - ob - 1;
-        if (rem <= 0 || ob + DB >= N) continue;
-        k_big_trsm<<<dim3((rem + TR_ROWS - 1) / TR_ROWS, 1), 256, GU_SMEM, S1>>>(a, s->list.p, ob, s->linv.p, s->linv_off.p);
-        if (last_bulk >= 0) cudaStreamWaitEvent(S1, s->ev_bulk[last_bulk], 0);       // R(k-1) also wrote block column k+1
         const int rem1 = N - (ob + DB);                                                // rows/cols from the next block on
+        const int rem2 = N - (ob + 2 * DB);                                            // ... from the block after it on
+        const bool near_step = use_near && rem > 0 && ob + DB < N && rem2 >= 0;
+        const int with_inv = (near_step && inv_side) ? 0 : 1;                               // inverse of this block formed on the side branch?
+        if (use_near && k > 0) launch_chain(k_big_diag128, dim3(1), sizeof(Diag128Smem), a, (const int32_t*)s->list.p, ob, s->linv.p, (const int64_t*)s->linv_off.p, with_inv);
+        else k_big_diag128<<<1, 256, sizeof(Diag128Smem), S1>>>(a, s->list.p, ob, s->linv.p, s->linv_off.p, with_inv);
+        if (rem <= 0 || ob + DB >= N) continue;
+        if (near_step) {
+            cudaEventRecord(s->ev_diag[k], S1);
+            if (last_side >= 0) cudaStreamWaitEvent(S1, s->ev_side[last_side], 0);     // C(k-1) wrote the rows N1(k) reads
+            if (inv_side) launch_chain(k_near_trsv, dim3(DB / NT_ROWS), NV_SMEM, a, (const int32_t*)s->list.p, ob);
+            else launch_chain(k_near_trsm, dim3(DB / NT_ROWS), NT_SMEM, a, (const int32_t*)s->list.p, ob, (const double*)s->linv.p, (const int64_t*)s->linv_off.p);
+            cudaEventRecord(s->ev_near[k], S1);
+            if (last_bulk >= 0) cudaStreamWaitEvent(S1, s->ev_bulk[last_bulk], 0);     // R(k-1) also wrote the next diagonal block
+            launch_chain(k_near_syrk, dim3(10), NS_SMEM, a, (const int32_t*)s->list.p, ob);
+            if (inv_side) {
+                cudaStreamWaitEvent(S3, s->ev_diag[k], 0);
+                k_big_inv128<<<1, 256, sizeof(Diag128Smem), S3>>>(a, s->list.p, ob, s->linv.p, s->linv_off.p);
+                if (rem2 <= 0) { cudaEventRecord(s->ev_side[k], S3); last_side = k; }
+            }
+            if (rem2 > 0) {
+                if (!inv_side) cudaStreamWaitEvent(S3, s->ev_diag[k], 0);
+                k_big_trsm<<<dim3((rem2 + TR_ROWS - 1) / TR_ROWS, 1), 256, GU_SMEM, S3>>>(a, s->list.p, ob, s->linv.p, s->linv_off.p, DB / TR_ROWS);
+                cudaStreamWaitEvent(S3, s->ev_near[k], 0);
+                if (last_bulk >= 0) cudaStreamWaitEvent(S3, s->ev_bulk[last_bulk], 0); // R(k-1) also wrote block column k+1
+                k_big_update_rows<<<dim3((rem2 + GU_M - 1) / GU_M, (DB + GU_N - 1) / GU_N, 1), 256, GU_SMEM, S3>>>(a, s->list.p, ob, DB, DB, 2 * DB, 1, 1);
+                cudaEventRecord(s->ev_side[k], S3);
+                last_side = k;
+                cudaStreamWaitEvent(S2, s->ev_side[k], 0);
+                const int nbx = (rem2 + GU_M - 1) / GU_M, nby = (rem2 + GU_N - 1) / GU_N;
+                k_big_update_dyn<<<2 * nsm, 256, GU_SMEM, S2>>>(a, s->list.p, ob, DB, 2 * DB, 1 << 30, 0, nbx, nby, s->tilecnt.p + k, n_reserved);
+                cudaEventRecord(s->ev_bulk[k], S2);
+                last_bulk = k;
+            }
+            continue;
+        }
+        // general path (partial last blocks, or B2_DENSE_NEAR=0): whole-panel trsm and whole-column update on the chain
+        if (last_side >= 0) cudaStreamWaitEvent(S1, s->ev_side[last_side], 0);
+        k_big_trsm<<<dim3((rem + TR_ROWS - 1) / TR_ROWS, 1), 256, GU_SMEM, S1>>>(a, s->list.p, ob, s->linv.p, s->linv_off.p, 0);
+        if (last_bulk >= 0) cudaStreamWaitEvent(S1, s->ev_bulk[last_bulk], 0);       // R(k-1) also wrote block column k+1
         k_big_update_pipe<<<dim3((rem1 + GU_M - 1) / GU_M, (DB + GU_N - 1) / GU_N, 1), 256, GU_SMEM, S1>>>(a, s->list.p, ob, DB, DB, 2 * DB, 1);
-        const int rem2 = N - (ob + 2 * DB);
         if (rem2 > 0) {
             cudaEventRecord(s->ev_chain[k], S1);
             cudaStreamWaitEvent(S2, s->ev_chain[k], 0);
@@ -1069,12 +1130,13 @@ void enqueue_dense_factor_lookahead(b2d_solver* s, cudaStream_t S1) {
         }
     }
     if (last_bulk >= 0) cudaStreamWaitEvent(S1, s->ev_bulk[last_bulk], 0);           // join
+    if (last_side >= 0) cudaStreamWaitEvent(S1, s->ev_side[last_side], 0);
 }
 
 void enqueue_dense_factor(b2d_solver* s, cudaStream_t st) {
     static int lookahead = -1;
     if (lookahead < 0) { const char* e = getenv("B2_DENSE_LOOKAHEAD"); lookahead = e ? (atoi(e) != 0) : 1; }
-    if (lookahead && s->aux_stream && s->N > 4 * DB) { enqueue_dense_factor_lookahead(s, st); return; }
+    if (lookahead && s->aux_stream && s->side_stream && s->N > 4 * DB) { enqueue_dense_factor_lookahead(s, st); return; }
     FactorArgs a;
     a.desc = s->desc.p; a.child_idx = nullptr; a.rel = nullptr; a.amap_src = nullptr; a.amap_dst = nullptr;
     a.A = nullptr; a.L = s->fact.p; a.ws = nullptr; a.dvec = s->dvec.p; a.counters = s->counters.p; a.eps = s->opt.pivot_eps;
@@ -1110,6 +1172,7 @@ int b2d_create(int32_t N, int32_t lda, const double* A_d, const b2_options* opt,
         cudaMallocHost((void**)&s->h_counters, 4 * sizeof(int32_t)) != cudaSuccess ||
         cudaStreamCreateWithFlags(&s->cap_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&s->aux_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&s->side_stream, cudaStreamNonBlocking) != cudaSuccess ||
         s->tilecnt.alloc((size_t)((N + DB - 1) / DB)) != cudaSuccess ||
         cudaMemset(s->fact.p, 0, s->fact.bytes()) != cudaSuccess || cudaMemset(s->counters.p, 0, 4 * sizeof(int32_t)) != cudaSuccess) {
         delete s;
@@ -1118,9 +1181,12 @@ int b2d_create(int32_t N, int32_t lda, const double* A_d, const b2_options* opt,
     if (set_smem_attrs() != B2_OK) { delete s; return B2_ERR_CUDA; }
     {
         const int nb = (N + DB - 1) / DB;
-        s->ev_chain.resize(nb); s->ev_bulk.resize(nb);
+        s->ev_chain.resize(nb); s->ev_bulk.resize(nb); s->ev_diag.resize(nb); s->ev_near.resize(nb); s->ev_side.resize(nb);
         for (int k = 0; k < nb; ++k) {
             if (cudaEventCreateWithFlags(&s->ev_chain[k], cudaEventDisableTiming) != cudaSuccess ||
+                cudaEventCreateWithFlags(&s->ev_diag[k], cudaEventDisableTiming) != cudaSuccess ||
+                cudaEventCreateWithFlags(&s->ev_near[k], cudaEventDisableTiming) != cudaSuccess ||
+                cudaEventCreateWithFlags(&s->ev_side[k], cudaEventDisableTiming) != cudaSuccess ||
                 cudaEventCreateWithFlags(&s->ev_bulk[k], cudaEventDisableTiming) != cudaSuccess) { delete s; return cuda_fail(cudaGetLastError(), "b2d_create events", __FILE__, __LINE__); }
         }
     }
