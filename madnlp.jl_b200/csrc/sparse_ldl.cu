@@ -1053,6 +1053,13 @@ void enqueue_dense_factor_lookahead(b2d_solver* s, cudaStream_t S1) {
     if (use_near < 0) { const char* e = getenv("B2_DENSE_NEAR"); use_near = e ? (atoi(e) != 0) : 1; }
     // chain kernels launched programmatically dependent on their stream predecessor (launch latency of D / N1 / N2 overlaps the
     // predecessor's run; each of them starts with pdl_sync())
+    // B2_DENSE_RELAX=1: R(k) waits for the panel's trsm only (not for the block-column update C(k), which it does not touch), and
+    // while the trailing update is long it leaves `early_reserved` SMs to the side branch so that T(k+1) / C(k+1) finish beside it
+    static int relax = -1, early_reserved = 8;
+    if (relax < 0) {
+        const char* e = getenv("B2_DENSE_RELAX"); relax = e ? (atoi(e) != 0) : 0;
+        if (const char* r = getenv("B2_DENSE_EARLY_RESERVED")) early_reserved = std::max(1, atoi(r));
+    }
     static int chain_pdl = -1;
     if (chain_pdl < 0) { const char* e = getenv("B2_DENSE_PDL"); chain_pdl = e ? (atoi(e) != 0) : 0; }
     auto launch_chain = [&](auto kern, dim3 grid, size_t smem, auto... args) {
@@ -1102,14 +1109,16 @@ void enqueue_dense_factor_lookahead(b2d_solver* s, cudaStream_t S1) {
             if (rem2 > 0) {
                 if (!inv_side) cudaStreamWaitEvent(S3, s->ev_diag[k], 0);
                 k_big_trsm<<<dim3((rem2 + TR_ROWS - 1) / TR_ROWS, 1), 256, GU_SMEM, S3>>>(a, s->list.p, ob, s->linv.p, s->linv_off.p, DB / TR_ROWS);
+                if (relax) cudaEventRecord(s->ev_chain[k], S3);                        // (ev_chain is free on this path: "panel k's L is complete")
                 cudaStreamWaitEvent(S3, s->ev_near[k], 0);
                 if (last_bulk >= 0) cudaStreamWaitEvent(S3, s->ev_bulk[last_bulk], 0); // R(k-1) also wrote block column k+1
                 k_big_update_rows<<<dim3((rem2 + GU_M - 1) / GU_M, (DB + GU_N - 1) / GU_N, 1), 256, GU_SMEM, S3>>>(a, s->list.p, ob, DB, DB, 2 * DB, 1, 1);
                 cudaEventRecord(s->ev_side[k], S3);
                 last_side = k;
-                cudaStreamWaitEvent(S2, s->ev_side[k], 0);
+                cudaStreamWaitEvent(S2, relax ? s->ev_chain[k] : s->ev_side[k], 0);
                 const int nbx = (rem2 + GU_M - 1) / GU_M, nby = (rem2 + GU_N - 1) / GU_N;
-                k_big_update_dyn<<<2 * nsm, 256, GU_SMEM, S2>>>(a, s->list.p, ob, DB, 2 * DB, 1 << 30, 0, nbx, nby, s->tilecnt.p + k, n_reserved);
+                const int nres = (relax && rem2 >= 2048) ? std::max(n_reserved, early_reserved) : n_reserved;
+                k_big_update_dyn<<<2 * nsm, 256, GU_SMEM, S2>>>(a, s->list.p, ob, DB, 2 * DB, 1 << 30, 0, nbx, nby, s->tilecnt.p + k, nres);
                 cudaEventRecord(s->ev_bulk[k], S2);
                 last_bulk = k;
             }
