@@ -331,12 +331,18 @@ def run_b200(args, rank, world, local_rank):
             i = first + j
             if not args.no_flush:
                 flush_buf.fill_(1.0)                      # (inside the timed region here)
-            nxt = pipe.prefetch(host[(i + 1) % N_ITERATES]) if j + 1 < count else None
             pipe.load(slot)
-            ok = la.step(mu=its[i % N_ITERATES].mu)
+            nxt = [None]
+            if j + 1 < count:
+                # the next iterate's H2D copies are queued while this step's assembly + factorisation run
+                def queue_next(i=i):
+                    nxt[0] = pipe.prefetch(host[(i + 1) % N_ITERATES])
+            else:
+                queue_next = None
+            ok = la.step(mu=its[i % N_ITERATES].mu, after_prologue=queue_next)
             assert ok
             pipe.push_result()
-            slot = nxt
+            slot = nxt[0]
         pipe.drain()
         e1.record(stream)
         e1.synchronize()

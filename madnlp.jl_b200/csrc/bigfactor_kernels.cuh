@@ -149,6 +149,7 @@ __global__ void __launch_bounds__(256, 1) k_big_diag128(FactorArgs a, const int3
     const int s = list[blockIdx.x];
     const FrontDesc d = a.desc[s];
     if (kb >= d.w) return;
+    trace_enter(a, 8 * (kb / DB) + TR_DIAG);
     extern __shared__ __align__(16) unsigned char dsm_raw[];
     Diag128Smem& sm = *reinterpret_cast<Diag128Smem*>(dsm_raw);
     const int f = d.f, nb = min(DB, d.w - kb);
@@ -256,8 +257,9 @@ __global__ void __launch_bounds__(256, 1) k_big_diag128(FactorArgs a, const int3
         a.dvec[d.col0 + kb + tid] = sm.dd[tid];
     }
     DPROF();
-    if (!with_inv) return;                                         // dense chain: the inverse is formed off the critical path (k_big_inv128)
+    if (!with_inv) { trace_exit(a, 8 * (kb / DB) + TR_DIAG); return; }   // dense chain: the inverse is formed off the critical path (k_big_inv128)
     diag128_invert_store(sm, tid, nb, Linv + linv_off[s] + (size_t)(kb / DB) * DB * DB);
+    trace_exit(a, 8 * (kb / DB) + TR_DIAG);
     DPROF();
 #ifdef B2_DIAG_PROF
     DPROF();
@@ -279,6 +281,7 @@ __global__ void __launch_bounds__(256, 2) k_big_trsm(FactorArgs a, const int32_t
     const int f = d.f, nb = min(DB, d.w - kb);
     const int r0 = kb + nb + (blockIdx.x + bx0) * TR_ROWS;             // bx0: first 64-row block handled by this launch
     if (r0 >= f) return;
+    trace_enter(a, 8 * (kb / DB) + TR_TRSM);
     extern __shared__ __align__(16) double gu_sm[];
     double* As = gu_sm;                                               // [stage][k][GU_LDA]  Linv(c, k)
     double* Bs = gu_sm + GU_STAGES * GU_K * GU_LDA;                   // [stage][k][GU_LDB]  A21(i, k)
@@ -359,6 +362,7 @@ __global__ void __launch_bounds__(256, 2) k_big_trsm(FactorArgs a, const int32_t
     if (r0 + i < f) {
         for (int cc = tid >> 6; cc < nb; cc += 4) Lp[(size_t)(kb + cc) * f + r0 + i] = Cs[i * GU_LDC + cc] * dinv[cc];
     }
+    trace_exit(a, 8 * (kb / DB) + TR_TRSM);
 }
 
 // ----------------------------------------------------------------------------------------------------------
@@ -389,6 +393,7 @@ __global__ void __launch_bounds__(256, 1) k_near_trsm(FactorArgs a, const int32_
     const FrontDesc d = a.desc[s];
     const int f = d.f;
     const int r0 = kb + DB + blockIdx.x * NT_ROWS;
+    trace_enter(a, 8 * (kb / DB) + TR_NEAR1);
     extern __shared__ __align__(16) double nt_sm[];
     double* As = nt_sm;                           // [128][NT_LDA]
     double* Bs = As + DB * NT_LDA;                // [128][NT_LDB]
@@ -436,6 +441,7 @@ __global__ void __launch_bounds__(256, 1) k_near_trsm(FactorArgs a, const int32_
             Lp[(size_t)(kb + cc) * f + r0 + g] = c[y][e] * dinv[cc];
         }
     }
+    trace_exit(a, 8 * (kb / DB) + TR_NEAR1);
 }
 
 constexpr int NS_T = 32;                         // tile order of k_near_syrk
@@ -451,6 +457,7 @@ __global__ void __launch_bounds__(256, 2) k_near_syrk(FactorArgs a, const int32_
     while (rem > ib) { rem -= ib + 1; ++ib; }
     const int jb = rem;
     const int base = kb + DB;                                          // first row / column of the next diagonal block
+    trace_enter(a, 8 * (kb / DB) + TR_NEAR2);
     extern __shared__ __align__(16) double ns_sm[];
     double* As = ns_sm;                           // [128][NS_LD]  L(base + 32 ib + i, kb + k)
     double* Bs = As + DB * NS_LD;                 // [128][NS_LD]  L(base + 32 jb + j, kb + k)
@@ -495,6 +502,7 @@ __global__ void __launch_bounds__(256, 2) k_near_syrk(FactorArgs a, const int32_
             const int i = base + NS_T * ib + mb + 8 * x + g, j = base + NS_T * jb + nb + 2 * q + e;
             if (i >= j) Lp[(size_t)j * f + i] = cold[x][e] + c[x][e];
         }
+    trace_exit(a, 8 * (kb / DB) + TR_NEAR2);
 }
 
 // The inverse of a finished diagonal block as its own kernel (one CTA): the dense chain leaves it to the side branch, where it runs
@@ -516,7 +524,9 @@ __global__ void __launch_bounds__(256, 1) k_big_inv128(FactorArgs a, const int32
     cp_async_commit_group();
     cp_async_wait_group_n<0>();
     __syncthreads();
+    trace_enter(a, 8 * (kb / DB) + TR_INV);
     diag128_invert_store(sm, tid, nb, Linv + linv_off[s] + (size_t)(kb / DB) * DB * DB);
+    trace_exit(a, 8 * (kb / DB) + TR_INV);
 }
 
 // Near-diagonal trsm WITHOUT the inverse: the 128 rows right below a finished diagonal block by forward substitution against L11
@@ -534,6 +544,7 @@ __global__ void __launch_bounds__(256, 1) k_near_trsv(FactorArgs a, const int32_
     double* Lp = a.L + d.lp_off;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int row = kb + DB + blockIdx.x * NT_ROWS + warp;
+    trace_enter(a, 8 * (kb / DB) + TR_NEAR1);
     for (int e = tid; e < DB * DB; e += 256) {
         const int c = e & (DB - 1), k = e >> 7;
         if (c > k) cp_async8_zfill(Ls + k * NT_LDB + c, Lp + (size_t)(kb + k) * f + kb + c, true);
@@ -561,6 +572,7 @@ __global__ void __launch_bounds__(256, 1) k_near_trsv(FactorArgs a, const int32_
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) Lp[(size_t)(kb + lane + 32 * j) * f + row] = x[j] * dinv[j];
+    trace_exit(a, 8 * (kb / DB) + TR_NEAR1);
 }
 
 }  // namespace b2

@@ -38,7 +38,18 @@ struct FactorArgs {
     double* dvec;         // D, permuted order
     int32_t* counters;    // [0] = #negative pivots, [1] = #perturbed pivots
     double eps;
+    unsigned long long* trace = nullptr;   // debug (B2_DENSE_TRACE): [slot][2] = first entry / last exit of a launch, %globaltimer ns
 };
+
+// Timeline stamps of the dense look-ahead schedule (b2d_debug_trace): slot = 8 * block column + kernel kind
+enum { TR_DIAG = 0, TR_NEAR1 = 1, TR_NEAR2 = 2, TR_TRSM = 3, TR_COL = 4, TR_BULK = 5, TR_INV = 6 };
+__device__ __forceinline__ unsigned long long global_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ void trace_enter(const FactorArgs& a, int slot) {
+    if (a.trace && threadIdx.x == 0) atomicMin(a.trace + 2 * slot, global_ns());
+}
+__device__ __forceinline__ void trace_exit(const FactorArgs& a, int slot) {
+    if (a.trace) { __syncthreads(); if (threadIdx.x == 0) atomicMax(a.trace + 2 * slot + 1, global_ns()); }
+}
 
 // ----------------------------------------------------------------------------------------------------------
 // S/M class: fused assemble + factor + store with the whole front in shared memory.
@@ -382,7 +393,9 @@ __global__ void __launch_bounds__(256, 2) k_big_update_rows(FactorArgs a, const 
                                                             int jhi_rel, int clip_jlo, int bx0) {
     extern __shared__ __align__(16) double gu_sm[];
     const FrontDesc d = a.desc[list[blockIdx.z]];
+    trace_enter(a, 8 * (kb0 / 128) + TR_COL);
     big_update_tile(a, d, kb0, kmax, jlo_rel, jhi_rel, clip_jlo, blockIdx.x + bx0, blockIdx.y, gu_sm);
+    trace_exit(a, 8 * (kb0 / 128) + TR_COL);
 }
 
 // The same update as a PERSISTENT kernel with a dynamic tile queue, for the look-ahead schedule of the dense factorisation:
@@ -397,12 +410,13 @@ __global__ void __launch_bounds__(256, 2) k_big_update_dyn(FactorArgs a, const i
     if ((int)smid() < n_reserved) return;
     const FrontDesc d = a.desc[list[0]];
     const int ntile = nbx * nby;
+    trace_enter(a, 8 * (kb0 / 128) + TR_BULK);
     for (;;) {
         __syncthreads();                                 // (the previous tile's epilogue has finished with shared memory)
         if (threadIdx.x == 0) t_sh = atomicAdd(tile_counter, 1);
         __syncthreads();
         const int t = t_sh;
-        if (t >= ntile) return;
+        if (t >= ntile) { trace_exit(a, 8 * (kb0 / 128) + TR_BULK); return; }
         big_update_tile(a, d, kb0, kmax, jlo_rel, jhi_rel, clip_jlo, t % nbx, t / nbx, gu_sm);
     }
 }

@@ -998,6 +998,7 @@ struct b2d_solver {
     b2_options opt;
     DevBuf<double> fact, dvec, linv, side, flow;     // flow: [2][nblk*128] hand-off vectors of the single-launch solve
     DevBuf<int32_t> tilecnt;                         // look-ahead schedule: one dynamic-tile counter per panel step
+    DevBuf<unsigned long long> trace;                // B2_DENSE_TRACE=1: [8 * nblk][2] first-entry / last-exit stamps (b2d_debug_trace)
     cudaStream_t aux_stream = nullptr;               // second branch of the look-ahead schedule (trailing updates)
     cudaStream_t side_stream = nullptr;              // third branch: rest of the panel (trsm + next block column) beside the next diagonal block
     std::vector<cudaEvent_t> ev_chain, ev_bulk, ev_diag, ev_near, ev_side;
@@ -1029,6 +1030,11 @@ __global__ void k_copy_lower(int N, int lda, const double* __restrict__ A, doubl
         F[(size_t)j * N + i] = A[(size_t)j * lda + i];
 }
 
+__global__ void k_trace_reset(unsigned long long* t, int nslot) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 2 * nslot) t[i] = (i & 1) ? 0ull : ~0ull;
+}
+
 // Look-ahead schedule of the dense LDL^T (three stream branches; captured into ONE graph by b2d_factorize).  Per block column k:
 //   chain S1:  D(k) diagonal block -> N1(k) the 128 x 128 block of L below it (k_near_trsm) -> N2(k) update of the NEXT diagonal block
 //              (k_near_syrk) -> D(k+1) ...                         -- the only kernels on the critical path, each a few SMs wide
@@ -1043,6 +1049,10 @@ void enqueue_dense_factor_lookahead(b2d_solver* s, cudaStream_t S1) {
     a.A = nullptr; a.L = s->fact.p; a.ws = nullptr; a.dvec = s->dvec.p; a.counters = s->counters.p; a.eps = s->opt.pivot_eps;
     const int N = s->N, nb = (N + DB - 1) / DB, nsm = sm_count();
     cudaStream_t S2 = s->aux_stream, S3 = s->side_stream;
+    if (s->trace.p) {
+        a.trace = s->trace.p;
+        k_trace_reset<<<(16 * nb + 255) / 256, 256, 0, S1>>>(s->trace.p, 8 * nb);
+    }
     static int n_reserved = -1;        // SMs the trailing update leaves to the chain (diagonal block: 1 CTA; near-diagonal kernels: 16 / 10 small CTAs)
     // B2_DENSE_INV_SIDE=1: the diagonal-block kernel stops after writing L11 / D back; the near-diagonal trsm substitutes against L11
     // (k_near_trsv) and the inverse (needed by the whole-panel trsm and by the solves) is formed by k_big_inv128 on the side branch
@@ -1183,6 +1193,7 @@ int b2d_create(int32_t N, int32_t lda, const double* A_d, const b2_options* opt,
         cudaStreamCreateWithFlags(&s->aux_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&s->side_stream, cudaStreamNonBlocking) != cudaSuccess ||
         s->tilecnt.alloc((size_t)((N + DB - 1) / DB)) != cudaSuccess ||
+        (getenv("B2_DENSE_TRACE") && atoi(getenv("B2_DENSE_TRACE")) && s->trace.alloc((size_t)16 * ((N + DB - 1) / DB)) != cudaSuccess) ||
         cudaMemset(s->fact.p, 0, s->fact.bytes()) != cudaSuccess || cudaMemset(s->counters.p, 0, 4 * sizeof(int32_t)) != cudaSuccess) {
         delete s;
         return cuda_fail(cudaGetLastError(), "b2d_create allocation", __FILE__, __LINE__);
@@ -1225,6 +1236,15 @@ int b2d_factorize(b2d_solver* s, void* stream) {
         B2_CUDA(cudaGetLastError());
     }
     s->factorized = true;
+    return B2_OK;
+}
+
+int b2d_debug_trace(b2d_solver* s, uint64_t* stamps_h, int64_t capacity, int64_t* count) {
+    if (!s || !count) { set_error("b2d_debug_trace: invalid argument"); return B2_ERR_INVALID; }
+    *count = (int64_t)s->trace.n;
+    if (!s->trace.p || !stamps_h || capacity < (int64_t)s->trace.n) return B2_OK;      // (count = 0: tracing is off)
+    B2_CUDA(cudaDeviceSynchronize());
+    B2_CUDA(cudaMemcpy(stamps_h, s->trace.p, s->trace.bytes(), cudaMemcpyDeviceToHost));
     return B2_OK;
 }
 

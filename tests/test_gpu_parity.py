@@ -366,9 +366,18 @@ def test_host_pipeline_returns_the_same_directions_as_serial_steps():
     got = []
     slot = pipe.prefetch(host[0])
     for i, it in enumerate(its):
-        nxt = pipe.prefetch(host[i + 1]) if i + 1 < len(its) else None
         pipe.load(slot)
-        assert la.step(mu=it.mu)
+        nxt = None
+        if i + 1 < len(its):
+            if i % 2:                                     # both placements of the prefetch: before the step / inside it
+                nxt = pipe.prefetch(host[i + 1])
+                assert la.step(mu=it.mu)
+            else:
+                box = []
+                assert la.step(mu=it.mu, after_prologue=lambda: box.append(pipe.prefetch(host[i + 1])))
+                nxt = box[0]
+        else:
+            assert la.step(mu=it.mu)
         hs = pipe.push_result()
         pipe.ev_d_out[hs].synchronize()
         got.append(pipe.d_host[hs].numpy().copy())
