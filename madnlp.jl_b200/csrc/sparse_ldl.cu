@@ -5,6 +5,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <stdexcept>
+#include <array>
 #include <vector>
 
 #include "analysis.hpp"
@@ -29,6 +30,10 @@ struct LevelSched {
     WarpLaunch W, W2;                               // fronts of order <= 32 / <= 64
     int offM = 0, nM = 0, maxfM = 0;                // shared-memory CTA class
     int offB = 0, nB = 0, maxfB = 0, maxwB = 0, maxchildB = 0, maxamapB = 0, maxrB = 0;   // HBM-resident class
+    // the first nLA fronts of the B list are factorised ONE AT A TIME with the three-branch look-ahead schedule (enqueue_front_lookahead);
+    // la[i] = {w, f, offset of its tile counters}; maxfBr / maxwBr: maxima over the remaining (batched) fronts
+    int nLA = 0, maxfBr = 0, maxwBr = 0;
+    std::vector<std::array<int, 3>> la;
     int offC = 0, nC = 0, maxfC = 0, maxwC = 0;     // M and B fronts together, for the multi-CTA solve kernels
 };
 struct Phase {
@@ -70,6 +75,10 @@ struct b2_solver {
     int64_t exch_cbv = 0;
     Phase phase[2];                  // 0 = local (owned subtrees), 1 = shared top tree
     cudaStream_t cap_stream = nullptr;
+    cudaStream_t la_bulk = nullptr, la_side = nullptr;   // side branches of the look-ahead schedule of the largest fronts
+    std::vector<cudaEvent_t> ev_pool;
+    size_t ev_next = 0;
+    DevBuf<int32_t> d_tilecnt;                           // dynamic-tile counters, one per 128-column block of every look-ahead front
     bool factorized = false;
     int64_t last_perturbed = 0;
     std::vector<uint8_t> owned_mask;  // original numbering
@@ -81,6 +90,9 @@ struct b2_solver {
             if (p.g_bwd) cudaGraphExecDestroy(p.g_bwd);
         }
         if (cap_stream) cudaStreamDestroy(cap_stream);
+        if (la_bulk) cudaStreamDestroy(la_bulk);
+        if (la_side) cudaStreamDestroy(la_side);
+        for (auto e : ev_pool) cudaEventDestroy(e);
         if (h_counters) cudaFreeHost(h_counters);
     }
 };
@@ -104,6 +116,153 @@ void launch_big_step(const FactorArgs& a, const int32_t* lb, int nfronts, int ob
     k_big_trsm<<<dim3((rem + TR_ROWS - 1) / TR_ROWS, nfronts), 256, GU_SMEM, st>>>(a, lb, ob, Linv, linv_off, 0);
     k_big_update_pipe<<<dim3((rem + GU_M - 1) / GU_M, (rem + GU_N - 1) / GU_N, nfronts), 256, GU_SMEM, st>>>(a, lb, ob, DB, DB, 1 << 30, 1);
     if (nl) *nl += 2;
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// Look-ahead schedule of ONE HBM-resident front (the dense solver's matrix: f = w = N; a big front of the multifrontal tree: f > w),
+// three stream branches joined back into S1 (captured into the caller's graph).  Per block column k of 128 pivots:
+//   chain S1:  D(k) diagonal block -> N1(k) the 128 x 128 block of L below it (k_near_trsm) -> N2(k) update of the NEXT diagonal block
+//              (k_near_syrk) -> D(k+1) ...                         -- the only kernels on the critical path, each a few SMs wide
+//   side  S3:  T(k) trsm of the rows from block k+2 on (after D(k)) -> C(k) rest of block column k+1 (after N1(k), R(k-1))
+//   bulk  S2:  R(k) update of the columns >= k+2 incl. the front's update block (persistent, dynamic tiles, leaves the reserved SMs
+//              to the chain)
+// N1(k+1) waits for C(k), N2(k) and C(k) wait for R(k-1).  While the trailing update is long (first panels) the chain waits for it;
+// once it is short the period is D + N1 + N2 instead of D + whole-panel trsm + whole-column update (42 + 12 + 8 us).
+// Block columns whose successor is not a full pivot block (tail of the pivots, w not a multiple of 128) take the general path:
+// whole-panel trsm and whole-column update on the chain.  B2_DENSE_NEAR=0 forces it everywhere (the two-branch schedule).
+// ----------------------------------------------------------------------------------------------------------
+__global__ void k_trace_reset(unsigned long long* t, int nslot) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 2 * nslot) t[i] = (i & 1) ? 0ull : ~0ull;
+}
+
+struct LookaheadCtx {
+    cudaStream_t S2 = nullptr, S3 = nullptr;
+    std::vector<cudaEvent_t>* pool = nullptr;        // events, created on demand, handed out in order
+    size_t* next = nullptr;
+    int32_t* tilecnt = nullptr;                      // one dynamic-tile counter per block column (zeroed by the caller)
+    cudaEvent_t ev() {
+        if (*next == pool->size()) { cudaEvent_t e; cudaEventCreateWithFlags(&e, cudaEventDisableTiming); pool->push_back(e); }
+        return (*pool)[(*next)++];
+    }
+};
+
+struct LookaheadKnobs { int n_reserved, inv_side, use_near, relax, early_reserved, chain_pdl; };
+const LookaheadKnobs& lookahead_knobs() {
+    static LookaheadKnobs K = [] {
+        LookaheadKnobs k;
+        auto geti = [](const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; };
+        // B2_DENSE_INV_SIDE=1: the diagonal-block kernel stops after writing L11 / D back; the near-diagonal trsm substitutes against L11
+        // (k_near_trsv) and the inverse (needed by the whole-panel trsm and by the solves) is formed by k_big_inv128 on the side branch
+        k.inv_side = geti("B2_DENSE_INV_SIDE", 0) != 0;
+        k.n_reserved = std::max(1, geti("B2_DENSE_RESERVED_SMS", k.inv_side ? 2 : 1));   // SMs the trailing update leaves to the chain
+        k.use_near = geti("B2_DENSE_NEAR", 1) != 0;
+        // B2_DENSE_RELAX (default 1): R(k) waits for the panel's trsm only (not for the block-column update C(k), which it does not touch), and
+        // while the trailing update is long it leaves `early_reserved` SMs to the side branch so that T(k+1) / C(k+1) finish beside it
+        k.relax = geti("B2_DENSE_RELAX", 1) != 0;
+        k.early_reserved = std::max(1, geti("B2_DENSE_EARLY_RESERVED", 4));
+        // chain kernels launched programmatically dependent on their stream predecessor (each of them starts with pdl_sync())
+        k.chain_pdl = geti("B2_DENSE_PDL", 0) != 0;
+        return k;
+    }();
+    return K;
+}
+
+void lookahead_attrs() {
+    static bool attr = false;
+    if (attr) return;
+    cudaFuncSetAttribute(k_big_diag128, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Diag128Smem));
+    cudaFuncSetAttribute(k_big_trsm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GU_SMEM);
+    cudaFuncSetAttribute(k_big_update_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GU_SMEM);
+    cudaFuncSetAttribute(k_big_update_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GU_SMEM);
+    cudaFuncSetAttribute(k_big_update_dyn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GU_SMEM);
+    cudaFuncSetAttribute(k_near_trsm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NT_SMEM);
+    cudaFuncSetAttribute(k_near_syrk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NS_SMEM);
+    cudaFuncSetAttribute(k_near_trsv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NV_SMEM);
+    cudaFuncSetAttribute(k_big_inv128, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Diag128Smem));
+    attr = true;
+}
+
+// `list1`: device pointer to the front's supernode id; f, w: its order and pivot count.  Returns the number of launches.
+int64_t enqueue_front_lookahead(const FactorArgs& a, const int32_t* list1, int f, int w, double* Linv, const int64_t* linv_off,
+                                LookaheadCtx& cx, cudaStream_t S1) {
+    const LookaheadKnobs& K = lookahead_knobs();
+    lookahead_attrs();
+    const int nb = (w + DB - 1) / DB, nsm = sm_count();
+    cudaStream_t S2 = cx.S2, S3 = cx.S3;
+    int64_t nl = 0;
+    auto launch_chain = [&](auto kern, dim3 grid, size_t smem, auto... args) {
+        if (K.chain_pdl) launch_pdl(kern, grid, dim3(256), smem, S1, args...);
+        else kern<<<grid, 256, smem, S1>>>(args...);
+        ++nl;
+    };
+    cudaEvent_t ev_bulk = nullptr, ev_side = nullptr;            // most recent R(.) / side-branch completion
+    for (int k = 0; k < nb; ++k) {
+        const int ob = k * DB;
+        const int nbk = std::min(DB, w - ob);                    // pivots of this block column
+        const int j1 = ob + nbk;                                 // first trailing row / column
+        const int rem2 = f - (ob + 2 * DB);                      // rows / columns from the block after the next on
+        const bool near_step = K.use_near && ob + 2 * DB <= w;   // the next diagonal block is a full pivot block
+        const int with_inv = (near_step && K.inv_side) ? 0 : 1;  // inverse of this block formed on the side branch?
+        if (K.use_near && k > 0) launch_chain(k_big_diag128, dim3(1), sizeof(Diag128Smem), a, list1, ob, Linv, linv_off, with_inv);
+        else { k_big_diag128<<<1, 256, sizeof(Diag128Smem), S1>>>(a, list1, ob, Linv, linv_off, with_inv); ++nl; }
+        if (j1 >= f) continue;                                   // no rows below (last block of a dense matrix)
+        if (near_step) {
+            cudaEvent_t ev_diag = cx.ev(), ev_near = cx.ev();
+            cudaEventRecord(ev_diag, S1);
+            if (ev_side) cudaStreamWaitEvent(S1, ev_side, 0);                          // C(k-1) wrote the rows N1(k) reads
+            if (K.inv_side) launch_chain(k_near_trsv, dim3(DB / NT_ROWS), NV_SMEM, a, list1, ob);
+            else launch_chain(k_near_trsm, dim3(DB / NT_ROWS), NT_SMEM, a, list1, ob, (const double*)Linv, linv_off);
+            cudaEventRecord(ev_near, S1);
+            if (ev_bulk) cudaStreamWaitEvent(S1, ev_bulk, 0);                          // R(k-1) also wrote the next diagonal block
+            launch_chain(k_near_syrk, dim3(10), NS_SMEM, a, list1, ob);
+            if (K.inv_side) {
+                cudaStreamWaitEvent(S3, ev_diag, 0);
+                k_big_inv128<<<1, 256, sizeof(Diag128Smem), S3>>>(a, list1, ob, Linv, linv_off);
+                ++nl;
+                if (rem2 <= 0) { ev_side = cx.ev(); cudaEventRecord(ev_side, S3); }
+            }
+            if (rem2 > 0) {
+                if (!K.inv_side) cudaStreamWaitEvent(S3, ev_diag, 0);
+                k_big_trsm<<<dim3((rem2 + TR_ROWS - 1) / TR_ROWS, 1), 256, GU_SMEM, S3>>>(a, list1, ob, Linv, linv_off, DB / TR_ROWS);
+                cudaEvent_t ev_panel = nullptr;
+                if (K.relax) { ev_panel = cx.ev(); cudaEventRecord(ev_panel, S3); }    // "panel k's L is complete"
+                cudaStreamWaitEvent(S3, ev_near, 0);
+                if (ev_bulk) cudaStreamWaitEvent(S3, ev_bulk, 0);                      // R(k-1) also wrote block column k+1
+                k_big_update_rows<<<dim3((rem2 + GU_M - 1) / GU_M, (DB + GU_N - 1) / GU_N, 1), 256, GU_SMEM, S3>>>(a, list1, ob, DB, DB, 2 * DB, 1, 1);
+                ev_side = cx.ev();
+                cudaEventRecord(ev_side, S3);
+                cudaStreamWaitEvent(S2, K.relax ? ev_panel : ev_side, 0);
+                const int nbx = (rem2 + GU_M - 1) / GU_M, nby = (rem2 + GU_N - 1) / GU_N;
+                const int nres = (K.relax && rem2 >= 2048) ? std::max(K.n_reserved, K.early_reserved) : K.n_reserved;
+                k_big_update_dyn<<<2 * nsm, 256, GU_SMEM, S2>>>(a, list1, ob, DB, 2 * DB, 1 << 30, 0, nbx, nby, cx.tilecnt + k, nres);
+                ev_bulk = cx.ev();
+                cudaEventRecord(ev_bulk, S2);
+                nl += 3;
+            }
+            continue;
+        }
+        // general path: whole-panel trsm and the update of the next 128 columns on the chain, the rest on the bulk branch
+        if (ev_side) cudaStreamWaitEvent(S1, ev_side, 0);
+        k_big_trsm<<<dim3((f - j1 + TR_ROWS - 1) / TR_ROWS, 1), 256, GU_SMEM, S1>>>(a, list1, ob, Linv, linv_off, 0);
+        if (ev_bulk) cudaStreamWaitEvent(S1, ev_bulk, 0);                              // R(k-1) also wrote block column k+1
+        const int jhi = std::min(f, ob + 2 * DB);
+        k_big_update_pipe<<<dim3((f - j1 + GU_M - 1) / GU_M, (jhi - j1 + GU_N - 1) / GU_N, 1), 256, GU_SMEM, S1>>>(a, list1, ob, DB, DB, 2 * DB, 1);
+        nl += 2;
+        if (rem2 > 0) {
+            cudaEvent_t ev_chain = cx.ev();
+            cudaEventRecord(ev_chain, S1);
+            cudaStreamWaitEvent(S2, ev_chain, 0);
+            const int nbx = (rem2 + GU_M - 1) / GU_M, nby = (rem2 + GU_N - 1) / GU_N;
+            k_big_update_dyn<<<2 * nsm, 256, GU_SMEM, S2>>>(a, list1, ob, DB, 2 * DB, 1 << 30, 0, nbx, nby, cx.tilecnt + k, K.n_reserved);
+            ev_bulk = cx.ev();
+            cudaEventRecord(ev_bulk, S2);
+            ++nl;
+        }
+    }
+    if (ev_bulk) cudaStreamWaitEvent(S1, ev_bulk, 0);                                  // join
+    if (ev_side) cudaStreamWaitEvent(S1, ev_side, 0);
+    return nl;
 }
 
 FactorArgs factor_args(b2_solver* s) {
@@ -169,6 +328,8 @@ int64_t enqueue_factor(b2_solver* s, int ph, cudaStream_t st) {
         return 2;
     }
     if (P.fused.n_cta) warp_launch(P.fused);
+    s->ev_next = 0;
+    if (s->d_tilecnt.p) cudaMemsetAsync(s->d_tilecnt.p, 0, s->d_tilecnt.bytes(), st);
     for (const LevelSched& lv : P.lev) {
         if (lv.W.n_cta) warp_launch(lv.W);
         if (lv.W2.n_cta) warp_launch(lv.W2);
@@ -186,7 +347,17 @@ int64_t enqueue_factor(b2_solver* s, int ph, cudaStream_t st) {
                 k_big_extend_add<<<dim3(std::max(1, std::min(2 * nsm / lv.nB + 1, (lv.maxrB * 32 + 255) / 256)), lv.nB), 256, 0, st>>>(a, lb, c);
                 ++nl;
             }
-            for (int ob = 0; ob < lv.maxwB; ob += DB) launch_big_step(a, lb, lv.nB, ob, lv.maxfB, s->d_Linv.p, s->d_linv_off.p, st, &nl);
+            // the largest fronts one at a time, each with the whole GPU: diagonal blocks / near-diagonal steps of panel k+1 run beside
+            // the trailing update of panel k (three stream branches, joined back into `st`)
+            for (int i = 0; i < lv.nLA; ++i) {
+                LookaheadCtx cx;
+                cx.S2 = s->la_bulk; cx.S3 = s->la_side; cx.pool = &s->ev_pool; cx.next = &s->ev_next; cx.tilecnt = s->d_tilecnt.p + lv.la[i][2];
+                nl += enqueue_front_lookahead(a, lb + i, lv.la[i][1], lv.la[i][0], s->d_Linv.p, s->d_linv_off.p, cx, st);
+            }
+            // the others batched level-wide, three launches per 128 pivot columns
+            if (lv.nB > lv.nLA)
+                for (int ob = 0; ob < lv.maxwBr; ob += DB)
+                    launch_big_step(a, lb + lv.nLA, lv.nB - lv.nLA, ob, lv.maxfBr, s->d_Linv.p, s->d_linv_off.p, st, &nl);
         }
     }
     if (P.topfused.n_cta) warp_launch(P.topfused);
@@ -314,6 +485,9 @@ int capture(b2_solver* s, cudaGraphExec_t* out, Fn fn) {
 }
 
 void build_schedule(b2_solver* s) {
+    // fronts with at least this many pivot columns get the look-ahead schedule (B2_LOOKAHEAD_MIN_W, 0 = off)
+    int la_min_w = 512, la_tiles = 0;
+    if (const char* e = getenv("B2_LOOKAHEAD_MIN_W")) la_min_w = atoi(e);
     const Symbolic& S = s->S;
     const int ns = S.nsuper;
     const int rank = std::max(0, s->opt.part_rank);
@@ -511,6 +685,22 @@ void build_schedule(b2_solver* s) {
             if (!Wx.empty()) lv.W = level_launch(Wx, 1);
             if (!W2x.empty()) lv.W2 = level_launch(W2x, 2);
             lv.offM = (int)sched.size(); lv.nM = (int)Mx.size(); sched.insert(sched.end(), Mx.begin(), Mx.end());
+            {   // look-ahead fronts first (stable: ascending supernode id inside both groups)
+                std::vector<int32_t> la_sn, rest;
+                for (int sn : Bx) {
+                    int w, f; fdim(sn, w, f);
+                    if (la_min_w > 0 && w >= la_min_w && s->la_bulk && s->la_side) {
+                        la_sn.push_back(sn);
+                        lv.la.push_back({w, f, la_tiles});
+                        la_tiles += (w + DB - 1) / DB;
+                    } else {
+                        rest.push_back(sn);
+                        lv.maxfBr = std::max(lv.maxfBr, f); lv.maxwBr = std::max(lv.maxwBr, w);
+                    }
+                }
+                lv.nLA = (int)la_sn.size();
+                Bx = la_sn; Bx.insert(Bx.end(), rest.begin(), rest.end());
+            }
             lv.offB = (int)sched.size(); lv.nB = (int)Bx.size(); sched.insert(sched.end(), Bx.begin(), Bx.end());
             lv.offC = lv.offM; lv.nC = lv.nM + lv.nB;        // M and B lists are adjacent
             P.lev.push_back(lv);
@@ -519,6 +709,7 @@ void build_schedule(b2_solver* s) {
     }
     if (sched.empty()) sched.push_back(0);
     B2_CUDA_THROW(s->d_sched.upload(sched.data(), sched.size()));
+    if (la_tiles) B2_CUDA_THROW(s->d_tilecnt.alloc((size_t)la_tiles));
 }
 
 int create_common(int32_t n, int64_t nnz, const int32_t* colptr_h, const int32_t* rowval_h, const double* nzval_d,
@@ -654,6 +845,8 @@ int create_common(int32_t n, int64_t nnz, const int32_t* colptr_h, const int32_t
         B2_CUDA_THROW(cudaMemset(s->d_cbv.p, 0, s->d_cbv.bytes()));
         B2_CUDA_THROW(cudaMallocHost((void**)&s->h_counters, 8 * sizeof(int32_t)));
         B2_CUDA_THROW(cudaStreamCreateWithFlags(&s->cap_stream, cudaStreamNonBlocking));
+        B2_CUDA_THROW(cudaStreamCreateWithFlags(&s->la_bulk, cudaStreamNonBlocking));
+        B2_CUDA_THROW(cudaStreamCreateWithFlags(&s->la_side, cudaStreamNonBlocking));
         build_schedule(s);
         if (set_smem_attrs() != B2_OK) throw std::runtime_error("attr");
     } catch (std::exception&) {
@@ -1001,7 +1194,8 @@ struct b2d_solver {
     DevBuf<unsigned long long> trace;                // B2_DENSE_TRACE=1: [8 * nblk][2] first-entry / last-exit stamps (b2d_debug_trace)
     cudaStream_t aux_stream = nullptr;               // second branch of the look-ahead schedule (trailing updates)
     cudaStream_t side_stream = nullptr;              // third branch: rest of the panel (trsm + next block column) beside the next diagonal block
-    std::vector<cudaEvent_t> ev_chain, ev_bulk, ev_diag, ev_near, ev_side;
+    std::vector<cudaEvent_t> ev_pool;               // events of the look-ahead schedule (created on demand)
+    size_t ev_next = 0;
     DevBuf<int64_t> linv_off;
     DevBuf<FrontDesc> desc;
     DevBuf<int32_t> list, counters;
@@ -1011,11 +1205,7 @@ struct b2d_solver {
     bool factorized = false;
     ~b2d_solver() {
         if (g_factor) cudaGraphExecDestroy(g_factor);
-        for (auto e : ev_chain) cudaEventDestroy(e);
-        for (auto e : ev_bulk) cudaEventDestroy(e);
-        for (auto e : ev_diag) cudaEventDestroy(e);
-        for (auto e : ev_near) cudaEventDestroy(e);
-        for (auto e : ev_side) cudaEventDestroy(e);
+        for (auto e : ev_pool) cudaEventDestroy(e);
         if (aux_stream) cudaStreamDestroy(aux_stream);
         if (side_stream) cudaStreamDestroy(side_stream);
         if (cap_stream) cudaStreamDestroy(cap_stream);
@@ -1030,126 +1220,21 @@ __global__ void k_copy_lower(int N, int lda, const double* __restrict__ A, doubl
         F[(size_t)j * N + i] = A[(size_t)j * lda + i];
 }
 
-__global__ void k_trace_reset(unsigned long long* t, int nslot) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < 2 * nslot) t[i] = (i & 1) ? 0ull : ~0ull;
-}
-
-// Look-ahead schedule of the dense LDL^T (three stream branches; captured into ONE graph by b2d_factorize).  Per block column k:
-//   chain S1:  D(k) diagonal block -> N1(k) the 128 x 128 block of L below it (k_near_trsm) -> N2(k) update of the NEXT diagonal block
-//              (k_near_syrk) -> D(k+1) ...                         -- the only kernels on the critical path, each a few SMs wide
-//   side  S3:  T(k) trsm of the rows from block k+2 on (after D(k)) -> C(k) rest of block column k+1 (after N1(k), R(k-1))
-//   bulk  S2:  R(k) update of the columns >= k+2 (after C(k); persistent, dynamic tiles, leaves the reserved SMs to the chain)
-// N1(k+1) waits for C(k), N2(k) and C(k) wait for R(k-1).  While the trailing update is long (first panels) the chain waits for it;
-// once it is short the period is D + N1 + N2 instead of D + whole-panel trsm + whole-column update (round 2 before: 42 + 12 + 8 us).
-// B2_DENSE_NEAR=0 restores that two-branch schedule (T and C on the chain).
 void enqueue_dense_factor_lookahead(b2d_solver* s, cudaStream_t S1) {
     FactorArgs a;
     a.desc = s->desc.p; a.child_idx = nullptr; a.rel = nullptr; a.amap_src = nullptr; a.amap_dst = nullptr;
     a.A = nullptr; a.L = s->fact.p; a.ws = nullptr; a.dvec = s->dvec.p; a.counters = s->counters.p; a.eps = s->opt.pivot_eps;
-    const int N = s->N, nb = (N + DB - 1) / DB, nsm = sm_count();
-    cudaStream_t S2 = s->aux_stream, S3 = s->side_stream;
+    const int N = s->N, nb = (N + DB - 1) / DB;
     if (s->trace.p) {
         a.trace = s->trace.p;
         k_trace_reset<<<(16 * nb + 255) / 256, 256, 0, S1>>>(s->trace.p, 8 * nb);
     }
-    static int n_reserved = -1;        // SMs the trailing update leaves to the chain (diagonal block: 1 CTA; near-diagonal kernels: 16 / 10 small CTAs)
-    // B2_DENSE_INV_SIDE=1: the diagonal-block kernel stops after writing L11 / D back; the near-diagonal trsm substitutes against L11
-    // (k_near_trsv) and the inverse (needed by the whole-panel trsm and by the solves) is formed by k_big_inv128 on the side branch
-    static int inv_side = -1;
-    if (inv_side < 0) { const char* e = getenv("B2_DENSE_INV_SIDE"); inv_side = e ? (atoi(e) != 0) : 0; }
-    if (n_reserved < 0) { const char* e = getenv("B2_DENSE_RESERVED_SMS"); n_reserved = e ? std::max(1, atoi(e)) : (inv_side ? 2 : 1); }
-    static int use_near = -1;
-    if (use_near < 0) { const char* e = getenv("B2_DENSE_NEAR"); use_near = e ? (atoi(e) != 0) : 1; }
-    // chain kernels launched programmatically dependent on their stream predecessor (launch latency of D / N1 / N2 overlaps the
-    // predecessor's run; each of them starts with pdl_sync())
-    // B2_DENSE_RELAX=1: R(k) waits for the panel's trsm only (not for the block-column update C(k), which it does not touch), and
-    // while the trailing update is long it leaves `early_reserved` SMs to the side branch so that T(k+1) / C(k+1) finish beside it
-    static int relax = -1, early_reserved = 8;
-    if (relax < 0) {
-        const char* e = getenv("B2_DENSE_RELAX"); relax = e ? (atoi(e) != 0) : 0;
-        if (const char* r = getenv("B2_DENSE_EARLY_RESERVED")) early_reserved = std::max(1, atoi(r));
-    }
-    static int chain_pdl = -1;
-    if (chain_pdl < 0) { const char* e = getenv("B2_DENSE_PDL"); chain_pdl = e ? (atoi(e) != 0) : 0; }
-    auto launch_chain = [&](auto kern, dim3 grid, size_t smem, auto... args) {
-        if (chain_pdl) launch_pdl(kern, grid, dim3(256), smem, S1, args...);
-        else kern<<<grid, 256, smem, S1>>>(args...);
-    };
-    static bool attr = false;
-    if (!attr) {
-        cudaFuncSetAttribute(k_big_diag128, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Diag128Smem));
-        cudaFuncSetAttribute(k_big_trsm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GU_SMEM);
-        cudaFuncSetAttribute(k_big_update_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GU_SMEM);
-        cudaFuncSetAttribute(k_big_update_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GU_SMEM);
-        cudaFuncSetAttribute(k_big_update_dyn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GU_SMEM);
-        cudaFuncSetAttribute(k_near_trsm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NT_SMEM);
-        cudaFuncSetAttribute(k_near_syrk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NS_SMEM);
-        cudaFuncSetAttribute(k_near_trsv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NV_SMEM);
-        cudaFuncSetAttribute(k_big_inv128, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Diag128Smem));
-        attr = true;
-    }
     cudaMemsetAsync(s->counters.p, 0, 2 * sizeof(int32_t), S1);
     cudaMemsetAsync(s->tilecnt.p, 0, s->tilecnt.bytes(), S1);
     k_copy_lower<<<dim3(std::max(1, std::min(8, (N + 255) / 256)), N), 256, 0, S1>>>(N, s->lda, s->A_d, s->fact.p);
-    int last_bulk = -1, last_side = -1;
-    for (int k = 0; k < nb; ++k) {
-        const int ob = k * DB;
-        const int rem = N - ob - 1;
-        const int rem1 = N - (ob + DB);                                                // rows/cols from the next block on
-        const int rem2 = N - (ob + 2 * DB);                                            // ... from the block after it on
-        const bool near_step = use_near && rem > 0 && ob + DB < N && rem2 >= 0;
-        const int with_inv = (near_step && inv_side) ? 0 : 1;                               // inverse of this block formed on the side branch?
-        if (use_near && k > 0) launch_chain(k_big_diag128, dim3(1), sizeof(Diag128Smem), a, (const int32_t*)s->list.p, ob, s->linv.p, (const int64_t*)s->linv_off.p, with_inv);
-        else k_big_diag128<<<1, 256, sizeof(Diag128Smem), S1>>>(a, s->list.p, ob, s->linv.p, s->linv_off.p, with_inv);
-        if (rem <= 0 || ob + DB >= N) continue;
-        if (near_step) {
-            cudaEventRecord(s->ev_diag[k], S1);
-            if (last_side >= 0) cudaStreamWaitEvent(S1, s->ev_side[last_side], 0);     // C(k-1) wrote the rows N1(k) reads
-            if (inv_side) launch_chain(k_near_trsv, dim3(DB / NT_ROWS), NV_SMEM, a, (const int32_t*)s->list.p, ob);
-            else launch_chain(k_near_trsm, dim3(DB / NT_ROWS), NT_SMEM, a, (const int32_t*)s->list.p, ob, (const double*)s->linv.p, (const int64_t*)s->linv_off.p);
-            cudaEventRecord(s->ev_near[k], S1);
-            if (last_bulk >= 0) cudaStreamWaitEvent(S1, s->ev_bulk[last_bulk], 0);     // R(k-1) also wrote the next diagonal block
-            launch_chain(k_near_syrk, dim3(10), NS_SMEM, a, (const int32_t*)s->list.p, ob);
-            if (inv_side) {
-                cudaStreamWaitEvent(S3, s->ev_diag[k], 0);
-                k_big_inv128<<<1, 256, sizeof(Diag128Smem), S3>>>(a, s->list.p, ob, s->linv.p, s->linv_off.p);
-                if (rem2 <= 0) { cudaEventRecord(s->ev_side[k], S3); last_side = k; }
-            }
-            if (rem2 > 0) {
-                if (!inv_side) cudaStreamWaitEvent(S3, s->ev_diag[k], 0);
-                k_big_trsm<<<dim3((rem2 + TR_ROWS - 1) / TR_ROWS, 1), 256, GU_SMEM, S3>>>(a, s->list.p, ob, s->linv.p, s->linv_off.p, DB / TR_ROWS);
-                if (relax) cudaEventRecord(s->ev_chain[k], S3);                        // (ev_chain is free on this path: "panel k's L is complete")
-                cudaStreamWaitEvent(S3, s->ev_near[k], 0);
-                if (last_bulk >= 0) cudaStreamWaitEvent(S3, s->ev_bulk[last_bulk], 0); // R(k-1) also wrote block column k+1
-                k_big_update_rows<<<dim3((rem2 + GU_M - 1) / GU_M, (DB + GU_N - 1) / GU_N, 1), 256, GU_SMEM, S3>>>(a, s->list.p, ob, DB, DB, 2 * DB, 1, 1);
-                cudaEventRecord(s->ev_side[k], S3);
-                last_side = k;
-                cudaStreamWaitEvent(S2, relax ? s->ev_chain[k] : s->ev_side[k], 0);
-                const int nbx = (rem2 + GU_M - 1) / GU_M, nby = (rem2 + GU_N - 1) / GU_N;
-                const int nres = (relax && rem2 >= 2048) ? std::max(n_reserved, early_reserved) : n_reserved;
-                k_big_update_dyn<<<2 * nsm, 256, GU_SMEM, S2>>>(a, s->list.p, ob, DB, 2 * DB, 1 << 30, 0, nbx, nby, s->tilecnt.p + k, nres);
-                cudaEventRecord(s->ev_bulk[k], S2);
-                last_bulk = k;
-            }
-            continue;
-        }
-        // general path (partial last blocks, or B2_DENSE_NEAR=0): whole-panel trsm and whole-column update on the chain
-        if (last_side >= 0) cudaStreamWaitEvent(S1, s->ev_side[last_side], 0);
-        k_big_trsm<<<dim3((rem + TR_ROWS - 1) / TR_ROWS, 1), 256, GU_SMEM, S1>>>(a, s->list.p, ob, s->linv.p, s->linv_off.p, 0);
-        if (last_bulk >= 0) cudaStreamWaitEvent(S1, s->ev_bulk[last_bulk], 0);       // R(k-1) also wrote block column k+1
-        k_big_update_pipe<<<dim3((rem1 + GU_M - 1) / GU_M, (DB + GU_N - 1) / GU_N, 1), 256, GU_SMEM, S1>>>(a, s->list.p, ob, DB, DB, 2 * DB, 1);
-        if (rem2 > 0) {
-            cudaEventRecord(s->ev_chain[k], S1);
-            cudaStreamWaitEvent(S2, s->ev_chain[k], 0);
-            const int nbx = (rem2 + GU_M - 1) / GU_M, nby = (rem2 + GU_N - 1) / GU_N;
-            k_big_update_dyn<<<2 * nsm, 256, GU_SMEM, S2>>>(a, s->list.p, ob, DB, 2 * DB, 1 << 30, 0, nbx, nby, s->tilecnt.p + k, n_reserved);
-            cudaEventRecord(s->ev_bulk[k], S2);
-            last_bulk = k;
-        }
-    }
-    if (last_bulk >= 0) cudaStreamWaitEvent(S1, s->ev_bulk[last_bulk], 0);           // join
-    if (last_side >= 0) cudaStreamWaitEvent(S1, s->ev_side[last_side], 0);
+    LookaheadCtx cx;
+    cx.S2 = s->aux_stream; cx.S3 = s->side_stream; cx.pool = &s->ev_pool; s->ev_next = 0; cx.next = &s->ev_next; cx.tilecnt = s->tilecnt.p;
+    enqueue_front_lookahead(a, s->list.p, N, N, s->linv.p, s->linv_off.p, cx, S1);
 }
 
 void enqueue_dense_factor(b2d_solver* s, cudaStream_t st) {
@@ -1199,17 +1284,6 @@ int b2d_create(int32_t N, int32_t lda, const double* A_d, const b2_options* opt,
         return cuda_fail(cudaGetLastError(), "b2d_create allocation", __FILE__, __LINE__);
     }
     if (set_smem_attrs() != B2_OK) { delete s; return B2_ERR_CUDA; }
-    {
-        const int nb = (N + DB - 1) / DB;
-        s->ev_chain.resize(nb); s->ev_bulk.resize(nb); s->ev_diag.resize(nb); s->ev_near.resize(nb); s->ev_side.resize(nb);
-        for (int k = 0; k < nb; ++k) {
-            if (cudaEventCreateWithFlags(&s->ev_chain[k], cudaEventDisableTiming) != cudaSuccess ||
-                cudaEventCreateWithFlags(&s->ev_diag[k], cudaEventDisableTiming) != cudaSuccess ||
-                cudaEventCreateWithFlags(&s->ev_near[k], cudaEventDisableTiming) != cudaSuccess ||
-                cudaEventCreateWithFlags(&s->ev_side[k], cudaEventDisableTiming) != cudaSuccess ||
-                cudaEventCreateWithFlags(&s->ev_bulk[k], cudaEventDisableTiming) != cudaSuccess) { delete s; return cuda_fail(cudaGetLastError(), "b2d_create events", __FILE__, __LINE__); }
-        }
-    }
     *out = s;
     return B2_OK;
 }

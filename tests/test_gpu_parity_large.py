@@ -152,9 +152,11 @@ def _product_perm(N, cp, rv, **opts):
     return perm
 
 
-@pytest.mark.parametrize("nx", [32])
-def test_augmented_grid_delta_1e8_against_the_ldl_oracle(nx):
-    """SparseKKTSystem-style quasi-definite matrix with delta = 1e-8, big (HBM-resident) fronts: inertia
+@pytest.mark.parametrize("nx,la_min_w", [(32, None), (32, 0)])
+def test_augmented_grid_delta_1e8_against_the_ldl_oracle(nx, la_min_w, monkeypatch):
+    """(la_min_w = None: fronts with >= 512 pivot columns are factorised with the three-branch look-ahead schedule -- the 32^2 and
+    32 x 16 separators here; 0: every big front through the level-batched launches.)
+    SparseKKTSystem-style quasi-definite matrix with delta = 1e-8, big (HBM-resident) fronts: inertia
     identical to the LDL^T oracle (src/LinearSolvers/ldl.jl restated) and the solution after Richardson refinement on K x = b
     within 1e-6 of the oracle's refined solution.  The oracle is the scalar up-looking LDL^T (no supernodes, no amalgamation, a
     different summation order) run in the product's nested-dissection order -- a minimum-degree order costs it 160 s at 30^3, and
@@ -163,6 +165,8 @@ def test_augmented_grid_delta_1e8_against_the_ldl_oracle(nx):
     _need_gpu()
     from madnlp_jl_b200.linear_solvers import B200SparseSolver, DeviceCSC
     from madnlp_jl_b200 import kkt as K
+    if la_min_w is not None:
+        monkeypatch.setenv("B2_LOOKAHEAD_MIN_W", str(la_min_w))
     N, n_tot, m, I, J, V = W.augmented_grid_kkt(nx, nx, nx, delta=1e-8)
     cp, rv, mp = o.coo_to_csc(I, J, N, N)
     nz = np.zeros(len(rv)); o.transfer(nz, V, mp)
