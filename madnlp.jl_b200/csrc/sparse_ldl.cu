@@ -485,8 +485,10 @@ int capture(b2_solver* s, cudaGraphExec_t* out, Fn fn) {
 }
 
 void build_schedule(b2_solver* s) {
-    // fronts with at least this many pivot columns get the look-ahead schedule (B2_LOOKAHEAD_MIN_W, 0 = off)
-    int la_min_w = 512, la_tiles = 0;
+    // fronts with at least this many pivot columns get the look-ahead schedule (B2_LOOKAHEAD_MIN_W; 0 = off, the default: on the 64^3
+    // augmented grid one front at a time with look-ahead measured 52.6 ms against 51.2 ms for the level-batched launches, whose
+    // diagonal-block kernels already run side by side across the fronts of a level -- profiles/r02_c5_lookahead.txt)
+    int la_min_w = 0, la_tiles = 0;
     if (const char* e = getenv("B2_LOOKAHEAD_MIN_W")) la_min_w = atoi(e);
     const Symbolic& S = s->S;
     const int ns = S.nsuper;

@@ -152,10 +152,10 @@ def _product_perm(N, cp, rv, **opts):
     return perm
 
 
-@pytest.mark.parametrize("nx,la_min_w", [(32, None), (32, 0)])
+@pytest.mark.parametrize("nx,la_min_w", [(32, None), (32, 512)])
 def test_augmented_grid_delta_1e8_against_the_ldl_oracle(nx, la_min_w, monkeypatch):
-    """(la_min_w = None: fronts with >= 512 pivot columns are factorised with the three-branch look-ahead schedule -- the 32^2 and
-    32 x 16 separators here; 0: every big front through the level-batched launches.)
+    """(la_min_w = None: every big front through the level-batched launches, the default; 512: fronts with >= 512 pivot columns are
+    factorised one at a time with the three-branch look-ahead schedule the dense solver uses -- the 32^2 and 32 x 16 separators here.)
     SparseKKTSystem-style quasi-definite matrix with delta = 1e-8, big (HBM-resident) fronts: inertia
     identical to the LDL^T oracle (src/LinearSolvers/ldl.jl restated) and the solution after Richardson refinement on K x = b
     within 1e-6 of the oracle's refined solution.  The oracle is the scalar up-looking LDL^T (no supernodes, no amalgamation, a
