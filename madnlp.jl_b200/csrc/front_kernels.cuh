@@ -267,6 +267,12 @@ __device__ __forceinline__ void cp_async_wait_group_n() { asm volatile("cp.async
 
 // one 128 x 64 tile (bx, by) of the update; `gu_sm` is the CTA's dynamic shared memory (GU_SMEM bytes).  Returns without work for
 // tiles above the diagonal / outside the column range.  All threads of the CTA must call it together.
+template <bool NAMED>
+__device__ __forceinline__ void gu_sync() {           // NAMED: only the 256 consumer threads of a 288-thread CTA (barrier id 1)
+    if (NAMED) asm volatile("bar.sync 1, 256;" ::: "memory");
+    else __syncthreads();
+}
+template <bool NAMED = false>
 __device__ __forceinline__ void big_update_tile(const FactorArgs& a, const FrontDesc& d, int kb0, int kmax, int jlo_rel, int jhi_rel, int clip_jlo,
                                                 int bx, int by, double* gu_sm) {
     if (kb0 >= d.w) return;
@@ -319,7 +325,7 @@ __device__ __forceinline__ void big_update_tile(const FactorArgs& a, const Front
         for (int y = 0; y < 4; ++y) c[x][y][0] = c[x][y][1] = 0.0;
     for (int ch = 0; ch < nchunk; ++ch) {
         cp_async_wait_group_n<GU_STAGES - 2>();
-        __syncthreads();                                              // slice ch landed; slice ch-1 fully consumed
+        gu_sync<NAMED>();                                              // slice ch landed; slice ch-1 fully consumed
         if (ch + GU_STAGES - 1 < nchunk) issue(ch + GU_STAGES - 1);
         cp_async_commit_group();
         const double* Ab = As + (size_t)(ch % GU_STAGES) * GU_K * GU_LDA;
@@ -344,7 +350,7 @@ __device__ __forceinline__ void big_update_tile(const FactorArgs& a, const Front
     // epilogue: accumulators -> shared memory (column-major tile), then a coalesced read-modify-write of C with all of
     // a thread's loads in flight at once (the fragment layout would make it 32 dependent 8-byte round trips per thread)
     cp_async_wait_group_n<0>();
-    __syncthreads();
+    gu_sync<NAMED>();
     double* Cs = gu_sm;                                               // [GU_N][GU_LDC]
 #pragma unroll
     for (int x = 0; x < 4; ++x)
@@ -352,7 +358,7 @@ __device__ __forceinline__ void big_update_tile(const FactorArgs& a, const Front
         for (int y = 0; y < 4; ++y)
 #pragma unroll
             for (int e = 0; e < 2; ++e) Cs[(wj + 8 * y + 2 * q + e) * GU_LDC + wi + 8 * x + g] = c[x][y][e];
-    __syncthreads();
+    gu_sync<NAMED>();
     const int r = f - d.w;
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
@@ -418,6 +424,198 @@ __global__ void __launch_bounds__(256, 2) k_big_update_dyn(FactorArgs a, const i
         const int t = t_sh;
         if (t >= ntile) { trace_exit(a, 8 * (kb0 / 128) + TR_BULK); return; }
         big_update_tile(a, d, kb0, kmax, jlo_rel, jhi_rel, clip_jlo, t % nbx, t / nbx, gu_sm);
+    }
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// The same 128 x 64 tile with operands staged by the TMA unit: 1-D bulk copies (cp.async.bulk.shared::cluster.global, one per
+// K-row of each operand: 1 KB of A, 512 B of B) issued by a ninth, producer warp into the same 4-stage ring, completion counted in
+// bytes on one mbarrier per stage ("full"); the eight consumer warps release a stage through a second mbarrier ("empty", one
+// arrival per warp) instead of a CTA-wide barrier per K-slice, so no warp ever waits for its siblings inside the K loop and no
+// consumer thread issues copies (12 cp.async per thread and slice before).  Requirements, checked per tile: every K-row of both
+// operands starts on a 16-byte boundary and spans an even number of doubles (f even), whole K-slices (kcount % 16 == 0).  Tiles
+// that do not qualify run the cp.async version on the consumer threads.  `it` counts the K-slices this CTA has pushed through the
+// ring since the barriers were initialised (stage = it % 4, phase parity = (it / 4) & 1); it is uniform over the CTA.
+// ----------------------------------------------------------------------------------------------------------
+constexpr int GU_NT_BULK = 288;
+constexpr size_t GU_SMEM_BULK = GU_SMEM + 2 * GU_STAGES * sizeof(unsigned long long);
+__device__ __forceinline__ unsigned gu_s32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void gu_mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(gu_s32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void gu_mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(gu_s32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void gu_mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(gu_s32(bar)) : "memory");
+}
+__device__ __forceinline__ void gu_mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "GU_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra GU_DONE;\n"
+        "bra GU_WAIT;\n"
+        "GU_DONE:\n"
+        "}\n" ::"r"(gu_s32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void gu_bulk_g2s(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(gu_s32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(gu_s32(bar)) : "memory");
+}
+
+// All 288 threads of the CTA call this together; the caller separates consecutive tiles by a CTA-wide barrier.
+__device__ __forceinline__ void big_update_tile_bulk(const FactorArgs& a, const FrontDesc& d, int kb0, int kmax, int jlo_rel, int jhi_rel,
+                                                     int clip_jlo, int bx, int by, double* gu_sm, unsigned& it) {
+    if (kb0 >= d.w) return;
+    const int f = d.f;
+    const int kcount = min(kmax, d.w - kb0);
+    const int jlo = kb0 + (clip_jlo ? min(jlo_rel, kcount) : jlo_rel);
+    const int jhi = min(f, kb0 + jhi_rel);
+    const int i0 = jlo + bx * GU_M, j0 = jlo + by * GU_N;
+    if (j0 > i0 + GU_M - 1 || i0 >= f || j0 >= jhi) return;          // tile above the diagonal / outside the front
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const double* Lp = a.L + d.lp_off;
+    const bool bulk_ok = (f & 1) == 0 && (kcount & (GU_K - 1)) == 0 && (i0 & 1) == 0 && (j0 & 1) == 0 &&
+                         ((reinterpret_cast<size_t>(Lp) & 15) == 0);
+    if (!bulk_ok) {                                                   // (uniform over the CTA)
+        if (warp < 8) big_update_tile<true>(a, d, kb0, kmax, jlo_rel, jhi_rel, clip_jlo, bx, by, gu_sm);
+        return;
+    }
+    double* As = gu_sm;                                               // [stage][k][GU_LDA]
+    double* Bs = gu_sm + GU_STAGES * GU_K * GU_LDA;                   // [stage][k][GU_LDB]
+    double* dneg = Bs + GU_STAGES * GU_K * GU_LDB;                    // -d_k
+    unsigned long long* full = reinterpret_cast<unsigned long long*>(dneg + 128);
+    unsigned long long* empty = full + GU_STAGES;
+    const int nchunk = kcount / GU_K;
+    const unsigned it0 = it;
+    it += nchunk;
+    if (warp == 8) {
+        // ---- producer warp: lane l < 16 moves K-row l of both operands of a slice
+        const unsigned bytesA = 8u * (unsigned)min(GU_M, f - i0), bytesB = 8u * (unsigned)min(GU_N, f - j0);
+        for (int ch = 0; ch < nchunk; ++ch) {
+            const unsigned g = it0 + ch, st = g % GU_STAGES;
+            if (g >= GU_STAGES) gu_mbar_wait(&empty[st], ((g / GU_STAGES) - 1) & 1);   // every consumer warp has left the stage's previous slice
+            if (lane == 0) gu_mbar_expect_tx(&full[st], GU_K * (bytesA + bytesB));
+            __syncwarp();
+            if (lane < GU_K) {
+                const size_t col = (size_t)(kb0 + ch * GU_K + lane) * f;
+                gu_bulk_g2s(As + ((size_t)st * GU_K + lane) * GU_LDA, Lp + col + i0, bytesA, &full[st]);
+                gu_bulk_g2s(Bs + ((size_t)st * GU_K + lane) * GU_LDB, Lp + col + j0, bytesB, &full[st]);
+            }
+        }
+        return;
+    }
+    // ---- consumers
+    const int g = lane >> 2, q = lane & 3;
+    const int wi = (warp & 3) * 32, wj = (warp >> 2) * 32;
+    if (tid < 128) dneg[tid] = (tid < kcount) ? -Lp[(size_t)(kb0 + tid) * f + kb0 + tid] : 0.0;
+    gu_sync<true>();
+    double c[4][4][2];
+#pragma unroll
+    for (int x = 0; x < 4; ++x)
+#pragma unroll
+        for (int y = 0; y < 4; ++y) c[x][y][0] = c[x][y][1] = 0.0;
+    for (int ch = 0; ch < nchunk; ++ch) {
+        const unsigned gi = it0 + ch, st = gi % GU_STAGES;
+        gu_mbar_wait(&full[st], (gi / GU_STAGES) & 1);
+        const double* Ab = As + (size_t)st * GU_K * GU_LDA;
+        const double* Bb = Bs + (size_t)st * GU_K * GU_LDB;
+#pragma unroll
+        for (int k0 = 0; k0 < GU_K; k0 += 4) {
+            const double sc = dneg[ch * GU_K + k0 + q];
+            double af[4], bf[4];
+#pragma unroll
+            for (int x = 0; x < 4; ++x) af[x] = Ab[(k0 + q) * GU_LDA + wi + 8 * x + g] * sc;
+#pragma unroll
+            for (int y = 0; y < 4; ++y) bf[y] = Bb[(k0 + q) * GU_LDB + wj + 8 * y + g];
+#pragma unroll
+            for (int x = 0; x < 4; ++x)
+#pragma unroll
+                for (int y = 0; y < 4; ++y)
+                    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                                 : "+d"(c[x][y][0]), "+d"(c[x][y][1])
+                                 : "d"(af[x]), "d"(bf[y]));
+        }
+        __syncwarp();
+        if (lane == 0) gu_mbar_arrive(&empty[st]);
+    }
+    // epilogue (as in big_update_tile): every consumer has passed its last `full` wait, so all copies have landed; the producer
+    // cannot touch the ring again before the caller's CTA-wide barrier
+    gu_sync<true>();
+    double* Cs = gu_sm;                                               // [GU_N][GU_LDC]
+#pragma unroll
+    for (int x = 0; x < 4; ++x)
+#pragma unroll
+        for (int y = 0; y < 4; ++y)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) Cs[(wj + 8 * y + 2 * q + e) * GU_LDC + wi + 8 * x + g] = c[x][y][e];
+    gu_sync<true>();
+    const int r = f - d.w;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        double t[4][4];
+        double* colp[4];
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+            const int jj = warp * 8 + half * 4 + cc, j = j0 + jj;
+            colp[cc] = (j < d.w) ? a.L + d.lp_off + (size_t)j * f : a.ws + d.cb_off + (size_t)(j - d.w) * r - d.w;
+#pragma unroll
+            for (int rr = 0; rr < 4; ++rr) {
+                const int i = i0 + lane + 32 * rr;
+                t[cc][rr] = (j < jhi && i < f && i >= j) ? colp[cc][i] : 0.0;
+            }
+        }
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+            const int jj = warp * 8 + half * 4 + cc, j = j0 + jj;
+#pragma unroll
+            for (int rr = 0; rr < 4; ++rr) {
+                const int i = i0 + lane + 32 * rr;
+                if (j < jhi && i < f && i >= j) colp[cc][i] = t[cc][rr] + Cs[jj * GU_LDC + lane + 32 * rr];
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ void gu_bulk_setup(double* gu_sm) {
+    unsigned long long* full = reinterpret_cast<unsigned long long*>(gu_sm + GU_STAGES * GU_K * (GU_LDA + GU_LDB) + 128);
+    if (threadIdx.x < GU_STAGES) {
+        gu_mbar_init(&full[threadIdx.x], 1);
+        gu_mbar_init(&full[GU_STAGES + threadIdx.x], 8);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+}
+
+// k_big_update_pipe / k_big_update_dyn with bulk-copy operand staging (288 threads: 8 consumer warps + 1 producer warp)
+__global__ void __launch_bounds__(GU_NT_BULK, 2) k_big_update_pipe_bulk(FactorArgs a, const int32_t* __restrict__ list, int kb0, int kmax,
+                                                                       int jlo_rel, int jhi_rel, int clip_jlo) {
+    extern __shared__ __align__(16) double gu_sm[];
+    gu_bulk_setup(gu_sm);
+    const FrontDesc d = a.desc[list[blockIdx.z]];
+    unsigned it = 0;
+    big_update_tile_bulk(a, d, kb0, kmax, jlo_rel, jhi_rel, clip_jlo, blockIdx.x, blockIdx.y, gu_sm, it);
+}
+__global__ void __launch_bounds__(GU_NT_BULK, 2) k_big_update_dyn_bulk(FactorArgs a, const int32_t* __restrict__ list, int kb0, int kmax,
+                                                                      int jlo_rel, int jhi_rel, int clip_jlo, int nbx, int nby, int* tile_counter,
+                                                                      int n_reserved) {
+    extern __shared__ __align__(16) double gu_sm[];
+    __shared__ int t_sh;
+    if ((int)smid() < n_reserved) return;
+    gu_bulk_setup(gu_sm);
+    const FrontDesc d = a.desc[list[0]];
+    const int ntile = nbx * nby;
+    unsigned it = 0;
+    trace_enter(a, 8 * (kb0 / 128) + TR_BULK);
+    for (;;) {
+        __syncthreads();                                 // (the previous tile's epilogue has finished with shared memory)
+        if (threadIdx.x == 0) t_sh = atomicAdd(tile_counter, 1);
+        __syncthreads();
+        const int t = t_sh;
+        if (t >= ntile) { trace_exit(a, 8 * (kb0 / 128) + TR_BULK); return; }
+        big_update_tile_bulk(a, d, kb0, kmax, jlo_rel, jhi_rel, clip_jlo, t % nbx, t / nbx, gu_sm, it);
     }
 }
 

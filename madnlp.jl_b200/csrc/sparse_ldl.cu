@@ -100,6 +100,10 @@ struct b2_solver {
 namespace {
 
 // one outer step of every big front in `lb`: diagonal block (factor + inverse), rows below, trailing update
+inline bool lookahead_bulk() {
+    static const bool on = [] { const char* e = getenv("B2_UPDATE_BULK"); return e && atoi(e) != 0; }();
+    return on;
+}
 void launch_big_step(const FactorArgs& a, const int32_t* lb, int nfronts, int ob, int maxf, double* Linv, const int64_t* linv_off,
                      cudaStream_t st, int64_t* nl) {
     static bool attr = false;
@@ -114,6 +118,11 @@ void launch_big_step(const FactorArgs& a, const int32_t* lb, int nfronts, int ob
     const int rem = maxf - ob - 1;                  // rows below the first pivot of the block (upper bound over the fronts)
     if (rem <= 0) return;
     k_big_trsm<<<dim3((rem + TR_ROWS - 1) / TR_ROWS, nfronts), 256, GU_SMEM, st>>>(a, lb, ob, Linv, linv_off, 0);
+    if (lookahead_bulk()) {
+        static bool battr = false;
+        if (!battr) { cudaFuncSetAttribute(k_big_update_pipe_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GU_SMEM_BULK); battr = true; }
+        k_big_update_pipe_bulk<<<dim3((rem + GU_M - 1) / GU_M, (rem + GU_N - 1) / GU_N, nfronts), GU_NT_BULK, GU_SMEM_BULK, st>>>(a, lb, ob, DB, DB, 1 << 30, 1);
+    } else
     k_big_update_pipe<<<dim3((rem + GU_M - 1) / GU_M, (rem + GU_N - 1) / GU_N, nfronts), 256, GU_SMEM, st>>>(a, lb, ob, DB, DB, 1 << 30, 1);
     if (nl) *nl += 2;
 }
@@ -147,7 +156,7 @@ struct LookaheadCtx {
     }
 };
 
-struct LookaheadKnobs { int n_reserved, inv_side, use_near, relax, early_reserved, chain_pdl; };
+struct LookaheadKnobs { int n_reserved, inv_side, use_near, relax, early_reserved, chain_pdl, bulk; };
 const LookaheadKnobs& lookahead_knobs() {
     static LookaheadKnobs K = [] {
         LookaheadKnobs k;
@@ -163,6 +172,8 @@ const LookaheadKnobs& lookahead_knobs() {
         k.early_reserved = std::max(1, geti("B2_DENSE_EARLY_RESERVED", 4));
         // chain kernels launched programmatically dependent on their stream predecessor (each of them starts with pdl_sync())
         k.chain_pdl = geti("B2_DENSE_PDL", 0) != 0;
+        // trailing updates with TMA bulk-copy operand staging + mbarrier ring + producer warp (front_kernels.cuh: big_update_tile_bulk)
+        k.bulk = geti("B2_UPDATE_BULK", 0) != 0;
         return k;
     }();
     return K;
@@ -176,6 +187,8 @@ void lookahead_attrs() {
     cudaFuncSetAttribute(k_big_update_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GU_SMEM);
     cudaFuncSetAttribute(k_big_update_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GU_SMEM);
     cudaFuncSetAttribute(k_big_update_dyn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GU_SMEM);
+    cudaFuncSetAttribute(k_big_update_dyn_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GU_SMEM_BULK);
+    cudaFuncSetAttribute(k_big_update_pipe_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GU_SMEM_BULK);
     cudaFuncSetAttribute(k_near_trsm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NT_SMEM);
     cudaFuncSetAttribute(k_near_syrk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NS_SMEM);
     cudaFuncSetAttribute(k_near_trsv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NV_SMEM);
@@ -235,7 +248,8 @@ int64_t enqueue_front_lookahead(const FactorArgs& a, const int32_t* list1, int f
                 cudaStreamWaitEvent(S2, K.relax ? ev_panel : ev_side, 0);
                 const int nbx = (rem2 + GU_M - 1) / GU_M, nby = (rem2 + GU_N - 1) / GU_N;
                 const int nres = (K.relax && rem2 >= 2048) ? std::max(K.n_reserved, K.early_reserved) : K.n_reserved;
-                k_big_update_dyn<<<2 * nsm, 256, GU_SMEM, S2>>>(a, list1, ob, DB, 2 * DB, 1 << 30, 0, nbx, nby, cx.tilecnt + k, nres);
+                if (K.bulk) k_big_update_dyn_bulk<<<2 * nsm, GU_NT_BULK, GU_SMEM_BULK, S2>>>(a, list1, ob, DB, 2 * DB, 1 << 30, 0, nbx, nby, cx.tilecnt + k, nres);
+                else k_big_update_dyn<<<2 * nsm, 256, GU_SMEM, S2>>>(a, list1, ob, DB, 2 * DB, 1 << 30, 0, nbx, nby, cx.tilecnt + k, nres);
                 ev_bulk = cx.ev();
                 cudaEventRecord(ev_bulk, S2);
                 nl += 3;
@@ -254,7 +268,8 @@ int64_t enqueue_front_lookahead(const FactorArgs& a, const int32_t* list1, int f
             cudaEventRecord(ev_chain, S1);
             cudaStreamWaitEvent(S2, ev_chain, 0);
             const int nbx = (rem2 + GU_M - 1) / GU_M, nby = (rem2 + GU_N - 1) / GU_N;
-            k_big_update_dyn<<<2 * nsm, 256, GU_SMEM, S2>>>(a, list1, ob, DB, 2 * DB, 1 << 30, 0, nbx, nby, cx.tilecnt + k, K.n_reserved);
+            if (K.bulk) k_big_update_dyn_bulk<<<2 * nsm, GU_NT_BULK, GU_SMEM_BULK, S2>>>(a, list1, ob, DB, 2 * DB, 1 << 30, 0, nbx, nby, cx.tilecnt + k, K.n_reserved);
+                else k_big_update_dyn<<<2 * nsm, 256, GU_SMEM, S2>>>(a, list1, ob, DB, 2 * DB, 1 << 30, 0, nbx, nby, cx.tilecnt + k, K.n_reserved);
             ev_bulk = cx.ev();
             cudaEventRecord(ev_bulk, S2);
             ++nl;
