@@ -432,9 +432,12 @@ __global__ void __launch_bounds__(256, 2) k_big_update_dyn(FactorArgs a, const i
 // K-row of each operand: 1 KB of A, 512 B of B) issued by a ninth, producer warp into the same 4-stage ring, completion counted in
 // bytes on one mbarrier per stage ("full"); the eight consumer warps release a stage through a second mbarrier ("empty", one
 // arrival per warp) instead of a CTA-wide barrier per K-slice, so no warp ever waits for its siblings inside the K loop and no
-// consumer thread issues copies (12 cp.async per thread and slice before).  Requirements, checked per tile: every K-row of both
-// operands starts on a 16-byte boundary and spans an even number of doubles (f even), whole K-slices (kcount % 16 == 0).  Tiles
-// that do not qualify run the cp.async version on the consumer threads.  `it` counts the K-slices this CTA has pushed through the
+// consumer thread issues copies (12 cp.async per thread and slice before).  Bulk copies move multiples of 16 bytes between
+// 16-byte aligned addresses, but a K-row of a front starts at element lp_off + k f + i0 of the factor array -- odd for every
+// other row when f is odd.  Such a row is copied from the element BEFORE it (one extra pair at the end when needed), so its data
+// sits one slot to the right in the shared-memory row (LDA has the room); since K-slices hold 16 rows and a lane always reads
+// rows k = q (mod 4), that shift is a per-lane constant folded into the operand base pointers.  Requirement, checked per tile:
+// whole K-slices (kcount % 16 == 0); other tiles run the cp.async version on the consumer threads.  `it` counts the K-slices this CTA has pushed through the
 // ring since the barriers were initialised (stage = it % 4, phase parity = (it / 4) & 1); it is uniform over the CTA.
 // ----------------------------------------------------------------------------------------------------------
 constexpr int GU_NT_BULK = 288;
@@ -477,8 +480,7 @@ __device__ __forceinline__ void big_update_tile_bulk(const FactorArgs& a, const 
     if (j0 > i0 + GU_M - 1 || i0 >= f || j0 >= jhi) return;          // tile above the diagonal / outside the front
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const double* Lp = a.L + d.lp_off;
-    const bool bulk_ok = (f & 1) == 0 && (kcount & (GU_K - 1)) == 0 && (i0 & 1) == 0 && (j0 & 1) == 0 &&
-                         ((reinterpret_cast<size_t>(Lp) & 15) == 0);
+    const bool bulk_ok = (kcount & (GU_K - 1)) == 0 && (reinterpret_cast<size_t>(a.L) & 15) == 0;
     if (!bulk_ok) {                                                   // (uniform over the CTA)
         if (warp < 8) big_update_tile<true>(a, d, kb0, kmax, jlo_rel, jhi_rel, clip_jlo, bx, by, gu_sm);
         return;
@@ -493,16 +495,21 @@ __device__ __forceinline__ void big_update_tile_bulk(const FactorArgs& a, const 
     it += nchunk;
     if (warp == 8) {
         // ---- producer warp: lane l < 16 moves K-row l of both operands of a slice
-        const unsigned bytesA = 8u * (unsigned)min(GU_M, f - i0), bytesB = 8u * (unsigned)min(GU_N, f - j0);
+        const int na = min(GU_M, f - i0), nb_ = min(GU_N, f - j0);
         for (int ch = 0; ch < nchunk; ++ch) {
             const unsigned g = it0 + ch, st = g % GU_STAGES;
             if (g >= GU_STAGES) gu_mbar_wait(&empty[st], ((g / GU_STAGES) - 1) & 1);   // every consumer warp has left the stage's previous slice
-            if (lane == 0) gu_mbar_expect_tx(&full[st], GU_K * (bytesA + bytesB));
+            // row `lane` of the slice: absolute element index of its first entry, rounded down to a 16-byte boundary
+            const size_t eA = (size_t)d.lp_off + (size_t)(kb0 + ch * GU_K + (lane & (GU_K - 1))) * f + i0;
+            const size_t eB = eA - i0 + j0;
+            const unsigned pA = (unsigned)(eA & 1), pB = (unsigned)(eB & 1);
+            const unsigned bytesA = 8u * ((na + pA + 1u) & ~1u), bytesB = 8u * ((nb_ + pB + 1u) & ~1u);
+            const unsigned total = __reduce_add_sync(0xffffffffu, lane < GU_K ? bytesA + bytesB : 0u);
+            if (lane == 0) gu_mbar_expect_tx(&full[st], total);
             __syncwarp();
             if (lane < GU_K) {
-                const size_t col = (size_t)(kb0 + ch * GU_K + lane) * f;
-                gu_bulk_g2s(As + ((size_t)st * GU_K + lane) * GU_LDA, Lp + col + i0, bytesA, &full[st]);
-                gu_bulk_g2s(Bs + ((size_t)st * GU_K + lane) * GU_LDB, Lp + col + j0, bytesB, &full[st]);
+                gu_bulk_g2s(As + ((size_t)st * GU_K + lane) * GU_LDA, a.L + (eA - pA), bytesA, &full[st]);
+                gu_bulk_g2s(Bs + ((size_t)st * GU_K + lane) * GU_LDB, a.L + (eB - pB), bytesB, &full[st]);
             }
         }
         return;
@@ -512,6 +519,8 @@ __device__ __forceinline__ void big_update_tile_bulk(const FactorArgs& a, const 
     const int wi = (warp & 3) * 32, wj = (warp >> 2) * 32;
     if (tid < 128) dneg[tid] = (tid < kcount) ? -Lp[(size_t)(kb0 + tid) * f + kb0 + tid] : 0.0;
     gu_sync<true>();
+    // this lane reads rows k = q (mod 4) only: their alignment shift (see the producer) is a constant of the lane
+    const int shA = (int)(((size_t)d.lp_off + (size_t)(kb0 + q) * f + i0) & 1), shB = (int)(((size_t)d.lp_off + (size_t)(kb0 + q) * f + j0) & 1);
     double c[4][4][2];
 #pragma unroll
     for (int x = 0; x < 4; ++x)
@@ -520,8 +529,8 @@ __device__ __forceinline__ void big_update_tile_bulk(const FactorArgs& a, const 
     for (int ch = 0; ch < nchunk; ++ch) {
         const unsigned gi = it0 + ch, st = gi % GU_STAGES;
         gu_mbar_wait(&full[st], (gi / GU_STAGES) & 1);
-        const double* Ab = As + (size_t)st * GU_K * GU_LDA;
-        const double* Bb = Bs + (size_t)st * GU_K * GU_LDB;
+        const double* Ab = As + (size_t)st * GU_K * GU_LDA + shA;
+        const double* Bb = Bs + (size_t)st * GU_K * GU_LDB + shB;
 #pragma unroll
         for (int k0 = 0; k0 < GU_K; k0 += 4) {
             const double sc = dneg[ch * GU_K + k0 + q];

@@ -834,7 +834,7 @@ int create_common(int32_t n, int64_t nnz, const int32_t* colptr_h, const int32_t
             }
             B2_CUDA_THROW(s->d_childrec.upload(cr.data(), cr.size()));
         }
-        B2_CUDA_THROW(s->d_L.alloc((size_t)S.lp_off[ns]));
+        B2_CUDA_THROW(s->d_L.alloc((size_t)S.lp_off[ns] + 2));          // (+2: the bulk-copy staging may read one aligned pair past a panel)
         B2_CUDA_THROW(s->d_Lt.alloc((size_t)S.lp_off[ns]));
         {
             const int wmax_ = std::min(W_MAX, s->opt.small_front_max);
@@ -1176,7 +1176,7 @@ int b2_debug_profile_front(b2_solver* s, int32_t sn, int32_t reps, int64_t* stam
 int b2_debug_get_factor(b2_solver* s, double* lval_h, double* dvec_h) {
     if (!s || s->symbolic_only) return B2_ERR_INVALID;
     B2_CUDA(cudaDeviceSynchronize());
-    if (lval_h) B2_CUDA(cudaMemcpy(lval_h, s->d_L.p, s->d_L.bytes(), cudaMemcpyDeviceToHost));
+    if (lval_h) B2_CUDA(cudaMemcpy(lval_h, s->d_L.p, (size_t)s->S.lp_off[s->S.nsuper] * sizeof(double), cudaMemcpyDeviceToHost));
     if (dvec_h) B2_CUDA(cudaMemcpy(dvec_h, s->d_dvec.p, s->d_dvec.bytes(), cudaMemcpyDeviceToHost));
     return B2_OK;
 }
@@ -1287,7 +1287,7 @@ int b2d_create(int32_t N, int32_t lda, const double* A_d, const b2_options* opt,
     int32_t zero = 0;
     int64_t zero64 = 0;
     if (s->side.alloc(N) != cudaSuccess || s->linv.alloc((size_t)((N + BS - 1) / BS) * BS * BS) != cudaSuccess || s->linv_off.upload(&zero64, 1) != cudaSuccess ||
-        s->fact.alloc((size_t)N * N) != cudaSuccess || s->dvec.alloc(N) != cudaSuccess ||
+        s->fact.alloc((size_t)N * N + 2) != cudaSuccess || s->dvec.alloc(N) != cudaSuccess ||
         s->flow.alloc((size_t)2 * ((N + BS - 1) / BS) * BS) != cudaSuccess || s->desc.upload(&d, 1) != cudaSuccess ||
         s->list.upload(&zero, 1) != cudaSuccess || s->counters.alloc(4) != cudaSuccess ||
         cudaMallocHost((void**)&s->h_counters, 4 * sizeof(int32_t)) != cudaSuccess ||
