@@ -101,7 +101,7 @@ namespace {
 
 // one outer step of every big front in `lb`: diagonal block (factor + inverse), rows below, trailing update
 inline bool lookahead_bulk() {
-    static const bool on = [] { const char* e = getenv("B2_UPDATE_BULK"); return e && atoi(e) != 0; }();
+    static const bool on = [] { const char* e = getenv("B2_UPDATE_BULK"); return !e || atoi(e) != 0; }();
     return on;
 }
 void launch_big_step(const FactorArgs& a, const int32_t* lb, int nfronts, int ob, int maxf, double* Linv, const int64_t* linv_off,
@@ -156,7 +156,7 @@ struct LookaheadCtx {
     }
 };
 
-struct LookaheadKnobs { int n_reserved, inv_side, use_near, relax, early_reserved, chain_pdl, bulk; };
+struct LookaheadKnobs { int n_reserved, inv_side, use_near, relax, early_reserved, chain_pdl, bulk, depth2; };
 const LookaheadKnobs& lookahead_knobs() {
     static LookaheadKnobs K = [] {
         LookaheadKnobs k;
@@ -173,7 +173,11 @@ const LookaheadKnobs& lookahead_knobs() {
         // chain kernels launched programmatically dependent on their stream predecessor (each of them starts with pdl_sync())
         k.chain_pdl = geti("B2_DENSE_PDL", 0) != 0;
         // trailing updates with TMA bulk-copy operand staging + mbarrier ring + producer warp (front_kernels.cuh: big_update_tile_bulk)
-        k.bulk = geti("B2_UPDATE_BULK", 0) != 0;
+        k.bulk = geti("B2_UPDATE_BULK", 1) != 0;
+        // B2_DENSE_DEPTH2=1: the side branch updates TWO block columns (k+1, k+2) and the bulk update starts at k+3, so the next diagonal
+        // block only waits for the bulk update of two panels back: the chain of panel k+1 (and its panel trsm) runs a whole bulk period
+        // ahead and R(k+1) can follow R(k) without a gap while the trailing update is long
+        k.depth2 = geti("B2_DENSE_DEPTH2", 0) != 0;
         return k;
     }();
     return K;
@@ -210,6 +214,8 @@ int64_t enqueue_front_lookahead(const FactorArgs& a, const int32_t* list1, int f
         ++nl;
     };
     cudaEvent_t ev_bulk = nullptr, ev_side = nullptr;            // most recent R(.) / side-branch completion
+    cudaEvent_t ev_bulk_prev = nullptr;                          // R(.) before the most recent one (depth-2 look-ahead)
+    const int cw = K.depth2 ? 2 * DB : DB;                       // columns the side branch updates per panel
     for (int k = 0; k < nb; ++k) {
         const int ob = k * DB;
         const int nbk = std::min(DB, w - ob);                    // pivots of this block column
@@ -227,7 +233,10 @@ int64_t enqueue_front_lookahead(const FactorArgs& a, const int32_t* list1, int f
             if (K.inv_side) launch_chain(k_near_trsv, dim3(DB / NT_ROWS), NV_SMEM, a, list1, ob);
             else launch_chain(k_near_trsm, dim3(DB / NT_ROWS), NT_SMEM, a, list1, ob, (const double*)Linv, linv_off);
             cudaEventRecord(ev_near, S1);
-            if (ev_bulk) cudaStreamWaitEvent(S1, ev_bulk, 0);                          // R(k-1) also wrote the next diagonal block
+            // R(k-1) also wrote the next diagonal block -- unless the side branch covers two block columns: then R(k-1) starts at
+            // block column k+2 and the last bulk writer of this tile is R(k-2)
+            if (K.depth2) { if (ev_bulk_prev) cudaStreamWaitEvent(S1, ev_bulk_prev, 0); }
+            else if (ev_bulk) cudaStreamWaitEvent(S1, ev_bulk, 0);
             launch_chain(k_near_syrk, dim3(10), NS_SMEM, a, list1, ob);
             if (K.inv_side) {
                 cudaStreamWaitEvent(S3, ev_diag, 0);
@@ -241,18 +250,23 @@ int64_t enqueue_front_lookahead(const FactorArgs& a, const int32_t* list1, int f
                 cudaEvent_t ev_panel = nullptr;
                 if (K.relax) { ev_panel = cx.ev(); cudaEventRecord(ev_panel, S3); }    // "panel k's L is complete"
                 cudaStreamWaitEvent(S3, ev_near, 0);
-                if (ev_bulk) cudaStreamWaitEvent(S3, ev_bulk, 0);                      // R(k-1) also wrote block column k+1
-                k_big_update_rows<<<dim3((rem2 + GU_M - 1) / GU_M, (DB + GU_N - 1) / GU_N, 1), 256, GU_SMEM, S3>>>(a, list1, ob, DB, DB, 2 * DB, 1, 1);
+                if (ev_bulk) cudaStreamWaitEvent(S3, ev_bulk, 0);                      // R(k-1) also wrote these block columns
+                k_big_update_rows<<<dim3((rem2 + GU_M - 1) / GU_M, (cw + GU_N - 1) / GU_N, 1), 256, GU_SMEM, S3>>>(a, list1, ob, DB, DB, DB + cw, 1, 1);
                 ev_side = cx.ev();
                 cudaEventRecord(ev_side, S3);
-                cudaStreamWaitEvent(S2, K.relax ? ev_panel : ev_side, 0);
-                const int nbx = (rem2 + GU_M - 1) / GU_M, nby = (rem2 + GU_N - 1) / GU_N;
-                const int nres = (K.relax && rem2 >= 2048) ? std::max(K.n_reserved, K.early_reserved) : K.n_reserved;
-                if (K.bulk) k_big_update_dyn_bulk<<<2 * nsm, GU_NT_BULK, GU_SMEM_BULK, S2>>>(a, list1, ob, DB, 2 * DB, 1 << 30, 0, nbx, nby, cx.tilecnt + k, nres);
-                else k_big_update_dyn<<<2 * nsm, 256, GU_SMEM, S2>>>(a, list1, ob, DB, 2 * DB, 1 << 30, 0, nbx, nby, cx.tilecnt + k, nres);
-                ev_bulk = cx.ev();
-                cudaEventRecord(ev_bulk, S2);
-                nl += 3;
+                nl += 2;
+                const int remb = f - (ob + DB + cw);                                   // columns left to the bulk branch
+                if (remb > 0) {
+                    cudaStreamWaitEvent(S2, K.relax ? ev_panel : ev_side, 0);
+                    const int nbx = (remb + GU_M - 1) / GU_M, nby = (remb + GU_N - 1) / GU_N;
+                    const int nres = (K.relax && remb >= 2048) ? std::max(K.n_reserved, K.early_reserved) : K.n_reserved;
+                    if (K.bulk) k_big_update_dyn_bulk<<<2 * nsm, GU_NT_BULK, GU_SMEM_BULK, S2>>>(a, list1, ob, DB, DB + cw, 1 << 30, 0, nbx, nby, cx.tilecnt + k, nres);
+                    else k_big_update_dyn<<<2 * nsm, 256, GU_SMEM, S2>>>(a, list1, ob, DB, DB + cw, 1 << 30, 0, nbx, nby, cx.tilecnt + k, nres);
+                    ev_bulk_prev = ev_bulk;
+                    ev_bulk = cx.ev();
+                    cudaEventRecord(ev_bulk, S2);
+                    ++nl;
+                }
             }
             continue;
         }
