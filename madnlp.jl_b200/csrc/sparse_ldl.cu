@@ -369,11 +369,12 @@ int64_t enqueue_factor(b2_solver* s, int ph, cudaStream_t st) {
         if (lv.nB) {
             const int32_t* lb = sched + lv.offB;
             const int nsm = sm_count();
-            k_big_zero<<<dim3(std::max(1, 2 * nsm / lv.nB), lv.nB), 256, 0, st>>>(a, lb);
+            // (latency-bound streaming kernels: enough warps to cover the DRAM round trips -- 32 / 64 resident warps per SM)
+            k_big_zero<<<dim3(std::max(1, 16 * nsm / lv.nB), lv.nB), 256, 0, st>>>(a, lb);
             k_big_scatter_A<<<dim3(std::max(1, std::min(nsm, (lv.maxamapB + 255) / 256)), lv.nB), 256, 0, st>>>(a, lb);
             nl += 2;
             for (int c = 0; c < lv.maxchildB; ++c) {
-                k_big_extend_add<<<dim3(std::max(1, std::min(2 * nsm / lv.nB + 1, (lv.maxrB * 32 + 255) / 256)), lv.nB), 256, 0, st>>>(a, lb, c);
+                k_big_extend_add<<<dim3(std::max(1, std::min(8 * nsm / lv.nB + 1, (lv.maxrB * 32 + 255) / 256)), lv.nB), 256, 0, st>>>(a, lb, c);
                 ++nl;
             }
             // the largest fronts one at a time, each with the whole GPU: diagonal blocks / near-diagonal steps of panel k+1 run beside
