@@ -154,6 +154,11 @@ int b2_symbolic_exchange(b2_solver* s, int64_t* cbv_off, int64_t* exch_cb, int64
 int b2_debug_get_factor(b2_solver* s, double* lval_h, double* dvec_h);
 /* test/debug: re-factor one warp-class front `reps` times with clock64() stamps at its 8 phase boundaries */
 int b2_debug_profile_front(b2_solver* s, int32_t sn, int32_t reps, int64_t* stamps_h);
+/* Debug: per-front device timeline of the team-class factor kernels.  With B2_SPARSE_TRACE=1 in the environment at b2_create every
+ * front of order <= 64 stamps %globaltimer (ns) when its team starts, when its children have been assembled and when it has
+ * finished: stamps_h[3 * sn + {0,1,2}].  Also returns the supernode parents and (w, f) of every front.  *count = number of
+ * supernodes; data is copied when capacity >= *count (stamps are zero when tracing is off). */
+int b2_debug_trace(b2_solver* s, uint64_t* stamps_h, int32_t* parent_h, int32_t* w_h, int32_t* f_h, int64_t capacity, int64_t* count);
 
 /* ------------------------------------------------------------------ dense LDL^T */
 typedef struct b2d_solver b2d_solver;

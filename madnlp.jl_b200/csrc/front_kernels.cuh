@@ -39,6 +39,7 @@ struct FactorArgs {
     int32_t* counters;    // [0] = #negative pivots, [1] = #perturbed pivots
     double eps;
     unsigned long long* trace = nullptr;   // debug (B2_DENSE_TRACE): [slot][2] = first entry / last exit of a launch, %globaltimer ns
+    unsigned long long* ftrace = nullptr;  // debug (B2_SPARSE_TRACE): [supernode][3] = team starts / children assembled / front finished
 };
 
 // Timeline stamps of the dense look-ahead schedule (b2d_debug_trace): slot = 8 * block column + kernel kind

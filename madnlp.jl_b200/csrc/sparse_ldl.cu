@@ -78,6 +78,7 @@ struct b2_solver {
     cudaStream_t la_bulk = nullptr, la_side = nullptr;   // side branches of the look-ahead schedule of the largest fronts
     std::vector<cudaEvent_t> ev_pool;
     size_t ev_next = 0;
+    DevBuf<unsigned long long> d_ftrace;                 // B2_SPARSE_TRACE=1: per-front stamps of the team-class factor kernels (b2_debug_trace)
     DevBuf<int32_t> d_tilecnt;                           // dynamic-tile counters, one per 128-column block of every look-ahead front
     bool factorized = false;
     int64_t last_perturbed = 0;
@@ -300,6 +301,7 @@ FactorArgs factor_args(b2_solver* s) {
     a.amap_src = s->d_amap_src.p; a.amap_dst = s->d_amap_dst.p;
     a.A = s->nzval_d; a.L = s->d_L.p; a.Lt = s->d_Lt.p; a.ws = s->d_ws.p; a.dvec = s->d_dvec.p;
     a.counters = s->d_counters.p; a.eps = s->opt.pivot_eps;
+    a.ftrace = s->d_ftrace.p;
     return a;
 }
 SolveArgs solve_args(b2_solver* s) {
@@ -849,6 +851,7 @@ int create_common(int32_t n, int64_t nnz, const int32_t* colptr_h, const int32_t
             }
             B2_CUDA_THROW(s->d_childrec.upload(cr.data(), cr.size()));
         }
+        if (const char* e = getenv("B2_SPARSE_TRACE")) if (atoi(e)) B2_CUDA_THROW(s->d_ftrace.alloc((size_t)3 * ns));
         B2_CUDA_THROW(s->d_L.alloc((size_t)S.lp_off[ns] + 2));          // (+2: the bulk-copy staging may read one aligned pair past a panel)
         B2_CUDA_THROW(s->d_Lt.alloc((size_t)S.lp_off[ns]));
         {
@@ -1185,6 +1188,26 @@ int b2_debug_profile_front(b2_solver* s, int32_t sn, int32_t reps, int64_t* stam
     }
     B2_CUDA(cudaDeviceSynchronize());
     B2_CUDA(cudaMemcpy(stamps_h, prof.p, 8 * reps * sizeof(long long), cudaMemcpyDeviceToHost));
+    return B2_OK;
+}
+
+int b2_debug_trace(b2_solver* s, uint64_t* stamps_h, int32_t* parent_h, int32_t* w_h, int32_t* f_h, int64_t capacity, int64_t* count) {
+    if (!s || !count) { set_error("b2_debug_trace: invalid argument"); return B2_ERR_INVALID; }
+    const int64_t ns = s->S.nsuper;
+    *count = ns;
+    if (capacity < ns) return B2_OK;
+    for (int64_t i = 0; i < ns; ++i) {
+        if (parent_h) parent_h[i] = s->S.sn_parent[i];
+        const int w = s->S.sn_first[i + 1] - s->S.sn_first[i];
+        if (w_h) w_h[i] = w;
+        if (f_h) f_h[i] = (int32_t)(s->S.rows_ptr[i + 1] - s->S.rows_ptr[i]);
+    }
+    if (stamps_h && s->d_ftrace.p) {
+        B2_CUDA(cudaDeviceSynchronize());
+        B2_CUDA(cudaMemcpy(stamps_h, s->d_ftrace.p, s->d_ftrace.bytes(), cudaMemcpyDeviceToHost));
+    } else if (stamps_h) {
+        std::memset(stamps_h, 0, (size_t)3 * ns * sizeof(uint64_t));
+    }
     return B2_OK;
 }
 

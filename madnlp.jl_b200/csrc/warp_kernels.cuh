@@ -187,6 +187,7 @@ __device__ __forceinline__ void front_factor_team(const FactorArgs& a, const Chi
     ChildRec* recs = (ChildRec*)(relst + MAXC * FMAX); // [MAXC]
     double* stage = (double*)(recs + MAXC);            // [STAGE]
     B2_STAMP(0);
+    if (a.ftrace && tid == 0) a.ftrace[3 * (size_t)s] = global_ns();
     const FrontDesc d = a.desc[s];
     const int f = d.f, w = d.w, r = f - w;
     B2_STAMP(1);
@@ -263,6 +264,7 @@ __device__ __forceinline__ void front_factor_team(const FactorArgs& a, const Chi
         c0 += nc;
     }
     B2_STAMP(4);
+    if (a.ftrace && tid == 0) a.ftrace[3 * (size_t)s + 1] = global_ns();
     // row `tid` of the front into registers: a[j] = F(tid, j)
     double av[FMAX + 1];
 #pragma unroll
@@ -344,6 +346,7 @@ __device__ __forceinline__ void front_factor_team(const FactorArgs& a, const Chi
     // barrier's synchronises-with edge -- the CUTLASS semaphore pattern), so no team-wide __threadfence() is needed
     team_sync<NW>(team);
     if (DEP && tid == 0) flag_set(done + s);
+    if (a.ftrace && tid == 0) a.ftrace[3 * (size_t)s + 2] = global_ns();
     B2_STAMP(7);
 }
 
