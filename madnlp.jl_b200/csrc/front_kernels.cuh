@@ -603,8 +603,15 @@ __device__ __forceinline__ void gu_bulk_setup(double* gu_sm) {
 __global__ void __launch_bounds__(GU_NT_BULK, 2) k_big_update_pipe_bulk(FactorArgs a, const int32_t* __restrict__ list, int kb0, int kmax,
                                                                        int jlo_rel, int jhi_rel, int clip_jlo) {
     extern __shared__ __align__(16) double gu_sm[];
-    gu_bulk_setup(gu_sm);
     const FrontDesc d = a.desc[list[blockIdx.z]];
+    {   // CTAs of tiles above the diagonal / outside the front (about half of the rectangular grid) leave before any set-up
+        if (kb0 >= d.w) return;
+        const int kcount = min(kmax, d.w - kb0);
+        const int jlo = kb0 + (clip_jlo ? min(jlo_rel, kcount) : jlo_rel);
+        const int i0 = jlo + blockIdx.x * GU_M, j0 = jlo + blockIdx.y * GU_N;
+        if (j0 > i0 + GU_M - 1 || i0 >= d.f || j0 >= min(d.f, kb0 + jhi_rel)) return;
+    }
+    gu_bulk_setup(gu_sm);
     unsigned it = 0;
     big_update_tile_bulk(a, d, kb0, kmax, jlo_rel, jhi_rel, clip_jlo, blockIdx.x, blockIdx.y, gu_sm, it);
 }

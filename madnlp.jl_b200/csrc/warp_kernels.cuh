@@ -216,34 +216,53 @@ __device__ __forceinline__ void front_factor_team(const FactorArgs& a, const Chi
     B2_STAMP(3);
     // ---- extend-add of the children (ascending id): rounds of <= MAXC children whose update blocks fit the stage;
     //      every block of a round is landed in shared memory by cp.async in ONE memory round trip.
+    // Dependency-driven schedule: the children are still added in ascending id (the summation order is part of the result), but a
+    // round does not wait for all of them -- it waits for the next child and takes along those behind it that have ALREADY finished,
+    // so a parent whose last child is late has staged and added the others by then (the tree's critical path pays one round, not
+    // the whole extend-add: tools/trace_sparse.py).
+    int* nready_sh = relst + FMAX - 1;                 // (row 0 of relst holds at most FMAX - 1 indices: this slot is free)
     for (int c0 = 0; c0 < d.nchild;) {
-        const int nrec = min(MAXC, d.nchild - c0);
-        if (tid < nrec) {
-            recs[tid] = childrec[d.child_off + c0 + tid];
-            if (DEP) flag_wait(done + recs[tid].sn, err);      // child fronts finished (its update block is in L2)
+        const int cb0 = (c0 / MAXC) * MAXC;            // children are fetched in blocks of MAXC records
+        const int ro = c0 - cb0;                       // first record of this round inside the block
+        if (ro == 0) {
+            if (tid < min(MAXC, d.nchild - cb0)) recs[tid] = childrec[d.child_off + cb0 + tid];
+            team_sync<NW>(team);
         }
-        team_sync<NW>(team);
+        int nrec = min(MAXC, d.nchild - cb0) - ro;
+        if (DEP) {
+            if (tid < 32) {
+                if (tid == 0) flag_wait(done + recs[ro].sn, err);          // child front finished (its update block is in L2)
+                __syncwarp();
+                int v = (tid == 0) ? 1 : 0;
+                if (tid > 0 && tid < nrec) asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(done + recs[ro + tid].sn) : "memory");
+                const unsigned m = __ballot_sync(0xffffffffu, v != 0);
+                if (tid == 0) *nready_sh = __ffs(~m) - 1;                  // length of the finished prefix (>= 1)
+            }
+            team_sync<NW>(team);
+            nrec = *nready_sh;
+        }
+        const ChildRec* rrec = recs + ro;
         int nc = 0, tot = 0;
         while (nc < nrec) {
-            const int sz = (recs[nc].rc * recs[nc].rc + 1) & ~1;
+            const int sz = (rrec[nc].rc * rrec[nc].rc + 1) & ~1;
             if (nc > 0 && tot + sz > STAGE) break;
             tot += sz; ++nc;
         }
         int off = 0;
         for (int c = 0; c < nc; ++c) {
-            const int rc = recs[c].rc;
-            const double* CB = a.ws + recs[c].cb_off;          // 16-byte aligned, padded to an even count
+            const int rc = rrec[c].rc;
+            const double* CB = a.ws + rrec[c].cb_off;          // 16-byte aligned, padded to an even count
             const int sz = (rc * rc + 1) & ~1;
             if (DEP) { for (int e = 2 * tid; e < sz; e += 2 * TEAM) cp_async16_cg(stage + off + e, CB + e); }
             else { for (int e = tid; e < rc * rc; e += TEAM) cp_async8(stage + off + e, CB + e); }
-            if (tid < rc) cp_async4(relst + c * FMAX + tid, a.rel + recs[c].rel_off + tid);
+            if (tid < rc) cp_async4(relst + c * FMAX + tid, a.rel + rrec[c].rel_off + tid);
             off += sz;
         }
         cp_async_wait_all();
         team_sync<NW>(team);
         off = 0;
         for (int c = 0; c < nc; ++c) {
-            const int rc = recs[c].rc;
+            const int rc = rrec[c].rc;
             const int* rl = relst + c * FMAX;
             const double* cs = stage + off;
             if (tid < rc) {
