@@ -342,8 +342,21 @@ __device__ __forceinline__ void front_factor_team(const FactorArgs& a, const Chi
         }
     }
     B2_STAMP(5);
+    // update block first (it is all the parent waits for): av[j] holds column w+j of row tid -- registers only, no barrier needed
+    if (tid >= w && tid < f) {
+        double* CBo = a.ws + d.cb_off;
+        const int ir = tid - w;
+#pragma unroll
+        for (int j = 0; j < FMAX; ++j) if (j <= ir) CBo[(size_t)j * r + ir] = av[j];
+    }
+    // hand-off: the team barrier orders every thread's stores before thread 0's st.release.gpu (release is cumulative over the
+    // barrier's synchronises-with edge -- the CUTLASS semaphore pattern), so no team-wide __threadfence() is needed.  The same
+    // barrier completes the pivot loop's writes of the panel columns into F.
     team_sync<NW>(team);
-    // panel: column-major (forward solve, parent-independent) and row-major copy (backward solve)
+    if (DEP && tid == 0) flag_set(done + s);
+    if (a.ftrace && tid == 0) a.ftrace[3 * (size_t)s + 2] = global_ns();
+    B2_STAMP(6);
+    // panel, off the tree's critical path: column-major (forward solve, parent-independent) and row-major copy (backward solve)
     {
         double* Lp = a.L + d.lp_off;
         for (int e = tid; e < f * w; e += TEAM) Lp[e] = F[e];
@@ -353,19 +366,7 @@ __device__ __forceinline__ void front_factor_team(const FactorArgs& a, const Chi
         }
         if (tid < w) a.dvec[d.col0 + tid] = F[tid + tid * f];
     }
-    B2_STAMP(6);
-    // update block: av[j] now holds column w+j of row tid
-    if (tid >= w && tid < f) {
-        double* CBo = a.ws + d.cb_off;
-        const int ir = tid - w;
-#pragma unroll
-        for (int j = 0; j < FMAX; ++j) if (j <= ir) CBo[(size_t)j * r + ir] = av[j];
-    }
-    // hand-off: the team barrier orders every thread's stores before thread 0's st.release.gpu (release is cumulative over the
-    // barrier's synchronises-with edge -- the CUTLASS semaphore pattern), so no team-wide __threadfence() is needed
-    team_sync<NW>(team);
-    if (DEP && tid == 0) flag_set(done + s);
-    if (a.ftrace && tid == 0) a.ftrace[3 * (size_t)s + 2] = global_ns();
+    team_sync<NW>(team);                               // (a team of the staged kernels reuses F for its next front)
     B2_STAMP(7);
 }
 
