@@ -69,7 +69,11 @@ typedef struct b2_options {
     int32_t dep_schedule;    /* bit 0 (factorisation), bit 1 (solves): when every front is team-class (order <= 64) run the sweep
                                 as ONE launch whose CTAs wait on their children's completion flags instead of on
                                 kernel boundaries.  Default 1: measured faster for the factorisation only.     */
-    int32_t reserved[5];
+    int32_t chain_merge_f;   /* > 0: a supernode with exactly ONE child absorbs it whatever the explicit zeros cost, as long as the
+                                merged front stays team-class (order <= min(chain_merge_f, 64)): on latency-bound trees every
+                                level of the critical path costs ~5 us of hand-off besides its pivots, the zeros nothing.
+                                Default 64; 0 = off (also what a zero-filled `reserved` field of older callers means) */
+    int32_t reserved[4];
 } b2_options;
 
 int b2_options_default(b2_options* opt);

@@ -15,6 +15,7 @@ struct AnalysisOptions {
     double relax_zeros = 0.25;
     int n_parts = 1;           // multi-GPU partition count
     int kkt_n_primal = 0;      // augmented-KKT hint: dual rows are ordered after one primal neighbour
+    int chain_merge_f = 0;     // > 0: single-child chains are merged while the front order stays <= this (latency, not flops)
 };
 
 // One front per supernode.  Pivot columns [first, first+w) in the PERMUTED numbering; the front has

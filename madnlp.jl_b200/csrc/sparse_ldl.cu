@@ -759,6 +759,7 @@ int create_common(int32_t n, int64_t nnz, const int32_t* colptr_h, const int32_t
     try {
         AnalysisOptions ao;
         ao.ordering = s->opt.ordering; ao.nemin = s->opt.nemin; ao.relax_zeros = s->opt.relax_zeros;
+        ao.chain_merge_f = s->opt.chain_merge_f;
         ao.n_parts = std::max(1, s->opt.n_parts);
         ao.kkt_n_primal = s->opt.kkt_n_primal;
         analyse(n, colptr_h, rowval_h, ao, user_perm_h, s->S);
@@ -949,6 +950,8 @@ int b2_options_default(b2_options* opt) {
     opt->small_front_max = 160;
     opt->fuse_max_fronts = 8;      // measured optimum on OPF-10k (profiles/r02_sweep.txt)
     opt->dep_schedule = 1;
+    opt->chain_merge_f = 64;
+    if (const char* e = getenv("B2_CHAIN_MERGE_F")) opt->chain_merge_f = atoi(e);
     opt->n_parts = 1;
     opt->part_rank = 0;
     return B2_OK;

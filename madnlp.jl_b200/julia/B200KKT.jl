@@ -32,15 +32,16 @@ Base.@kwdef mutable struct B200Options <: AbstractOptions
     b200_kkt_n_primal::Int32 = 0        # set by the KKT overloads below for SparseKKTSystem
     b200_fuse_max_fronts::Int32 = 8
     b200_dep_schedule::Int32 = 1
+    b200_chain_merge_f::Int32 = 64
 end
 
 struct CB2Options
     ordering::Int32; nemin::Int32; relax_zeros::Float64; pivot_eps::Float64
     use_cuda_graph::Int32; small_front_max::Int32; n_parts::Int32; part_rank::Int32
-    kkt_n_primal::Int32; fuse_max_fronts::Int32; dep_schedule::Int32; reserved::NTuple{5,Int32}
+    kkt_n_primal::Int32; fuse_max_fronts::Int32; dep_schedule::Int32; chain_merge_f::Int32; reserved::NTuple{4,Int32}
 end
 CB2Options(o::B200Options) = CB2Options(o.b200_ordering, o.b200_nemin, o.b200_relax_zeros, o.b200_pivot_eps,
-    o.b200_use_cuda_graph, o.b200_small_front_max, 1, 0, o.b200_kkt_n_primal, o.b200_fuse_max_fronts, o.b200_dep_schedule, ntuple(_ -> Int32(0), 5))
+    o.b200_use_cuda_graph, o.b200_small_front_max, 1, 0, o.b200_kkt_n_primal, o.b200_fuse_max_fronts, o.b200_dep_schedule, o.b200_chain_merge_f, ntuple(_ -> Int32(0), 4))
 
 last_error() = unsafe_string(ccall((:b2_last_error, libb200kkt), Cstring, ()))
 function check(rc::Cint, exc)
