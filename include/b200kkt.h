@@ -72,7 +72,8 @@ typedef struct b2_options {
     int32_t chain_merge_f;   /* > 0: a supernode with exactly ONE child absorbs it whatever the explicit zeros cost, as long as the
                                 merged front stays team-class (order <= min(chain_merge_f, 64)): on latency-bound trees every
                                 level of the critical path costs ~5 us of hand-off besides its pivots, the zeros nothing.
-                                Default 64; 0 = off (also what a zero-filled `reserved` field of older callers means) */
+                                Default 0 = off (measured slower on the OPF trees: the single-child chains sit at the bottom, where the
+                                tree is throughput-bound and bigger leaves hurt); kept as an option for trees with long chains on top */
     int32_t reserved[4];
 } b2_options;
 

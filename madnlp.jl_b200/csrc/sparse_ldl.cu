@@ -950,7 +950,8 @@ int b2_options_default(b2_options* opt) {
     opt->small_front_max = 160;
     opt->fuse_max_fronts = 8;      // measured optimum on OPF-10k (profiles/r02_sweep.txt)
     opt->dep_schedule = 1;
-    opt->chain_merge_f = 64;
+    opt->chain_merge_f = 0;      // measured on the OPF-10k tree: 16 -> 11 levels but the merged (two-warp, 14 us) leaves make the
+                                 // throughput-bound bottom of the tree 30 us longer: factorize 0.145 -> 0.172 ms (profiles/r02_chain_merge.txt)
     if (const char* e = getenv("B2_CHAIN_MERGE_F")) opt->chain_merge_f = atoi(e);
     opt->n_parts = 1;
     opt->part_rank = 0;

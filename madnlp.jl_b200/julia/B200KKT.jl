@@ -32,7 +32,7 @@ Base.@kwdef mutable struct B200Options <: AbstractOptions
     b200_kkt_n_primal::Int32 = 0        # set by the KKT overloads below for SparseKKTSystem
     b200_fuse_max_fronts::Int32 = 8
     b200_dep_schedule::Int32 = 1
-    b200_chain_merge_f::Int32 = 64
+    b200_chain_merge_f::Int32 = 0
 end
 
 struct CB2Options
