@@ -69,10 +69,12 @@ if __name__ == "__main__":
         if os.path.exists(os.path.join(G, src)):
             launch_summary(os.path.join(G, src), os.path.join(P, dst), title)
     for src, dst, title in [("r02_prof_factor_dep.ncu-rep", "r02_prof_factor_dep_summary.txt", "k_factor_dep (numeric LDL^T of the OPF-10k tree in one launch)"),
+                            ("r02_prof_update_bulk.ncu-rep", "r02_prof_update_bulk_summary.txt", "k_big_update_dyn_bulk (trailing update of the dense LDL^T, TMA bulk-copy staging + mbarrier ring + producer warp), N=4096"),
                             ("r02_prof_ozaki.ncu-rep", "r02_prof_ozaki_summary.txt", "ozk::k_ozaki_syrk v2 (tcgen05 int8 digits + TMA), K=2048 n=4096"),
                             ("r02_prof_dense_solve.ncu-rep", "r02_prof_dense_solve_summary.txt", "k_dense_solve_flow (dense triangular solves, one launch), N=4096")]:
         if os.path.exists(os.path.join(G, src)):
             rep_summary(os.path.join(G, src), os.path.join(P, dst), title)
-    for f in ("r02_step_timeline.txt", "r02_profile_front.txt", "r02_c5md.json"):
+    for f in ("r02_step_timeline.txt", "r02_profile_front.txt", "r02_c5md.json", "r02_sparse_timeline.txt", "r02_dense_timeline.txt", "r02_bench_1gpu.json",
+              "r02_bench_reference.json"):
         if os.path.exists(os.path.join(G, f)):
             open(os.path.join(P, f), "w").write(open(os.path.join(G, f)).read())
