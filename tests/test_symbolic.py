@@ -69,6 +69,25 @@ def test_condensed_opf_300_and_negative_pivots():
     assert S.stats["nnz_l"] >= len(rv) and S.stats["n_levels"] == S.n_levels
 
 
+@pytest.mark.parametrize("chain_merge_f", [32, 64])
+def test_only_children_are_absorbed_when_the_latency_rule_is_on(chain_merge_f):
+    """b2_options.chain_merge_f: a supernode with exactly one child absorbs it while the merged front order stays <= chain_merge_f
+    (<= 64), whatever the explicit zeros -- fewer tree levels; the numeric replay must still reproduce the dense solution, and no
+    chain link may be left that the rule could still merge."""
+    n, cp, rv = _condensed_pattern("case300_synth")
+    rng = np.random.default_rng(chain_merge_f)
+    nz = _well_conditioned_values(cp, rv, n, rng)
+    S0 = _check(n, cp, rv, nz, 0, chain_merge_f=0)
+    S1 = _check(n, cp, rv, nz, 0, chain_merge_f=chain_merge_f)
+    assert S1.ns < S0.ns and S1.sn_level.max() <= S0.sn_level.max()
+    nchild = np.bincount(S1.sn_parent[S1.sn_parent >= 0], minlength=S1.ns)
+    f1 = np.diff(S1.rows_ptr); w1 = np.diff(S1.sn_first)
+    for s_ in range(S1.ns):
+        p_ = S1.sn_parent[s_]
+        if p_ >= 0 and nchild[p_] == 1:
+            assert w1[s_] + f1[p_] > min(chain_merge_f, 64)    # (an only child with w_child + f_parent <= bound would have been absorbed)
+
+
 def test_augmented_kkt_pattern_quasi_definite():
     """SparseKKTSystem-style [[H+S, J'],[J, -dI]] (config 5 generator, small): inertia must be (n_tot, 0, m)."""
     N, n_tot, m, I, J, V = W.augmented_grid_kkt(5, 4, 6)
