@@ -108,7 +108,21 @@ class ClockSampler:
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
         def run():
-            while not self._stop.is_set():
+            # one nvidia-smi process in loop mode (a sample every 20 ms: the timed region is ~0.7 s); if that does not produce
+            # lines (old driver), fall back to one process per sample
+            try:
+                self._proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index), "-lms", "20"],
+                                              stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                for line in self._proc.stdout:
+                    if self._stop.is_set():
+                        break
+                    line = line.strip()
+                    if line:
+                        self.rows.append([x.strip() for x in line.split(",")])
+            except Exception:
+                pass
+            looped = bool(self.rows)
+            while not self._stop.is_set() and not looped:
                 try:
                     out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
                                          capture_output=True, text=True, timeout=5).stdout.strip()
@@ -117,11 +131,17 @@ class ClockSampler:
                 except Exception:
                     pass
                 self._stop.wait(0.02)
+        self._proc = None
         self._t = threading.Thread(target=run, daemon=True)
         self._t.start()
 
     def stop(self):
         self._stop.set()
+        if getattr(self, "_proc", None) is not None:
+            try:
+                self._proc.terminate()
+            except Exception:
+                pass
         if self._t:
             self._t.join(timeout=6)
         sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
