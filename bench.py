@@ -347,10 +347,10 @@ def run_b200(args, rank, world, local_rank):
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         slot = pipe.prefetch(host[first % N_ITERATES])
+        if not args.no_flush:
+            flush_buf.fill_(1.0)                          # (inside the timed region here)
         for j in range(count):
             i = first + j
-            if not args.no_flush:
-                flush_buf.fill_(1.0)                      # (inside the timed region here)
             pipe.load(slot)
             nxt = [None]
             if j + 1 < count:
@@ -361,6 +361,8 @@ def run_b200(args, rank, world, local_rank):
                 queue_next = None
             ok = la.step(mu=its[i % N_ITERATES].mu, after_prologue=queue_next)
             assert ok
+            if not args.no_flush and j + 1 < count:
+                flush_buf.fill_(1.0)                      # L2 flush between steps, queued first so that it runs under the host's hand-over work
             pipe.push_result()
             slot = nxt[0]
         pipe.drain()
