@@ -215,6 +215,32 @@ def test_condensed_opf_step_direction_and_inertia(case, seed):
         assert res < 1e-12
 
 
+@pytest.mark.parametrize("dep_schedule,chain_merge_f", [(3, 0), (1, 48), (0, 0)])
+def test_schedule_and_amalgamation_options_give_the_same_answers(dep_schedule, chain_merge_f):
+    """b2_options.dep_schedule (bit 0: single-launch factorisation, bit 1: single-launch flag-driven sweeps; 0: level launches) and
+    chain_merge_f (only children absorbed while the front stays team-class) change the schedule / the supernode partition, never the
+    mathematics: same inertia as the oracle, refined direction within 1e-6, single-solve residual within fp64 backward stability."""
+    _need_gpu()
+    from madnlp_jl_b200 import kkt as K
+    model, st = W.acopf_case("case300_synth")
+    cb = _cb(st)
+    it = W.ipm_iterates(model, st, 1, seed=5)[0]
+    kc = o.SparseCondensedKKTSystem(cb, o.DenseLDLInertiaSolver)
+    opt = pkg.capi.default_options(dep_schedule=dep_schedule, chain_merge_f=chain_merge_f)
+    kg = K.create_kkt_system(K.SparseCondensedKKTSystem, cb, None, opt)
+    _load(kg, kc, it)
+    kc.linear_solver.factorize(); kg.linear_solver.factorize()
+    assert kg.linear_solver.inertia() == kc.linear_solver.inertia()
+    dc, okc, rc = _refined_direction_cpu(kc, it.rhs)
+    dg, okg, rg = _refined_direction_gpu(kg, it.rhs)
+    assert okc and okg and rg < 1e-8
+    assert np.abs(dg - dc).max() / np.abs(dc).max() <= 1e-6
+    b = np.random.default_rng(11).standard_normal(kg.n)
+    xg = kg.linear_solver.solve_linear_system(_dev(b)).cpu().numpy()
+    Kfull = o.tril_to_full(kc.aug_colptr, kc.aug_rowval, kc.aug_nz, kc.n)
+    assert np.abs(Kfull @ xg - b).max() / (abs(Kfull).max() * np.abs(xg).max() + np.abs(b).max()) < 1e-12
+
+
 def test_negative_curvature_is_counted():
     """A10: an indefinite condensed matrix must report the same (pos, zero, neg) as the oracle and fail is_inertia_correct."""
     _need_gpu()
