@@ -68,7 +68,9 @@ typedef struct b2_options {
                                 CTA of a single launch (0 = plain level-by-level schedule)                      */
     int32_t dep_schedule;    /* bit 0 (factorisation), bit 1 (solves): when every front is team-class (order <= 64) run the sweep
                                 as ONE launch whose CTAs wait on their children's completion flags instead of on
-                                kernel boundaries.  Default 1: measured faster for the factorisation only.     */
+                                kernel boundaries.  Default 1: measured faster for the factorisation only.
+                                bit 2 (hybrid sweeps): the fused bottom subtrees keep their staged kernel, every front above
+                                them runs in one flag-driven launch (instead of one launch per level)          */
     int32_t chain_merge_f;   /* > 0: a supernode with exactly ONE child absorbs it whatever the explicit zeros cost, as long as the
                                 merged front stays team-class (order <= min(chain_merge_f, 64)): on latency-bound trees every
                                 level of the critical path costs ~5 us of hand-off besides its pivots, the zeros nothing.

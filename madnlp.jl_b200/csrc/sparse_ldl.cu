@@ -43,6 +43,9 @@ struct Phase {
     // single-launch dependency-driven schedule (used instead of fused + levels when every front is team-class)
     int offAllC = 0, nAllC = 0, maxwAllC = 0;       // every M/B front of the phase (diagonal-block inversion)
     int dep_ngroup = 0, dep_type_off = 0, dep_ptr_off = 0, dep_tasks_off = 0, dep_maxf1 = 0, dep_maxf2 = 0;
+    // hybrid sweeps (dep_schedule bit 2): the fused bottom subtrees by their staged kernel, every front above them as ONE flag-driven
+    // launch (groups in level order of the upper tree); flags of the fused fronts are preset from d_flags_tpl
+    int dep2_ngroup = 0, dep2_type_off = 0, dep2_ptr_off = 0, dep2_tasks_off = 0;
     cudaGraphExec_t g_factor = nullptr, g_fwd = nullptr, g_bwd = nullptr;
     int64_t n_factor_launches = 0, n_solve_launches = 0;
     int64_t n_fused_fronts = 0;
@@ -70,6 +73,7 @@ struct b2_solver {
     DevBuf<double> d_Linv, d_side;
     DevBuf<int64_t> d_linv_off;
     DevBuf<int32_t> d_flags, d_parent;   // dependency flags [3][nsuper], supernode parents
+    DevBuf<int32_t> d_flags_tpl;         // [nsuper] 1 for fronts of the fused bottom subtrees (hybrid sweeps), else 0
     int32_t* h_counters = nullptr;   // pinned
     std::vector<int64_t> cbv_off;
     int64_t exch_cbv = 0;
@@ -446,6 +450,24 @@ int64_t enqueue_solve(b2_solver* s, int ph, bool forward, cudaStream_t st) {
         else k_bwd_dep<<<P.dep_ngroup, 128, smd, st>>>(a, ds, s->d_parent.p, flags, s->d_counters.p + 4, ticket);
         return 2;
     }
+    if (P.dep2_ngroup && (s->opt.dep_schedule & 4)) {
+        // hybrid: the bottom subtrees in their fused staged kernel, everything above them in one flag-driven launch
+        DepSched ds;
+        ds.grp_type = sched + P.dep2_type_off; ds.grp_ptr = sched + P.dep2_ptr_off; ds.tasks = sched + P.dep2_tasks_off; ds.ngroup = P.dep2_ngroup;
+        int* flags = s->d_flags.p + (size_t)(forward ? 1 : 2) * s->S.nsuper;
+        int* ticket = s->d_flags.p + (size_t)3 * s->S.nsuper;
+        const size_t smd = sizeof(double) * std::max<size_t>((size_t)4 * SolveSmem<1>::doubles, (size_t)SolveSmem<2>::doubles);
+        if (forward) {
+            if (P.fused.n_cta) warp_launch(P.fused, true);
+            cudaMemcpyAsync(flags, s->d_flags_tpl.p, (size_t)s->S.nsuper * sizeof(int32_t), cudaMemcpyDeviceToDevice, st);   // fused fronts: done
+            k_fwd_dep<<<P.dep2_ngroup, 128, smd, st>>>(a, s->d_childrec.p, ds, flags, s->d_counters.p + 4, ticket);
+        } else {
+            cudaMemsetAsync(flags, 0, (size_t)s->S.nsuper * sizeof(int32_t), st);
+            k_bwd_dep<<<P.dep2_ngroup, 128, smd, st>>>(a, ds, s->d_parent.p, flags, s->d_counters.p + 4, ticket);
+            if (P.fused.n_cta) warp_launch(P.fused, true);
+        }
+        return nl + 2;
+    }
     if (forward && P.fused.n_cta) warp_launch(P.fused, true);
     if (!forward && P.topfused.n_cta) warp_launch(P.topfused);
     const int nlev = (int)P.lev.size();
@@ -664,6 +686,40 @@ void build_schedule(b2_solver* s) {
         P.maxwAllC = 0;
         std::vector<std::vector<int32_t>> by_level(nul);
         for (int sn = 0; sn < ns; ++sn) if (ulev[sn] >= 0) by_level[ulev[sn]].push_back(sn);
+        // ---- hybrid sweeps: one flag-driven launch for the whole upper tree (only when all of it is team-class and unsharded)
+        P.dep2_ngroup = 0;
+        if ((s->opt.dep_schedule & 4) && s->opt.n_parts <= 1 && wmax > 32 && ph == 0) {
+            bool all_team = nul > 0;
+            for (int l = 0; l < nul && all_team; ++l)
+                for (int sn : by_level[l]) { int w, f; fdim(sn, w, f); if (f > wmax) { all_team = false; break; } }
+            if (all_team) {
+                std::vector<int32_t> order;
+                for (int l = 0; l < nul; ++l) order.insert(order.end(), by_level[l].begin(), by_level[l].end());
+                std::vector<int32_t> gtype, gptr(1, 0), tasks;
+                size_t k = 0;
+                while (k < order.size()) {
+                    int w, f; fdim(order[k], w, f);
+                    if (f > 32) { gtype.push_back(2); tasks.push_back(order[k]); ++k; }
+                    else {
+                        gtype.push_back(1);
+                        int c = 0;
+                        while (k < order.size() && c < FW_WARPS) {
+                            int w2, f2; fdim(order[k], w2, f2);
+                            if (f2 > 32) break;
+                            tasks.push_back(order[k]); ++k; ++c;
+                        }
+                    }
+                    gptr.push_back((int32_t)tasks.size());
+                }
+                P.dep2_ngroup = (int)gtype.size();
+                P.dep2_type_off = (int)sched.size(); sched.insert(sched.end(), gtype.begin(), gtype.end());
+                P.dep2_ptr_off = (int)sched.size(); sched.insert(sched.end(), gptr.begin(), gptr.end());
+                P.dep2_tasks_off = (int)sched.size(); sched.insert(sched.end(), tasks.begin(), tasks.end());
+                std::vector<int32_t> tpl(ns, 0);
+                for (int sn = 0; sn < ns; ++sn) if (mine[sn] && root_of[sn] >= 0) tpl[sn] = 1;
+                B2_CUDA_THROW(s->d_flags_tpl.upload(tpl.data(), tpl.size()));
+            }
+        }
         // ---- the top of the tree: trailing levels that hold at most 4 team-class fronts each are chained inside ONE CTA
         //      (stage = level): a launch boundary per level would cost more than the fronts themselves.
         P.topfused = WarpLaunch();
@@ -950,6 +1006,7 @@ int b2_options_default(b2_options* opt) {
     opt->small_front_max = 160;
     opt->fuse_max_fronts = 8;      // measured optimum on OPF-10k (profiles/r02_sweep.txt)
     opt->dep_schedule = 1;
+    if (const char* e = getenv("B2_DEP_SCHEDULE")) opt->dep_schedule = atoi(e);
     opt->chain_merge_f = 0;      // measured on the OPF-10k tree: 16 -> 11 levels but the merged (two-warp, 14 us) leaves make the
                                  // throughput-bound bottom of the tree 30 us longer: factorize 0.145 -> 0.172 ms (profiles/r02_chain_merge.txt)
     if (const char* e = getenv("B2_CHAIN_MERGE_F")) opt->chain_merge_f = atoi(e);

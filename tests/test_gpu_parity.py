@@ -215,9 +215,10 @@ def test_condensed_opf_step_direction_and_inertia(case, seed):
         assert res < 1e-12
 
 
-@pytest.mark.parametrize("dep_schedule,chain_merge_f", [(3, 0), (1, 48), (0, 0)])
+@pytest.mark.parametrize("dep_schedule,chain_merge_f", [(3, 0), (5, 0), (1, 48), (0, 0)])
 def test_schedule_and_amalgamation_options_give_the_same_answers(dep_schedule, chain_merge_f):
-    """b2_options.dep_schedule (bit 0: single-launch factorisation, bit 1: single-launch flag-driven sweeps; 0: level launches) and
+    """b2_options.dep_schedule (bit 0: single-launch factorisation, bit 1: single-launch flag-driven sweeps, bit 2: hybrid sweeps --
+    fused bottom subtrees + one flag-driven launch for the tree above them; 0: level launches) and
     chain_merge_f (only children absorbed while the front stays team-class) change the schedule / the supernode partition, never the
     mathematics: same inertia as the oracle, refined direction within 1e-6, single-solve residual within fp64 backward stability."""
     _need_gpu()
