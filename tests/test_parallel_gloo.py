@@ -72,7 +72,7 @@ def _worker(rank, world, port, q):
 
 
 @pytest.mark.timeout(300)
-@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("world", [2, 4, 8])
 def test_sharded_protocol_with_gloo(world):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
