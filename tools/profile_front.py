@@ -20,7 +20,7 @@ S=Symbolic(kg.n,kg.aug_com.colptr,kg.aug_com.rowval)
 ws=S.sn_first[1:]-S.sn_first[:-1]; fs=(S.rows_ptr[1:]-S.rows_ptr[:-1]).astype(int)
 ch=S.children()
 order=np.argsort(-(ws*fs))[:6]
-names=["desc","zero","A","children","pivots","schur","store"]
+names=["desc","zero","A","children","pivots","update-block+hand-off","panel-store"]
 for sn in list(order)+[int(np.argmax(S.sn_level))]:
     reps=4; st_=np.zeros(8*reps,dtype=np.int64)
     capi.check(lib.b2_debug_profile_front(kg.linear_solver._h,int(sn),reps,st_.ctypes.data))
